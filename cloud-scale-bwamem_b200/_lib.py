@@ -1,0 +1,82 @@
+"""ctypes binding of libcsbwa_sw.so (include/csbwa_sw.h).  No CPU fallback: compute entry
+points raise CsbwaError when the library reports an error (e.g. no CUDA device)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK, E_NODEVICE, E_BADARG, E_BADWIRE, E_SHORTOUT, E_CUDA, E_NOMEM, E_SCRATCH = 0, -1, -2, -3, -4, -5, -6, -7
+
+JOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"),
+                      ("xtra", "<i4"), ("pad", "<i4")])
+
+EXPORTS = [
+    "csbwa_init", "csbwa_shutdown", "csbwa_device_count", "csbwa_strerror", "csbwa_last_error", "csbwa_version",
+    "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
+    "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
+    "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("ext_calls", "ext_tasks", "ext_cells", "ext_in_bytes", "ext_out_bytes",
+                                         "aln_calls", "aln_jobs", "aln_cells", "aln_in_bytes", "aln_out_bytes",
+                                         "kernel_launches")] + \
+               [(n, C.c_double) for n in ("h2d_ms", "kernel_ms", "d2h_ms", "host_ms")]
+
+
+class CsbwaError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("csbwa error %d: %s" % (code, detail))
+
+
+_lib = None
+
+
+def lib():
+    """Load (building first if stale) the native library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError("libcsbwa_sw.so missing: the CUDA extension is required, there is no fallback")
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.csbwa_init.argtypes = [C.c_int]; L.csbwa_init.restype = C.c_int
+    L.csbwa_shutdown.restype = C.c_int
+    L.csbwa_device_count.restype = C.c_int
+    L.csbwa_strerror.argtypes = [C.c_int]; L.csbwa_strerror.restype = C.c_char_p
+    L.csbwa_last_error.restype = C.c_char_p
+    L.csbwa_version.restype = C.c_char_p
+    L.csbwa_get_stats.argtypes = [C.POINTER(Stats)]
+    L.csbwa_extend_batch.argtypes = [vp, i32, vp, i32, C.c_int]; L.csbwa_extend_batch.restype = C.c_int
+    L.csbwa_align2_batch.argtypes = [vp, i32, vp, i64, vp, C.c_int]; L.csbwa_align2_batch.restype = C.c_int
+    L.csbwa_extend_scratch_bytes.argtypes = [i32, i64]; L.csbwa_extend_scratch_bytes.restype = i64
+    L.csbwa_extend_batch_device.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp]; L.csbwa_extend_batch_device.restype = C.c_int
+    L.csbwa_align2_scratch_bytes.argtypes = [i32, i64, i64]; L.csbwa_align2_scratch_bytes.restype = i64
+    L.csbwa_align2_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp]; L.csbwa_align2_batch_device.restype = C.c_int
+    L.csbwa_extend_launches_per_call.restype = C.c_int
+    L.csbwa_align2_launches_per_call.restype = C.c_int
+    L.csbwa_pack_ext_bytes.argtypes = [i32, vp]; L.csbwa_pack_ext_bytes.restype = i64
+    L.csbwa_pack_ext_tasks.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64]; L.csbwa_pack_ext_tasks.restype = i64
+    L.csbwa_pack_ext_from_seeds.argtypes = [i32, vp, i32, vp, i64, vp, vp, vp, i64]; L.csbwa_pack_ext_from_seeds.restype = i64
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        L = lib()
+        raise CsbwaError(rc, "%s (%s)" % (L.csbwa_strerror(rc).decode(), L.csbwa_last_error().decode()))
+    return rc
+
+
+def stats():
+    s = Stats()
+    check(lib().csbwa_get_stats(C.byref(s)))
+    return {k: getattr(s, k) for k, _ in Stats._fields_}

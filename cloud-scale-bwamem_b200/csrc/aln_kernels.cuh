@@ -1,0 +1,275 @@
+// aln_kernels.cuh -- device orchestration of one batched mate-SW call (seam 2).
+//
+//   k_aln_classify : job -> size class by query length, per-class job lists (atomic append)
+//   k_aln_warp<C>  : one warp per job, 32-stage systolic SWAlign2 (forward + reverse pass),
+//                    C = query columns per lane (2/4/5/8 -> qlen <= 64/128/160/256)
+//   k_aln_generic  : one thread per job for anything else (qlen > 256, empty inputs, ...)
+// Warps pull jobs from a per-class atomic cursor; b-arrays live in a bump-allocated slice of
+// the caller's scratch.
+#pragma once
+#include <cuda_runtime.h>
+#include "aln_core.cuh"
+
+namespace csw {
+
+constexpr int ALN_NCLS = 5;   // 0: generic, 1: C=8, 2: C=5, 3: C=4, 4: C=2
+struct AlnJob { long long q_off, t_off; int q_len, t_len, xtra, pad; };
+
+struct AlnHdr {
+    SwOpt opt;
+    int32_t n_jobs;
+    int32_t err;
+    uint32_t count[ALN_NCLS];
+    uint32_t work[ALN_NCLS];
+    unsigned long long bump;        // bytes used of the dynamic region
+    unsigned long long dyn_bytes;   // capacity of the dynamic region
+};
+
+struct AlnScratch {
+    AlnHdr *hdr;
+    uint32_t *list[ALN_NCLS];
+    char *dyn;
+};
+__host__ __device__ inline size_t aln_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t aln_scratch_fixed(int n)
+{
+    return aln_align256(sizeof(AlnHdr)) + ALN_NCLS * aln_align256((size_t)n * 4);
+}
+// dynamic need of one job: b-array (2 ints per possible entry) + generic H/E rows
+__host__ __device__ inline size_t aln_job_dyn(int qlen, int tlen, bool generic)
+{
+    size_t b = ((size_t)(tlen > 0 ? tlen : 0) / 2 + 2) * 8;
+    if (generic) b += ((size_t)(qlen > 0 ? qlen : 0) + 2) * 8;
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline AlnScratch aln_carve(void *p, int n)
+{
+    AlnScratch s;
+    char *c = (char *)p;
+    s.hdr = (AlnHdr *)c; c += aln_align256(sizeof(AlnHdr));
+    for (int k = 0; k < ALN_NCLS; ++k) { s.list[k] = (uint32_t *)c; c += aln_align256((size_t)n * 4); }
+    s.dyn = c;
+    return s;
+}
+
+CSW_HD int aln_class_of(const SwOpt &o, int qlen, int tlen)
+{
+    if (!aln_fast_eligible(o, qlen, tlen, 8)) return 0;
+    if (qlen > 160) return 1;
+    if (qlen > 128) return 2;
+    if (qlen > 64) return 3;
+    return 4;
+}
+
+__global__ void k_aln_classify(const AlnJob *__restrict__ jobs, int n, AlnScratch sc, unsigned long long dyn_bytes)
+{
+    __shared__ SwOpt sopt;
+    if (threadIdx.x == 0) {
+        fill_default_opt(sopt);
+        finish_opt(sopt);
+        if (blockIdx.x == 0) { sc.hdr->opt = sopt; sc.hdr->n_jobs = n; sc.hdr->dyn_bytes = dyn_bytes; }
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int cls = aln_class_of(sopt, jobs[k].q_len, jobs[k].t_len);
+    // warp-aggregated append
+    const unsigned act = __activemask();
+    const unsigned same = __match_any_sync(act, cls);
+    const int leader = __ffs(same) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&sc.hdr->count[cls], (uint32_t)__popc(same));
+    base = __shfl_sync(same, base, leader);
+    sc.list[cls][base + __popc(same & ((1u << lane) - 1))] = (uint32_t)k;
+}
+
+__device__ __forceinline__ char *aln_bump(AlnHdr *hdr, char *dyn, size_t bytes)
+{
+    unsigned long long off = atomicAdd(&hdr->bump, (unsigned long long)bytes);
+    if (off + bytes > hdr->dyn_bytes) { atomicExch(&hdr->err, -7); return nullptr; }
+    return dyn + off;
+}
+
+// ---- one systolic pass over the target ------------------------------------------------
+// Returns (warp-uniform) the bookkeeping of the lane that owns the last query column.
+template <int C>
+__device__ __forceinline__ void aln_warp_pass(const SwOpt &o, const uint8_t *__restrict__ q,
+                                              const uint8_t *__restrict__ t, int qn, int tlen,
+                                              bool rev, int qe, int te, int xtra,
+                                              int *bsc, int *bte, AlnBook &bk_out, int &rows_done)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int LQ = (qn - 1) / C;
+    AlnLane<C> L;
+    L.setup(o, q, qn, rev, qe, lane);
+    AlnBook bk;
+    bk.init(o, xtra);
+    int rows = 0;
+    AlnMsg out;
+    out.h = 0; out.ft = 0; out.key = 0;
+    // target bases: one 32-row chunk per lane register, next chunk prefetched
+    int tcur = 0, tnext = 0;
+    if (lane < tlen) tcur = t[aln_tidx(rev, te, lane)];
+    if (32 + lane < tlen) tnext = t[aln_tidx(rev, te, 32 + lane)];
+    const int nsteps = tlen + LQ;
+    for (int s = 0; s < nsteps; ++s) {
+        if ((s & 31) == 0 && s > 0) {
+            tcur = tnext;
+            const int nx = s + 32 + lane;
+            tnext = nx < tlen ? t[aln_tidx(rev, te, nx)] : 0;
+        }
+        int t0 = __shfl_sync(FULL, tcur, s & 31);
+        if (t0 > 4) t0 = 4;
+        AlnMsg in;
+        in.h = __shfl_up_sync(FULL, out.h, 1);
+        in.ft = __shfl_up_sync(FULL, out.ft, 1);
+        in.key = __shfl_up_sync(FULL, out.key, 1);
+        if (lane == 0) { in.h = 0; in.ft = t0 << 16; in.key = 0; }
+        const int row = s - lane;
+        if (row >= 0 && row < tlen && lane <= LQ) {
+            L.step(o, in, out);
+            if (lane == LQ) {
+                int m, mj;
+                aln_decode_key(out.key, m, mj);
+                bk.row(row, m, mj, bsc, bte);
+                rows = row + 1;
+            }
+        }
+        if (__any_sync(FULL, bk.stop)) break;
+    }
+    // broadcast the owner's bookkeeping
+    bk_out.best = __shfl_sync(FULL, bk.best, LQ);
+    bk_out.best_i = __shfl_sync(FULL, bk.best_i, LQ);
+    bk_out.best_j = __shfl_sync(FULL, bk.best_j, LQ);
+    bk_out.nb = __shfl_sync(FULL, bk.nb, LQ);
+    bk_out.min_sc = bk.min_sc; bk_out.end_sc = bk.end_sc; bk_out.sat = bk.sat;
+    bk_out.stop = false; bk_out.last_te = 0; bk_out.last_sc = 0;
+    rows_done = __shfl_sync(FULL, rows, LQ);
+    __syncwarp();
+}
+
+// second best over the b-array, all lanes (S/util/SWUtil.scala:552-566: first strictly greater)
+__device__ __forceinline__ void aln_second_best_warp(const SwOpt &o, int nb, const int *bsc, const int *bte, AlnRes &r)
+{
+    if (r.score == 255 || nb <= 0) return;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int tmp = (r.score + o.a - 1) / o.a;
+    const int low = r.te - tmp, high = r.te + tmp;
+    long long bestk = -1;   // score << 32 | (0x7fffffff - k)
+    for (int k = lane; k < nb; k += 32) {
+        const int e = bte[k], sc = bsc[k];
+        if (e < low || e > high) {
+            const long long key = ((long long)sc << 32) | (long long)(0x7fffffff - k);
+            if (key > bestk) bestk = key;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const long long other = __shfl_xor_sync(FULL, bestk, d);
+        if (other > bestk) bestk = other;
+    }
+    if (bestk >= 0) {
+        const int sc = (int)(bestk >> 32);
+        const int k = 0x7fffffff - (int)(bestk & 0xffffffffLL);
+        if (sc > r.score2) { r.score2 = sc; r.te2 = bte[k]; }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(128)
+k_aln_warp(const AlnJob *__restrict__ jobs, const uint8_t *__restrict__ seqs, AlnScratch sc,
+           int32_t *__restrict__ out, unsigned long long *cells_acc, int cls)
+{
+    const unsigned FULL = 0xffffffffu;
+    const SwOpt &o = sc.hdr->opt;
+    const int lane = threadIdx.x & 31;
+    const uint32_t njobs = sc.hdr->count[cls];
+    unsigned long long my_cells = 0;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&sc.hdr->work[cls], 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= njobs) break;
+        const int k = (int)sc.list[cls][w];
+        const AlnJob jb = jobs[k];
+        const uint8_t *q = seqs + jb.q_off;
+        const uint8_t *t = seqs + jb.t_off;
+        unsigned long long bp = 0;
+        if (lane == 0) bp = (unsigned long long)aln_bump(sc.hdr, sc.dyn, aln_job_dyn(jb.q_len, jb.t_len, false));
+        bp = __shfl_sync(FULL, bp, 0);
+        int32_t *o7 = out + (size_t)7 * k;
+        if (bp == 0) {
+            if (lane < 7) o7[lane] = 0;
+            continue;
+        }
+        int *bsc = (int *)bp;
+        int *bte = bsc + (jb.t_len / 2 + 2);
+        AlnBook bk;
+        int rows = 0;
+        aln_warp_pass<C>(o, q, t, jb.q_len, jb.t_len, false, 0, 0, jb.xtra, bsc, bte, bk, rows);
+        AlnRes r;
+        aln_finish_head(bk, r);
+        aln_second_best_warp(o, bk.nb, bsc, bte, r);
+        unsigned long long cells = (unsigned long long)jb.q_len * (unsigned)rows;
+        const int xtra = jb.xtra;
+        if (!((xtra & XSTART) == 0 || ((xtra & XSUBO) && r.score < (xtra & 0xffff)))) {
+            AlnRes rr;
+            const int qn2 = r.qe + 1;
+            if (qn2 >= 1) {
+                AlnBook bk2;
+                int rows2 = 0;
+                aln_warp_pass<C>(o, q, t, qn2, jb.t_len, true, r.qe, r.te, XSTOP | r.score, bsc, bte, bk2, rows2);
+                aln_finish_head(bk2, rr);
+                cells += (unsigned long long)qn2 * (unsigned)rows2;
+            } else {
+                // zero query columns: every row has m = 0 (S/util/SWUtil.scala:469-542 with qLen = 0)
+                AlnBook bk2;
+                bk2.init(o, XSTOP | r.score);
+                for (int i = 0; i < jb.t_len && !bk2.stop; ++i) {
+                    if (0 > bk2.best) { bk2.best = 0; bk2.best_i = i; bk2.best_j = -1;
+                                        if (0 >= bk2.end_sc || 0 >= bk2.sat) bk2.stop = true; }
+                    else break;   // nothing can change after the first row
+                }
+                aln_finish_head(bk2, rr);
+            }
+            if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+        }
+        if (lane == 0) {
+            o7[0] = r.score; o7[1] = r.te; o7[2] = r.qe; o7[3] = r.score2; o7[4] = r.te2; o7[5] = r.tb; o7[6] = r.qb;
+            my_cells += cells;
+        }
+        __syncwarp();
+    }
+    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
+}
+
+__global__ void __launch_bounds__(128)
+k_aln_generic(const AlnJob *__restrict__ jobs, const uint8_t *__restrict__ seqs, AlnScratch sc,
+              int32_t *__restrict__ out, unsigned long long *cells_acc)
+{
+    const SwOpt &o = sc.hdr->opt;
+    const uint32_t njobs = sc.hdr->count[0];
+    unsigned long long my_cells = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < njobs; w += gridDim.x * blockDim.x) {
+        const int k = (int)sc.list[0][w];
+        const AlnJob jb = jobs[k];
+        int32_t *o7 = out + (size_t)7 * k;
+        const int qn = jb.q_len > 0 ? jb.q_len : 0, tn = jb.t_len > 0 ? jb.t_len : 0;
+        char *bp = aln_bump(sc.hdr, sc.dyn, aln_job_dyn(qn, tn, true));
+        if (!bp) { for (int i = 0; i < 7; ++i) o7[i] = 0; continue; }
+        int *bsc = (int *)bp;
+        int *bte = bsc + (tn / 2 + 2);
+        int *H = bte + (tn / 2 + 2);
+        int *E = H + (qn + 2);
+        AlnRes r;
+        my_cells += (unsigned long long)sw_align2_generic(o, seqs + jb.q_off, qn, seqs + jb.t_off, tn, jb.xtra,
+                                                          H, E, bsc, bte, r);
+        o7[0] = r.score; o7[1] = r.te; o7[2] = r.qe; o7[3] = r.score2; o7[4] = r.te2; o7[5] = r.tb; o7[6] = r.qb;
+    }
+    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
+}
+
+} // namespace csw

@@ -1,0 +1,633 @@
+// csbwa_api.cu -- C ABI of libcsbwa_sw.so (see include/csbwa_sw.h for the contract and the
+// reference interfaces each entry point replaces).
+//
+// Host-buffer entry points (csbwa_extend_batch / csbwa_align2_batch) take a per-GPU context
+// from a pool: one CUDA stream, pinned staging buffers and device buffers that only ever
+// grow, so a steady-state call performs no allocation: memcpy into pinned -> H2D -> kernels
+// -> D2H -> memcpy out, all on the context's stream.  Many host threads (Spark task threads
+// of one executor JVM) can be inside these calls at once; each holds a different context, so
+// their copies and kernels overlap on the GPU.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <vector>
+
+#include "../../include/csbwa_sw.h"
+#define CSBWA_E_BADWIRE_DEV CSBWA_E_BADWIRE
+#include "ext_kernels.cuh"
+#include "aln_kernels.cuh"
+
+using namespace csw;
+
+static_assert(sizeof(csbwa_job) == sizeof(AlnJob), "job layout");
+static_assert(sizeof(csbwa_kswr) == 7 * sizeof(int32_t), "kswr layout");
+
+// ------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------
+static thread_local char tl_err[256] = "";
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(tl_err, sizeof tl_err, fmt, a, b);
+    return code;
+}
+#define CU_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) return fail(CSBWA_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" const char *csbwa_last_error(void) { return tl_err; }
+extern "C" const char *csbwa_version(void) { return "csbwa-sw-b200 0.1 (sm_100a)"; }
+extern "C" const char *csbwa_strerror(int code)
+{
+    switch (code) {
+    case CSBWA_OK: return "ok";
+    case CSBWA_E_NODEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case CSBWA_E_BADARG: return "bad argument";
+    case CSBWA_E_BADWIRE: return "inconsistent extension byte buffer";
+    case CSBWA_E_SHORTOUT: return "output array too small";
+    case CSBWA_E_CUDA: return "CUDA runtime error";
+    case CSBWA_E_NOMEM: return "allocation failed";
+    case CSBWA_E_SCRATCH: return "device scratch too small";
+    default: return "unknown error";
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// stats
+// ------------------------------------------------------------------------------------
+static std::mutex g_stats_mu;
+static csbwa_stats g_stats;
+
+// ------------------------------------------------------------------------------------
+// kernel launch sequences (device-resident core of both seams)
+// ------------------------------------------------------------------------------------
+struct DevInfo { int sms = 0; bool attrs_set = false; };
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int ensure_dev_attrs(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevInfo &d = g_dev[dev];
+    if (d.attrs_set) return CSBWA_OK;
+    cudaDeviceProp p;
+    CU_TRY(cudaGetDeviceProperties(&p, dev));
+    d.sms = p.multiProcessorCount;
+    const int big = 128 * 1024;
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    d.attrs_set = true;
+    return CSBWA_OK;
+}
+
+static const int kExtLaunches = 3 + 2 * EXT_NCLS;
+static const int kAlnLaunches = 1 + ALN_NCLS;
+extern "C" int csbwa_extend_launches_per_call(void) { return kExtLaunches; }
+extern "C" int csbwa_align2_launches_per_call(void) { return kAlnLaunches; }
+
+extern "C" int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes)
+{
+    // fixed part (header, two job lists, left results) + generic H/E rows addressed by the
+    // task's block offset (16 B per input byte)
+    return (int64_t)ext_scratch_bytes(n_tasks, in_bytes);
+}
+
+template <int SIDE>
+static void launch_ext_side(const uint8_t *d_in, int in_bytes, ExtScratch &sc, int16_t *d_out,
+                            unsigned long long *d_cells, int n, int sms, cudaStream_t st)
+{
+    for (int cls = 0; cls < EXT_NCLS; ++cls) {
+        if (cls == 0) {
+            int grid = (n + EXT_BD - 1) / EXT_BD;
+            if (grid > sms * 8) grid = sms * 8;
+            k_ext_side<SIDE, false><<<grid, EXT_BD, 0, st>>>(d_in, in_bytes, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                              d_out, d_cells, cls);
+        } else {
+            const int cap = ext_class_cap(cls);
+            const int bd = cls == 1 ? 64 : EXT_BD;
+            const size_t smem = (size_t)cap * bd * 4;
+            const int per_sm = cls == 1 ? 3 : (cls == 2 ? 3 : 7);
+            int grid = (n + bd - 1) / bd;
+            if (grid > sms * per_sm) grid = sms * per_sm;
+            k_ext_side<SIDE, true><<<grid, bd, smem, st>>>(d_in, in_bytes, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                            d_out, d_cells, cls);
+        }
+    }
+}
+
+static int launch_extend(const uint8_t *d_in, int in_bytes, int n, int16_t *d_out,
+                         unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
+                         cudaStream_t st, int dev)
+{
+    if (n <= 0) return CSBWA_OK;
+    if ((int64_t)ext_scratch_bytes(n, in_bytes) > scratch_bytes) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
+    int rc = ensure_dev_attrs(dev);
+    if (rc) return rc;
+    ExtScratch sc = ext_carve(d_scratch, n);
+    CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
+    const int tb = 256, gb = (n + tb - 1) / tb;
+    k_ext_hist<<<gb, tb, 0, st>>>(d_in, in_bytes, n, sc.hdr);
+    k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
+    k_ext_scatter<<<gb, tb, 0, st>>>(d_in, in_bytes, n, sc.hdr, sc.order[0], sc.order[1]);
+    launch_ext_side<0>(d_in, in_bytes, sc, d_out, d_cells, n, g_dev[dev].sms, st);
+    launch_ext_side<1>(d_in, in_bytes, sc, d_out, d_cells, n, g_dev[dev].sms, st);
+    CU_TRY(cudaGetLastError());
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
+                                         void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    if (!d_in || !d_out || !d_scratch || in_bytes < 32 || n_tasks < 0) return fail(CSBWA_E_BADARG, "bad argument");
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    int rc = launch_extend((const uint8_t *)d_in, in_bytes, n_tasks, (int16_t *)d_out,
+                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
+    if (rc == CSBWA_OK && n_tasks > 0) {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.kernel_launches += kExtLaunches;
+    }
+    return rc;
+}
+
+extern "C" int64_t csbwa_align2_scratch_bytes(int32_t n_jobs, int64_t total_q_len, int64_t total_t_len)
+{
+    // fixed part + b-arrays (8 B per two target rows, 16-B rounding) + generic H/E rows
+    return (int64_t)aln_scratch_fixed(n_jobs) + 4 * total_t_len + 8 * total_q_len + (int64_t)64 * n_jobs + 4096;
+}
+
+static int launch_align2(const AlnJob *d_jobs, int n, const uint8_t *d_seqs, int32_t *d_out,
+                         unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
+                         cudaStream_t st, int dev)
+{
+    if (n <= 0) return CSBWA_OK;
+    const int64_t fixed = (int64_t)aln_scratch_fixed(n);
+    if (scratch_bytes <= fixed) return fail(CSBWA_E_SCRATCH, "align scratch too small");
+    int rc = ensure_dev_attrs(dev);
+    if (rc) return rc;
+    const int sms = g_dev[dev].sms;
+    AlnScratch sc = aln_carve(d_scratch, n);
+    CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(AlnHdr), st));
+    const int tb = 256, gb = (n + tb - 1) / tb;
+    k_aln_classify<<<gb, tb, 0, st>>>(d_jobs, n, sc, (unsigned long long)(scratch_bytes - fixed));
+    int gw = (n + 3) / 4;
+    if (gw > sms * 8) gw = sms * 8;
+    int gg = (n + 127) / 128;
+    if (gg > sms * 8) gg = sms * 8;
+    k_aln_generic<<<gg, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells);
+    k_aln_warp<8><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 1);
+    k_aln_warp<5><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 2);
+    k_aln_warp<4><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 3);
+    k_aln_warp<2><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 4);
+    CU_TRY(cudaGetLastError());
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, void *d_out,
+                                         void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    if (!d_jobs || !d_seqs || !d_out || !d_scratch || n_jobs < 0) return fail(CSBWA_E_BADARG, "bad argument");
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    int rc = launch_align2((const AlnJob *)d_jobs, n_jobs, (const uint8_t *)d_seqs, (int32_t *)d_out,
+                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
+    if (rc == CSBWA_OK && n_jobs > 0) {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.kernel_launches += kAlnLaunches;
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// contexts (host-buffer seams)
+// ------------------------------------------------------------------------------------
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct Ctx {
+    int dev = -1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Buf h_in, h_out, d_in, d_out, d_scratch, d_aux;   // pinned host in/out, device in/out/scratch/aux
+    unsigned long long *d_cells = nullptr;
+    unsigned long long *h_cells = nullptr;   // pinned
+    int32_t *h_err = nullptr;                // pinned
+};
+
+static std::mutex g_mu;
+static bool g_inited = false;
+static int g_ndev = 0;
+static std::vector<std::vector<Ctx *>> g_free;   // per device
+static std::atomic<unsigned> g_rr{0};
+
+static int grow_pinned(Buf &b, size_t need)
+{
+    if (need <= b.cap) return CSBWA_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t cap = need + need / 4 + 4096;
+    if (cudaMallocHost(&b.p, cap) != cudaSuccess) { b.p = nullptr; return fail(CSBWA_E_NOMEM, "cudaMallocHost failed"); }
+    b.cap = cap;
+    return CSBWA_OK;
+}
+static int grow_dev(Buf &b, size_t need)
+{
+    if (need <= b.cap) return CSBWA_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t cap = need + need / 4 + 4096;
+    if (cudaMalloc(&b.p, cap) != cudaSuccess) { b.p = nullptr; return fail(CSBWA_E_NOMEM, "cudaMalloc failed"); }
+    b.cap = cap;
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_init(int n_gpus)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return g_ndev;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(CSBWA_E_NODEVICE, "%s", e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA devices");
+    }
+    if (n_gpus > 0 && n_gpus < n) n = n_gpus;
+    if (n > 64) n = 64;
+    g_ndev = n;
+    g_free.assign(n, {});
+    memset(&g_stats, 0, sizeof g_stats);
+    g_inited = true;
+    return g_ndev;
+}
+
+extern "C" int csbwa_device_count(void) { return g_inited ? g_ndev : 0; }
+
+static void destroy_ctx(Ctx *c)
+{
+    cudaSetDevice(c->dev);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->h_in.p) cudaFreeHost(c->h_in.p);
+    if (c->h_out.p) cudaFreeHost(c->h_out.p);
+    if (c->d_in.p) cudaFree(c->d_in.p);
+    if (c->d_out.p) cudaFree(c->d_out.p);
+    if (c->d_scratch.p) cudaFree(c->d_scratch.p);
+    if (c->d_aux.p) cudaFree(c->d_aux.p);
+    if (c->d_cells) cudaFree(c->d_cells);
+    if (c->h_cells) cudaFreeHost(c->h_cells);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" int csbwa_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return CSBWA_OK;
+    for (auto &v : g_free) { for (Ctx *c : v) destroy_ctx(c); v.clear(); }
+    g_inited = false;
+    g_ndev = 0;
+    return CSBWA_OK;
+}
+
+static int acquire_ctx(int device, Ctx **out)
+{
+    if (!g_inited) {
+        int rc = csbwa_init(0);
+        if (rc < 0) return rc;
+    }
+    int dev = device;
+    if (dev < 0) dev = (int)(g_rr.fetch_add(1) % (unsigned)g_ndev);
+    if (dev >= g_ndev) return fail(CSBWA_E_BADARG, "device index out of range");
+    CU_TRY(cudaSetDevice(dev));
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto &v = g_free[dev];
+        if (!v.empty()) { *out = v.back(); v.pop_back(); return CSBWA_OK; }
+    }
+    int rc = ensure_dev_attrs(dev);
+    if (rc) return rc;
+    Ctx *c = new Ctx();
+    c->dev = dev;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(CSBWA_E_CUDA, "stream create failed"); }
+    for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { destroy_ctx(c); return fail(CSBWA_E_CUDA, "event create failed"); }
+    if (cudaMalloc(&c->d_cells, 8) != cudaSuccess || cudaMallocHost(&c->h_cells, 8) != cudaSuccess ||
+        cudaMallocHost(&c->h_err, 8) != cudaSuccess) { destroy_ctx(c); return fail(CSBWA_E_NOMEM, "context allocation failed"); }
+    *out = c;
+    return CSBWA_OK;
+}
+static void release_ctx(Ctx *c)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited && c->dev < (int)g_free.size()) g_free[c->dev].push_back(c);
+    else destroy_ctx(c);
+}
+
+struct CtxGuard {
+    Ctx *c;
+    ~CtxGuard() { if (c) release_ctx(c); }
+};
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// host-side sanity check of the extension buffer (cheap; the device re-validates per record)
+static int check_ext_wire(const uint8_t *in, int32_t in_bytes, int32_t *n_out)
+{
+    if (in_bytes < CSBWA_EXT_HDR_BYTES) return fail(CSBWA_E_BADWIRE, "buffer shorter than the 32-byte header");
+    if (in_bytes % 4) return fail(CSBWA_E_BADWIRE, "buffer length is not a multiple of 4");
+    int32_t n;
+    memcpy(&n, in + 8, 4);
+    if (n < 0 || (int64_t)32 + (int64_t)32 * n > in_bytes) return fail(CSBWA_E_BADWIRE, "taskNum inconsistent with buffer length");
+    *n_out = n;
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts, int device)
+{
+    const double t0 = now_ms();
+    if (!in || !out || in_bytes < 0 || out_shorts < 0) return fail(CSBWA_E_BADARG, "null buffer or negative size");
+    int32_t n = 0;
+    int rc = check_ext_wire(in, in_bytes, &n);
+    if (rc) return rc;
+    if (out_shorts < CSBWA_EXT_RET_SHORTS * n) return fail(CSBWA_E_SHORTOUT, "reply array too small");
+    if (n == 0) return CSBWA_OK;
+    Ctx *c = nullptr;
+    rc = acquire_ctx(device, &c);
+    if (rc) return rc;
+    CtxGuard guard{c};
+    const size_t out_bytes = (size_t)n * CSBWA_EXT_RET_SHORTS * 2;
+    const size_t scr = ext_scratch_bytes(n, in_bytes);
+    if ((rc = grow_pinned(c->h_in, in_bytes)) || (rc = grow_pinned(c->h_out, out_bytes)) ||
+        (rc = grow_dev(c->d_in, in_bytes)) || (rc = grow_dev(c->d_out, out_bytes)) ||
+        (rc = grow_dev(c->d_scratch, scr)))
+        return rc;
+    memcpy(c->h_in.p, in, in_bytes);
+    CU_TRY(cudaEventRecord(c->ev[0], c->st));
+    CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
+    CU_TRY(cudaEventRecord(c->ev[1], c->st));
+    rc = launch_extend((const uint8_t *)c->d_in.p, in_bytes, n, (int16_t *)c->d_out.p, c->d_cells,
+                       c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(c->ev[2], c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_cells, c->d_cells, 8, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_err, &((ExtHdr *)c->d_scratch.p)->err, 4, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaEventRecord(c->ev[3], c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    if (*c->h_err != 0) return fail(CSBWA_E_BADWIRE, "a task record points outside the buffer");
+    memcpy(out, c->h_out.p, out_bytes);
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.ext_calls++; g_stats.ext_tasks += n; g_stats.ext_cells += (int64_t)*c->h_cells;
+        g_stats.ext_in_bytes += in_bytes; g_stats.ext_out_bytes += (int64_t)out_bytes;
+        g_stats.kernel_launches += kExtLaunches;
+        g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += d;
+        g_stats.host_ms += now_ms() - t0;
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes,
+                                  csbwa_kswr *out, int device)
+{
+    const double t0 = now_ms();
+    if (n_jobs < 0 || seq_bytes < 0 || (n_jobs > 0 && (!jobs || !seqs || !out))) return fail(CSBWA_E_BADARG, "null buffer or negative size");
+    if (n_jobs == 0) return CSBWA_OK;
+    int64_t tq = 0, tt = 0;
+    for (int32_t k = 0; k < n_jobs; ++k) {
+        const csbwa_job &j = jobs[k];
+        if (j.q_len < 0 || j.t_len < 0 || j.q_off < 0 || j.t_off < 0 ||
+            j.q_off + j.q_len > seq_bytes || j.t_off + j.t_len > seq_bytes)
+            return fail(CSBWA_E_BADARG, "job sequence range outside seqs[]");
+        tq += j.q_len; tt += j.t_len;
+    }
+    Ctx *c = nullptr;
+    int rc = acquire_ctx(device, &c);
+    if (rc) return rc;
+    CtxGuard guard{c};
+    const size_t jb = (size_t)n_jobs * sizeof(csbwa_job);
+    const size_t jb_al = (jb + 255) & ~(size_t)255;
+    const size_t in_bytes = jb_al + (size_t)seq_bytes;
+    const size_t out_bytes = (size_t)n_jobs * sizeof(csbwa_kswr);
+    const size_t scr = (size_t)csbwa_align2_scratch_bytes(n_jobs, tq, tt);
+    if ((rc = grow_pinned(c->h_in, in_bytes)) || (rc = grow_pinned(c->h_out, out_bytes)) ||
+        (rc = grow_dev(c->d_in, in_bytes)) || (rc = grow_dev(c->d_out, out_bytes)) ||
+        (rc = grow_dev(c->d_scratch, scr)))
+        return rc;
+    memcpy(c->h_in.p, jobs, jb);
+    memcpy((char *)c->h_in.p + jb_al, seqs, (size_t)seq_bytes);
+    CU_TRY(cudaEventRecord(c->ev[0], c->st));
+    CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
+    CU_TRY(cudaEventRecord(c->ev[1], c->st));
+    rc = launch_align2((const AlnJob *)c->d_in.p, n_jobs, (const uint8_t *)c->d_in.p + jb_al, (int32_t *)c->d_out.p,
+                       c->d_cells, c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(c->ev[2], c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_cells, c->d_cells, 8, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_err, &((AlnHdr *)c->d_scratch.p)->err, 4, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaEventRecord(c->ev[3], c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    if (*c->h_err != 0) return fail(CSBWA_E_SCRATCH, "device scratch exhausted");
+    memcpy(out, c->h_out.p, out_bytes);
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.aln_calls++; g_stats.aln_jobs += n_jobs; g_stats.aln_cells += (int64_t)*c->h_cells;
+        g_stats.aln_in_bytes += (int64_t)(jb + seq_bytes); g_stats.aln_out_bytes += (int64_t)out_bytes;
+        g_stats.kernel_launches += kAlnLaunches;
+        g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += d;
+        g_stats.host_ms += now_ms() - t0;
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_get_stats(csbwa_stats *out)
+{
+    if (!out) return CSBWA_E_BADARG;
+    std::lock_guard<std::mutex> lk(g_stats_mu);
+    *out = g_stats;
+    return CSBWA_OK;
+}
+extern "C" int csbwa_reset_stats(void)
+{
+    std::lock_guard<std::mutex> lk(g_stats_mu);
+    memset(&g_stats, 0, sizeof g_stats);
+    return CSBWA_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// host packer (the caller's side of seam 1, for non-JVM hosts)
+// restates runOnFPGAJNI's packing, S/worker1/MemChainToAlignBatched.scala:76-172
+// ------------------------------------------------------------------------------------
+static inline int64_t task_words(const int32_t *len4)
+{
+    const int64_t tot = (int64_t)len4[0] + len4[1] + len4[2] + len4[3];
+    return (((tot + 1) / 2) + 3) / 4;
+}
+
+extern "C" int64_t csbwa_pack_ext_bytes(int32_t n_tasks, const int32_t *len4)
+{
+    if (n_tasks < 0 || (n_tasks > 0 && !len4)) return CSBWA_E_BADARG;
+    int64_t words = 8 + 8 * (int64_t)n_tasks;
+    for (int32_t k = 0; k < n_tasks; ++k) words += task_words(len4 + 4 * (size_t)k);
+    return words * 4;
+}
+
+static inline int scala_maxgap(int qlen, int maxmat, int clip, int o, int e)
+{
+    double x = (double)(qlen * maxmat + clip - o) / (double)e + 1.0;   // :106-109, .toInt then .toShort
+    int v;
+    if (x != x) v = 0;
+    else if (x >= 2147483647.0) v = 2147483647;
+    else if (x <= -2147483648.0) v = -2147483647 - 1;
+    else v = (int)x;
+    return v;
+}
+
+extern "C" int64_t csbwa_pack_ext_tasks(int32_t n_tasks, const uint8_t *seqs, const int64_t *off4,
+                                        const int32_t *len4, const int32_t *meta4, const int32_t *opt7,
+                                        uint8_t *out, int64_t cap)
+{
+    if (n_tasks < 0 || !opt7 || !out || (n_tasks > 0 && (!seqs || !off4 || !len4 || !meta4))) return CSBWA_E_BADARG;
+    const int64_t need = csbwa_pack_ext_bytes(n_tasks, len4);
+    if (need > cap) return CSBWA_E_SHORTOUT;
+    memset(out, 0, (size_t)need);
+    for (int i = 0; i < 7; ++i) out[i] = (uint8_t)opt7[i];           // :78-84 (.toByte)
+    memcpy(out + 8, &n_tasks, 4);                                       // :85
+    const int o_del = opt7[0], e_del = opt7[1], o_ins = opt7[2], e_ins = opt7[3], c5 = opt7[4], c3 = opt7[5];
+    int64_t pos = 8 + 8 * (int64_t)n_tasks;                             // :92, in words
+    for (int32_t k = 0; k < n_tasks; ++k) {
+        const int32_t *len = len4 + 4 * (size_t)k;      // leftQ, leftR, rightQ, rightR
+        const int32_t *meta = meta4 + 4 * (size_t)k;    // regScore, qBeg, h0, idx
+        uint8_t *rec = out + 32 + 32 * (size_t)k;
+        int16_t s;
+        s = (int16_t)len[0]; memcpy(rec + 0, &s, 2);
+        s = (int16_t)len[1]; memcpy(rec + 2, &s, 2);
+        s = (int16_t)len[2]; memcpy(rec + 4, &s, 2);
+        s = (int16_t)len[3]; memcpy(rec + 6, &s, 2);
+        int32_t p32 = (int32_t)pos; memcpy(rec + 8, &p32, 4);
+        s = (int16_t)meta[0]; memcpy(rec + 12, &s, 2);
+        s = (int16_t)meta[1]; memcpy(rec + 14, &s, 2);
+        s = (int16_t)meta[2]; memcpy(rec + 16, &s, 2);
+        s = (int16_t)meta[3]; memcpy(rec + 18, &s, 2);
+        s = (int16_t)scala_maxgap(len[0], 1, c5, o_ins, e_ins); memcpy(rec + 20, &s, 2);
+        s = (int16_t)scala_maxgap(len[0], 1, c5, o_del, e_del); memcpy(rec + 22, &s, 2);
+        s = (int16_t)scala_maxgap(len[2], 1, c3, o_ins, e_ins); memcpy(rec + 24, &s, 2);
+        s = (int16_t)scala_maxgap(len[2], 1, c3, o_del, e_del); memcpy(rec + 26, &s, 2);
+        memcpy(rec + 28, &meta[3], 4);
+        // nibbles: wire order leftQ, rightQ, leftR, rightR (:125-161)
+        static const int order[4] = {0, 2, 1, 3};
+        uint8_t *blk = out + pos * 4;
+        uint32_t acc = 0;
+        int cnt = 0;
+        int64_t wi = 0;
+        for (int sgi = 0; sgi < 4; ++sgi) {
+            const int sg = order[sgi];
+            const uint8_t *src = seqs + off4[4 * (size_t)k + sg];
+            for (int32_t j = 0; j < len[sg]; ++j) {
+                acc = (acc << 4) | (uint32_t)(src[j] & 0x0f);
+                if (++cnt == 8) { memcpy(blk + 4 * wi, &acc, 4); ++wi; cnt = 0; acc = 0; }
+            }
+        }
+        if (cnt) { acc <<= 4 * (8 - cnt); memcpy(blk + 4 * wi, &acc, 4); ++wi; }
+        pos += task_words(len);
+    }
+    return need;
+}
+
+// ------------------------------------------------------------------------------------
+// host task builder (the caller's side of seam 1, one level up): from a read, its seed and
+// the chain window [rmax0, rmax1) build the four segments exactly like memChainToAlnBatched
+// (S/worker1/MemChainToAlignBatched.scala:500-563: left query/reference REVERSED, right
+// forward; h0 = regScore = seed.len * a) and pack them like runOnFPGAJNI (:76-172).
+// reads: n_reads x read_len bytes (codes 0..4); ref: forward reference, 1 base per byte.
+// seed5: per task {read index, qBeg, len, rBeg, rmax0, rmax1} as int64[6].
+// Returns bytes written or a negative code.  Pass out == NULL to get the size only.
+// ------------------------------------------------------------------------------------
+extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *reads, int32_t read_len,
+                                             const uint8_t *ref, int64_t ref_len, const int64_t *seed6,
+                                             const int32_t *opt7, uint8_t *out, int64_t cap)
+{
+    if (n_tasks < 0 || read_len <= 0 || !opt7 || (n_tasks > 0 && (!reads || !ref || !seed6))) return CSBWA_E_BADARG;
+    int64_t words = 8 + 8 * (int64_t)n_tasks;
+    for (int32_t k = 0; k < n_tasks; ++k) {
+        const int64_t *s = seed6 + 6 * (size_t)k;
+        const int64_t qb = s[1], len = s[2], rb = s[3], r0 = s[4], r1 = s[5];
+        if (qb < 0 || len <= 0 || qb + len > read_len || r0 < 0 || r1 > ref_len || r0 > rb || rb + len > r1)
+            return CSBWA_E_BADARG;
+        const int64_t lq = qb, rq = read_len - (qb + len);
+        const int64_t lr = lq > 0 ? rb - r0 : 0, rr = rq > 0 ? r1 - (rb + len) : 0;
+        const int64_t tot = lq + lr + rq + rr;
+        words += (((tot + 1) / 2) + 3) / 4;
+    }
+    const int64_t need = words * 4;
+    if (!out) return need;
+    if (need > cap) return CSBWA_E_SHORTOUT;
+    memset(out, 0, (size_t)(32 + 32 * (int64_t)n_tasks));
+    for (int i = 0; i < 7; ++i) out[i] = (uint8_t)opt7[i];
+    memcpy(out + 8, &n_tasks, 4);
+    const int o_del = opt7[0], e_del = opt7[1], o_ins = opt7[2], e_ins = opt7[3], c5 = opt7[4], c3 = opt7[5];
+    int64_t pos = 8 + 8 * (int64_t)n_tasks;
+    for (int32_t k = 0; k < n_tasks; ++k) {
+        const int64_t *s = seed6 + 6 * (size_t)k;
+        const uint8_t *rd = reads + (size_t)s[0] * read_len;
+        const int64_t qb = s[1], len = s[2], rb = s[3], r0 = s[4], r1 = s[5];
+        const int lq = (int)qb, rq = (int)(read_len - (qb + len));
+        const int lr = lq > 0 ? (int)(rb - r0) : 0, rr = rq > 0 ? (int)(r1 - (rb + len)) : 0;
+        const int h0 = (int)len;   // seed.len * a, a = 1
+        uint8_t *rec = out + 32 + 32 * (size_t)k;
+        int16_t v;
+        v = (int16_t)lq; memcpy(rec + 0, &v, 2);
+        v = (int16_t)lr; memcpy(rec + 2, &v, 2);
+        v = (int16_t)rq; memcpy(rec + 4, &v, 2);
+        v = (int16_t)rr; memcpy(rec + 6, &v, 2);
+        int32_t p32 = (int32_t)pos; memcpy(rec + 8, &p32, 4);
+        v = (int16_t)h0; memcpy(rec + 12, &v, 2);          // regScore
+        v = (int16_t)qb; memcpy(rec + 14, &v, 2);
+        v = (int16_t)h0; memcpy(rec + 16, &v, 2);
+        v = (int16_t)k;  memcpy(rec + 18, &v, 2);
+        v = (int16_t)scala_maxgap(lq, 1, c5, o_ins, e_ins); memcpy(rec + 20, &v, 2);
+        v = (int16_t)scala_maxgap(lq, 1, c5, o_del, e_del); memcpy(rec + 22, &v, 2);
+        v = (int16_t)scala_maxgap(rq, 1, c3, o_ins, e_ins); memcpy(rec + 24, &v, 2);
+        v = (int16_t)scala_maxgap(rq, 1, c3, o_del, e_del); memcpy(rec + 26, &v, 2);
+        int32_t idx = k; memcpy(rec + 28, &idx, 4);
+        uint8_t *blk = out + pos * 4;
+        uint32_t acc = 0;
+        int cnt = 0;
+        int64_t wi = 0;
+        auto push = [&](uint8_t b) {
+            acc = (acc << 4) | (uint32_t)(b & 0x0f);
+            if (++cnt == 8) { memcpy(blk + 4 * wi, &acc, 4); ++wi; cnt = 0; acc = 0; }
+        };
+        for (int j = 0; j < lq; ++j) push(rd[lq - 1 - j]);              // leftQ reversed (:505-510)
+        for (int j = 0; j < rq; ++j) push(rd[qb + len + j]);            // rightQ (:528-533)
+        for (int j = 0; j < lr; ++j) push(ref[rb - 1 - j]);             // leftR reversed (:511-517)
+        for (int j = 0; j < rr; ++j) push(ref[rb + len + j]);           // rightR (:534-541)
+        if (cnt) { acc <<= 4 * (8 - cnt); memcpy(blk + 4 * wi, &acc, 4); ++wi; }
+        const int64_t tot = (int64_t)lq + lr + rq + rr;
+        pos += (((tot + 1) / 2) + 3) / 4;
+    }
+    return need;
+}
+#include "csbwa_jni.inc"

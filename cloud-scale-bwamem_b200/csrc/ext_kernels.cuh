@@ -1,0 +1,258 @@
+// ext_kernels.cuh -- device orchestration of one batched-extension call (seam 1).
+//
+// Per call (all on one stream, no host synchronisation):
+//   k_ext_hist     : parse + validate the 32-B task records, histogram both sides by query length
+//   k_ext_scan     : descending prefix over the 257 bins, class boundaries
+//   k_ext_scatter  : counting-sort scatter -> per-side job lists ordered longest-first
+//   k_ext_side<L>  : one thread per LEFT job, one launch per size class (shared-memory budget)
+//   k_ext_side<R>  : one thread per task; RIGHT SWExtend seeded with the left score, then the
+//                    ExtRet record is finalised and written (10 shorts)
+// Jobs are length-binned so the 32 lanes of a warp run bands of (nearly) equal width; warps
+// pull 32-job chunks from a per-class atomic cursor (longest first).
+#pragma once
+#include <cuda_runtime.h>
+#include "ext_core.cuh"
+
+namespace csw {
+
+constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty side, 256 = generic
+constexpr int EXT_NCLS = 4;            // 0: generic, 1: cap 256, 2: cap 128, 3: cap 64
+constexpr int EXT_BD = 128;            // threads per block of the side kernels
+
+struct ExtHdr {
+    SwOpt opt;
+    int32_t n_tasks;
+    int32_t err;
+    uint32_t hist[2][EXT_NBIN];
+    uint32_t base[2][EXT_NBIN];        // start of each bin in the descending order
+    uint32_t cursor[2][EXT_NBIN];
+    uint32_t cls_beg[2][EXT_NCLS + 1]; // job range of each class inside order[side]
+    uint32_t work[2][EXT_NCLS];        // dynamic chunk cursors
+};
+
+// scratch layout helpers ----------------------------------------------------------
+struct ExtScratch {
+    ExtHdr *hdr;
+    uint32_t *order[2];   // [n]
+    SideRes *left;        // [n]
+    int *eh;              // generic H/E rows
+};
+__host__ __device__ inline size_t ext_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t ext_scratch_fixed(int n)
+{
+    return ext_align256(sizeof(ExtHdr)) + 2 * ext_align256((size_t)n * 4) +
+           ext_align256((size_t)n * sizeof(SideRes));
+}
+__host__ __device__ inline size_t ext_scratch_bytes(int n, int64_t in_bytes)
+{
+    return ext_scratch_fixed(n) + (size_t)16 * (size_t)in_bytes + (size_t)32 * n + 256;
+}
+__host__ __device__ inline ExtScratch ext_carve(void *p, int n)
+{
+    ExtScratch s;
+    char *c = (char *)p;
+    s.hdr = (ExtHdr *)c; c += ext_align256(sizeof(ExtHdr));
+    s.order[0] = (uint32_t *)c; c += ext_align256((size_t)n * 4);
+    s.order[1] = (uint32_t *)c; c += ext_align256((size_t)n * 4);
+    s.left = (SideRes *)c; c += ext_align256((size_t)n * sizeof(SideRes));
+    s.eh = (int *)c;
+    return s;
+}
+
+CSW_HD int ext_class_of_bin(int bin)
+{
+    if (bin == 256) return 0;
+    if (bin > 127) return 1;
+    if (bin > 63) return 2;
+    return 3;
+}
+__host__ __device__ inline int ext_class_cap(int cls) { return cls == 1 ? 256 : (cls == 2 ? 128 : 64); }
+
+// parse the 32-byte common header into SwOpt (MemChainToAlignBatched.scala:78-85)
+CSW_HD void ext_parse_header(const uint8_t *in, SwOpt &o)
+{
+    fill_default_opt(o);
+    o.o_del = in[0]; o.e_del = in[1]; o.o_ins = in[2]; o.e_ins = in[3];
+    o.pen_clip5 = in[4]; o.pen_clip3 = in[5]; o.w = in[6];
+    if (in[7] & 1) o.zdrop = (int16_t)(in[12] | (in[13] << 8));
+    finish_opt(o);
+}
+
+// validate one record; returns false (and zeroes the lengths) when it would read out of bounds
+CSW_HD bool ext_task_ok(const ExtTask &t, int n, int in_bytes)
+{
+    if (t.lq < 0 || t.lr < 0 || t.rq < 0 || t.rr < 0) return false;
+    const long long tot = (long long)t.lq + t.lr + t.rq + t.rr;
+    const long long blk = (((tot + 1) / 2) + 3) / 4;   // words
+    if (t.pos < 8 + 8 * n) return false;
+    if (((long long)t.pos + blk) * 4 > in_bytes) return false;
+    return true;
+}
+
+// bin of one side: 0 = nothing to do, 1..255 = u8 fast path by query length, 256 = generic
+CSW_HD int ext_side_bin(const SwOpt &o, int qlen, int h0)
+{
+    if (qlen <= 0) return 0;
+    return u8_eligible(o, qlen, h0) ? qlen : 256;
+}
+
+__global__ void k_ext_hist(const uint8_t *__restrict__ in, int in_bytes, int n, ExtHdr *hdr)
+{
+    __shared__ uint32_t sh[2][EXT_NBIN];
+    __shared__ SwOpt sopt;
+    for (int i = threadIdx.x; i < 2 * EXT_NBIN; i += blockDim.x) (&sh[0][0])[i] = 0;
+    if (threadIdx.x == 0) {
+        ext_parse_header(in, sopt);
+        if (blockIdx.x == 0) { hdr->opt = sopt; hdr->n_tasks = n; }
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        ExtTask t = read_task(in, k);
+        int bl = 0, br = 0;
+        if (!ext_task_ok(t, n, in_bytes)) {
+            atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
+        } else {
+            // the right side's h0 is the left score, bounded by h0 + lq * max(mat)
+            bl = ext_side_bin(sopt, t.lq, t.h0);
+            const int h0r = t.lq > 0 ? t.h0 + t.lq * sopt.max_mat : t.reg_score;
+            br = ext_side_bin(sopt, t.rq, h0r);
+            if (t.lq > 0 && bl == 256 && br != 0) br = 256;   // keep score bounds trivially safe
+        }
+        if (bl) atomicAdd(&sh[0][bl], 1u);
+        atomicAdd(&sh[1][br], 1u);                            // every task has a right/finalise job
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * EXT_NBIN; i += blockDim.x) {
+        uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&(&hdr->hist[0][0])[i], v);
+    }
+}
+
+__global__ void k_ext_scan(ExtHdr *hdr)
+{
+    // one warp per side; bins are few, a serial scan by lane 0 is enough
+    const int side = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && side < 2) {
+        uint32_t acc = 0;
+        int cls = 0;
+        hdr->cls_beg[side][0] = 0;
+        for (int b = EXT_NBIN - 1; b >= 0; --b) {
+            const int c = ext_class_of_bin(b);
+            while (cls < c) hdr->cls_beg[side][++cls] = acc;
+            hdr->base[side][b] = acc;
+            hdr->cursor[side][b] = 0;
+            acc += hdr->hist[side][b];
+        }
+        while (cls < EXT_NCLS) hdr->cls_beg[side][++cls] = acc;
+        for (int c = 0; c < EXT_NCLS; ++c) hdr->work[side][c] = 0;
+    }
+}
+
+__global__ void k_ext_scatter(const uint8_t *__restrict__ in, int in_bytes, int n, ExtHdr *hdr,
+                              uint32_t *__restrict__ order_l, uint32_t *__restrict__ order_r)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const SwOpt &o = hdr->opt;
+    ExtTask t = read_task(in, k);
+    int bl = 0, br = 0;
+    if (ext_task_ok(t, n, in_bytes)) {
+        bl = ext_side_bin(o, t.lq, t.h0);
+        const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
+        br = ext_side_bin(o, t.rq, h0r);
+        if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+    }
+    if (bl) order_l[hdr->base[0][bl] + atomicAdd(&hdr->cursor[0][bl], 1u)] = (uint32_t)k;
+    order_r[hdr->base[1][br] + atomicAdd(&hdr->cursor[1][br], 1u)] = (uint32_t)k;
+}
+
+// ---------------------------------------------------------------------------------
+// side kernels
+// ---------------------------------------------------------------------------------
+// One SWExtend side with band retries; FAST selects the u8 shared-memory core.
+template <bool FAST>
+CSW_HD void ext_run_side(const SwOpt &o, const uint32_t *words, int q_nib, int qlen,
+                                             int t_nib, int tlen, int end_bonus, int h0, int prev,
+                                             uint32_t *col, int stride, int *H, int *E,
+                                             SideRes &out)
+{
+    SwExtRes r;
+    int aw = o.w, cells = 0;
+    if (FAST) u8_stage_query(col, stride, words, q_nib, qlen);
+    for (int i = 0; i < CSW_MAX_BAND_TRY; ++i) {
+        aw = o.w << i;
+        if (FAST) sw_extend_u8(o, col, stride, qlen, words, t_nib, tlen, aw, end_bonus, h0, r);
+        else sw_extend_generic(o, words, q_nib, qlen, t_nib, tlen, aw, end_bonus, h0, H, E, 1, r);
+        cells += r.cells;
+        if (r.score == prev || r.max_off < (aw >> 1) + (aw >> 2)) break;
+        prev = r.score;
+    }
+    out.score = (int16_t)r.score; out.qle = (int16_t)r.qle; out.tle = (int16_t)r.tle;
+    out.gtle = (int16_t)r.gtle; out.gscore = (int16_t)r.gscore; out.aw = (int16_t)aw;
+    out.cells = cells;
+}
+
+// SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range; FAST = u8 core.
+template <int SIDE, bool FAST>
+__global__ void __launch_bounds__(EXT_BD)
+k_ext_side(const uint8_t *__restrict__ in, int in_bytes, ExtHdr *hdr, const uint32_t *__restrict__ order,
+           SideRes *__restrict__ left, int *__restrict__ ehbase, int16_t *__restrict__ out,
+           unsigned long long *cells_acc, int cls)
+{
+    extern __shared__ uint32_t smem[];
+    const SwOpt &o = hdr->opt;
+    const int n = hdr->n_tasks;
+    const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
+    const int lane = threadIdx.x & 31;
+    const int stride = (int)blockDim.x;
+    uint32_t *col = smem + threadIdx.x;            // column j at col[j * stride]
+    unsigned long long my_cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&hdr->work[SIDE][cls], 32u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0) + jbeg;
+        if (chunk >= jend) break;
+        const uint32_t job = chunk + lane;
+        if (job < jend) {
+            const int k = (int)order[job];
+            ExtTask t = read_task(in, k);
+            if (!ext_task_ok(t, n, in_bytes)) { t.lq = t.lr = t.rq = t.rr = 0; t.pos = 8 + 8 * n; }
+            const uint32_t *words = (const uint32_t *)in + t.pos;
+            int *H = nullptr, *E = nullptr;
+            if (!FAST) {
+                const long long boff = (long long)t.pos * 4 - (32 + 32LL * n);
+                int *reg = (int *)((char *)ehbase + 16 * boff + 32LL * k);
+                const int qm = t.lq > t.rq ? t.lq : t.rq;
+                H = reg; E = reg + (qm + 2);
+            }
+            if (SIDE == 0) {
+                SideRes L;
+                ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
+                                   t.reg_score, col, stride, H, E, L);
+                left[k] = L;
+                my_cells += (unsigned)L.cells;
+            } else {
+                SideRes L, R;
+                L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
+                R = L;
+                if (t.lq > 0) L = left[k];
+                if (t.rq > 0) {
+                    const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
+                    ext_run_side<FAST>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0,
+                                       sc0, col, stride, H, E, R);
+                    my_cells += (unsigned)R.cells;
+                }
+                int16_t rec[10];
+                ext_finalize(o, t, &L, &R, rec);
+                uint32_t *dst = (uint32_t *)(out + (size_t)10 * k);
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
+            }
+        }
+    }
+    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
+}
+
+} // namespace csw

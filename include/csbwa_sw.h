@@ -1,0 +1,163 @@
+/*
+ * csbwa_sw.h -- C ABI of libcsbwa_sw.so: the B200 (sm_100a) drop-in for
+ * CS-BWAMEM's batched Smith-Waterman hot path.
+ *
+ * Two seams of the reference are replaced (paths relative to the reference repo;
+ * S/ = src/main/scala/cs/ucla/edu/bwaspark/, N/ = src/main/native/,
+ * F/ = src/main/jni_fpga/):
+ *
+ *   (1) batched seed extension  -- the jni_fpga byte-buffer seam
+ *         Java:   S/jni/SWExtendFPGAJNI.scala:21-23
+ *         native: F/sw_extend_fpga.c:116-193   (shm + TCP to the FPGA host)
+ *         packer: S/worker1/MemChainToAlignBatched.scala:59-191 (runOnFPGAJNI)
+ *         truth:  S/worker1/MemChainToAlignBatched.scala:789-883 (extension)
+ *                 S/util/SWUtil.scala:61-230 (SWExtend)
+ *   (2) batched mate-rescue SW  -- the MateSWJNI seam, flattened to jobs
+ *         Java:   S/jni/MateSWJNI.scala:23-26
+ *         native: N/jni_mate_sw.c:58-60, N/bwamem_pair.c:159-228 (ksw_align2 calls)
+ *         truth:  S/util/SWUtil.scala:417-601 (SWAlign / SWAlign2),
+ *                 call site S/worker2/MemSamPe.scala:1186-1190
+ *
+ * All entry points are plain C: pointers + sizes, no CUDA or torch types.
+ * Return value: 0 (or a non-negative count) on success, a negative CSBWA_E_* code
+ * on failure -- never exit()/abort() like the reference shims do
+ * (F/sw_extend_fpga.c:133-143).  There is NO CPU fallback: without a usable CUDA
+ * device every compute entry point returns CSBWA_E_NODEVICE.
+ * All entry points are re-entrant; concurrent callers (Spark task threads of one
+ * executor JVM) each get their own stream + staging buffers from a per-GPU pool.
+ */
+#ifndef CSBWA_SW_H
+#define CSBWA_SW_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSBWA_OK            0
+#define CSBWA_E_NODEVICE   -1   /* no CUDA device / driver */
+#define CSBWA_E_BADARG     -2   /* null pointer, negative size, bad device index */
+#define CSBWA_E_BADWIRE    -3   /* byte buffer inconsistent (sizes, taskPos out of range) */
+#define CSBWA_E_SHORTOUT   -4   /* output array too small */
+#define CSBWA_E_CUDA       -5   /* a CUDA runtime call failed; see csbwa_last_error() */
+#define CSBWA_E_NOMEM      -6   /* host or device allocation failed */
+#define CSBWA_E_SCRATCH    -7   /* caller-provided device scratch too small */
+
+/* ---- wire format of seam (1), as built by runOnFPGAJNI (MemChainToAlignBatched.scala:76-172)
+ *  header (32 B): [0]oDel [1]eDel [2]oIns [3]eIns [4]penClip5 [5]penClip3 [6]w (bytes),
+ *                 [8..11] taskNum int32 LE, everything else 0.
+ *  OPTIONAL extension (ours; 0 = reference behaviour): [7] bit0 set => [12..13] = zdrop int16.
+ *  taskNum x 32-B records: int16 leftQlen,leftRlen,rightQlen,rightRlen; int32 taskPos (in 4-byte
+ *  words from buffer start); int16 regScore,qBeg,h0,idx16; int16 leftMaxIns,leftMaxDel,
+ *  rightMaxIns,rightMaxDel; int32 idx.
+ *  sequence blocks: 4-bit bases, 8 per int32 (first base in the most significant nibble, word LE),
+ *  per task leftQ,rightQ,leftR,rightR concatenated and zero-padded to a whole word.
+ *  zdrop (100) and the 5x5 matrix (1/-4/-1) are not transmitted: MemOptType defaults
+ *  (S/datatype/MemOptType.scala:28-75) are used, exactly as the FPGA contract implies.
+ *  reply: int16[10*taskNum]: idx lo16, idx hi16, qBeg, qEnd, rBeg, rEnd, score, trueScore, width, 0
+ *  (MemChainToAlignBatched.scala:178-190).                                                   */
+#define CSBWA_EXT_HDR_BYTES   32
+#define CSBWA_EXT_REC_BYTES   32
+#define CSBWA_EXT_RET_SHORTS  10
+
+/* ---- seam (2): one SWAlign2 call = one job.  Bases are 1 byte each, codes 0..4. */
+typedef struct {
+    int64_t q_off, t_off;   /* byte offsets of query / target inside seqs[] */
+    int32_t q_len, t_len;
+    int32_t xtra;           /* KSW_X* flags | minScore, S/util/SWUtil.scala:29-32 */
+    int32_t pad;
+} csbwa_job;
+
+/* = SWAlnType (S/datatype/SWAlnType.scala:21-29) = kswr_t (N/ksw.h:40-46) */
+typedef struct {
+    int32_t score, te, qe, score2, te2, tb, qb;
+} csbwa_kswr;
+
+#define CSBWA_XBYTE  0x10000
+#define CSBWA_XSTOP  0x20000
+#define CSBWA_XSUBO  0x40000
+#define CSBWA_XSTART 0x80000
+
+/* cumulative counters since csbwa_init / csbwa_reset_stats (the reference's
+ * SWBatchTimeBreakdown split, S/profiling/SWBatchTimeBreakdown.scala:27-41) */
+typedef struct {
+    int64_t ext_calls, ext_tasks, ext_cells, ext_in_bytes, ext_out_bytes;
+    int64_t aln_calls, aln_jobs, aln_cells, aln_in_bytes, aln_out_bytes;
+    int64_t kernel_launches;     /* our kernels only */
+    double  h2d_ms, kernel_ms, d2h_ms, host_ms; /* CUDA-event / wall split, summed over calls */
+} csbwa_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* n_gpus <= 0: use every visible device.  Returns the number of devices in use. Idempotent. */
+int csbwa_init(int n_gpus);
+int csbwa_shutdown(void);
+int csbwa_device_count(void);
+const char *csbwa_strerror(int code);
+const char *csbwa_last_error(void);     /* thread-local detail string of the last failure */
+const char *csbwa_version(void);
+int csbwa_get_stats(csbwa_stats *out);
+int csbwa_reset_stats(void);
+
+/* ---- seam (1): host buffers in, host buffers out ------------------------
+ * Replaces Java_cs_ucla_edu_bwaspark_jni_SWExtendFPGAJNI_swExtendFPGAJNI
+ * (F/sw_extend_fpga.c:116-193).  `in`/`out` are ordinary (pageable) host memory;
+ * device = -1 picks a GPU round-robin per call.  Blocks until `out` is filled. */
+int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes,
+                       int16_t *out, int32_t out_shorts, int device);
+
+/* ---- seam (2): host buffers in, host buffers out ------------------------
+ * Replaces the ksw_align2 loop of mem_matesw (N/bwamem_pair.c:159-228) /
+ * SWAlign2 at S/worker2/MemSamPe.scala:1190.  Scoring = MemOptType defaults. */
+int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs,
+                       const uint8_t *seqs, int64_t seq_bytes,
+                       csbwa_kswr *out, int device);
+
+/* ---- device-resident variants (pipelines, benchmarking) -----------------
+ * All pointers are DEVICE pointers on the current CUDA device; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  Nothing is synchronised:
+ * kernels are enqueued on `stream` and the call returns.
+ * d_cells (nullable): uint64 accumulator, += exact DP cells computed.
+ * Scratch must hold csbwa_*_scratch_bytes(); it may be reused between calls
+ * on the same stream.                                                        */
+int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes);
+int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int32_t n_tasks,
+                              void *d_out /* int16[10*n_tasks] */,
+                              void *d_cells, void *d_scratch, int64_t scratch_bytes,
+                              void *stream);
+
+int64_t csbwa_align2_scratch_bytes(int32_t n_jobs, int64_t total_q_len, int64_t total_t_len);
+int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs,
+                              void *d_out /* csbwa_kswr[n_jobs] */,
+                              void *d_cells, void *d_scratch, int64_t scratch_bytes,
+                              void *stream);
+
+/* number of kernels one *_batch_device call enqueues (for launch accounting) */
+int csbwa_extend_launches_per_call(void);
+int csbwa_align2_launches_per_call(void);
+
+/* ---- host-side helper: the caller's packer, for C/C++ hosts --------------
+ * Restates runOnFPGAJNI's packing (MemChainToAlignBatched.scala:76-172) so that a
+ * non-JVM host (tests, bench, a C++ driver) can build the same bytes.
+ * seqs: 1 base per byte; per task the four segments leftQ,leftR,rightQ,rightR are
+ * located by off[4*k..4*k+3] / len[4*k..4*k+3] (left segments already reversed).
+ * meta: int32[4*k..] = regScore, qBeg, h0, idx.   opt7: oDel,eDel,oIns,eIns,penClip5,penClip3,w.
+ * Returns bytes written (<= cap) or a negative code; csbwa_pack_ext_bytes gives the size. */
+int64_t csbwa_pack_ext_bytes(int32_t n_tasks, const int32_t *len4);
+int64_t csbwa_pack_ext_tasks(int32_t n_tasks, const uint8_t *seqs, const int64_t *off4,
+                             const int32_t *len4, const int32_t *meta4, const int32_t *opt7,
+                             uint8_t *out, int64_t cap);
+
+
+/* One level up: build the tasks themselves the way memChainToAlnBatched does
+ * (S/worker1/MemChainToAlignBatched.scala:500-563: left query/reference reversed, right
+ * forward, h0 = regScore = seed.len * a) and pack them.  reads: n x read_len bytes; ref: forward
+ * reference, 1 base/byte; seed6: per task int64 {read index, qBeg, len, rBeg, rmax0, rmax1}.
+ * out == NULL returns the size only. */
+int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *reads, int32_t read_len,
+                                  const uint8_t *ref, int64_t ref_len, const int64_t *seed6,
+                                  const int32_t *opt7, uint8_t *out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSBWA_SW_H */

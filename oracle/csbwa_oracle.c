@@ -1,0 +1,442 @@
+/*
+ * csbwa_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Scalar restatement of the Scala semantics of the CS-BWAMEM Smith-Waterman hot
+ * path; see csbwa_oracle.h for the parity-pinning statement.  Each function
+ * cites the reference text it follows (S/ = src/main/scala/cs/ucla/edu/bwaspark/).
+ * Quirks that are kept on purpose are marked QUIRK.
+ */
+#include "csbwa_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* Scala Double.toInt: truncation toward zero, saturating, NaN -> 0. */
+static int d2i_scala(double x)
+{
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return INT_MAX;
+    if (x <= -2147483648.0) return INT_MIN;
+    return (int)x;
+}
+
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+void orc_default_opt(orc_opt_t *o)
+{
+    /* S/datatype/MemOptType.scala:28-38 */
+    o->a = 1; o->b = 4;
+    o->o_del = 6; o->e_del = 1; o->o_ins = 6; o->e_ins = 1;
+    o->pen_clip5 = 5; o->pen_clip3 = 5;
+    o->w = 100; o->zdrop = 100;
+    /* bwaFillScmat, :58-75: 4x4 block a / -b, row+column 4 (N) = -1 */
+    int k = 0;
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) o->mat[k++] = (int8_t)(i == j ? o->a : -o->b);
+        o->mat[k++] = -1;
+    }
+    for (int j = 0; j < 5; ++j) o->mat[k++] = -1;
+}
+
+/* ------------------------------------------------------------------------- */
+/* SWExtend  (S/util/SWUtil.scala:61-230)                                     */
+/* ------------------------------------------------------------------------- */
+void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                   int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                   int w, int end_bonus, int zdrop, int h0, orc_ext_t *out)
+{
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int32_t *H = (int32_t *)calloc((size_t)qlen + 2, sizeof(int32_t)); /* eh(j).h */
+    int32_t *E = (int32_t *)calloc((size_t)qlen + 2, sizeof(int32_t)); /* eh(j).e */
+    int8_t *prof = (int8_t *)malloc((size_t)(qlen > 0 ? qlen : 1) * (size_t)m);
+    int64_t cells = 0;
+
+    /* query profile (:80-94): prof[k*qlen + j] = mat(k*m + query(j)) */
+    for (int k = 0; k < m; ++k)
+        for (int j = 0; j < qlen; ++j) prof[(size_t)k * qlen + j] = mat[k * m + query[j]];
+
+    /* first row (:96-104) */
+    H[0] = h0;
+    if (qlen >= 1) H[1] = h0 > oe_ins ? h0 - oe_ins : 0;
+    for (int j = 2; j <= qlen && H[j - 1] > e_ins; ++j) H[j] = H[j - 1] - e_ins;
+
+    /* band clamp (:106-115), Double arithmetic then toInt */
+    int mmax = mat[0];
+    for (int k = 1; k < m * m; ++k) mmax = imax(mmax, mat[k]);
+    int max_ins = d2i_scala((double)(qlen * mmax + end_bonus - o_ins) / (double)e_ins + 1.0);
+    if (max_ins < 1) max_ins = 1;
+    if (w > max_ins) w = max_ins;
+    int max_del = d2i_scala((double)(qlen * mmax + end_bonus - o_del) / (double)e_del + 1.0);
+    if (max_del < 1) max_del = 1;
+    if (w > max_del) w = max_del;
+
+    /* DP (:117-220) */
+    int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+    int beg = 0, end = qlen;
+    for (int i = 0; i < tlen; ++i) {
+        const int8_t *srow = prof + (size_t)target[i] * qlen;
+        int f = 0, rm = 0, rmj = -1;
+        int h1 = h0 - (o_del + e_del * (i + 1));       /* first column (:137-138) */
+        if (h1 < 0) h1 = 0;
+        if (beg < i - w) beg = i - w;                  /* band (:140-142) */
+        if (end > i + w + 1) end = i + w + 1;
+        if (end > qlen) end = qlen;
+
+        int j = beg;
+        for (; j < end; ++j) {                         /* cell update (:151-171) */
+            int h = H[j] + srow[j];
+            int e = E[j];
+            H[j] = h1;
+            if (h < e) h = e;
+            if (h < f) h = f;
+            h1 = h;
+            if (rm <= h) { rmj = j; rm = h; }           /* last j wins ties (:158) */
+            int t = h - oe_del; if (t < 0) t = 0;
+            e -= e_del;         if (e < t) e = t;
+            E[j] = e;
+            t = h - oe_ins;     if (t < 0) t = 0;
+            f -= e_ins;         if (f < t) f = t;
+            ++cells;
+        }
+        H[end] = h1; E[end] = 0;                       /* (:174-175) */
+        /* j is the loop variable: == end if the loop ran, == beg otherwise (:177) */
+        if (j == qlen && gscore <= h1) { best_ie = i; gscore = h1; }
+
+        if (rm == 0) break;                            /* (:184) */
+        if (rm > best) {
+            best = rm; best_i = i; best_j = rmj;
+            int off = rmj - i; if (off < 0) off = -off;
+            if (max_off < off) max_off = off;
+        } else if (zdrop > 0) {
+            /* QUIRK (:194-199): the Scala `else` binds to the INNER if, so the
+             * e_ins test is only reached when di > dj, and there is no test at
+             * all when di <= dj.  (C ksw_extend2 differs, N/ksw.c:455-461.) */
+            int di = i - best_i, dj = rmj - best_j;
+            if (di > dj) {
+                if (best - rm - (di - dj) * e_del > zdrop) break;
+                else if (best - rm - (dj - di) * e_ins > zdrop) break;
+            }
+        }
+        /* band shrink for the next row (:202-214) */
+        j = rmj;
+        while (j >= beg && H[j] > 0) --j;
+        beg = j + 1;
+        j = rmj + 2;
+        while (j <= end && H[j] > 0) ++j;
+        end = j;
+    }
+
+    out->score = best;
+    out->qle = best_j + 1;
+    out->tle = best_i + 1;
+    out->gtle = best_ie + 1;
+    out->gscore = gscore;
+    out->max_off = max_off;
+    out->cells = cells;
+    free(H); free(E); free(prof);
+}
+
+/* ------------------------------------------------------------------------- */
+/* extension()  (S/worker1/MemChainToAlignBatched.scala:789-883)              */
+/* ------------------------------------------------------------------------- */
+#define ORC_MAX_BAND_TRY 2 /* :50 */
+
+void orc_extension(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r)
+{
+    int aw0 = opt->w, aw1 = opt->w;
+    int reg_score = t->reg_score;
+    orc_ext_t x;
+    memset(&x, 0, sizeof x);
+    x.qle = x.tle = x.gtle = x.gscore = x.max_off = -1;
+
+    r->q_beg = 0; r->r_beg = 0; r->q_end = t->right_qlen; r->r_end = 0;
+    r->score = -1;                  /* ExtRet default, ExtensionParameters.scala:84 */
+    r->true_score = t->reg_score;
+    r->cells = 0; r->n_calls = 0;
+
+    if (t->left_qlen > 0) {         /* :809-842 */
+        for (int i = 0; i < ORC_MAX_BAND_TRY; ++i) {
+            int prev = reg_score;
+            aw0 = opt->w << i;
+            orc_sw_extend(t->left_qlen, t->left_q, t->left_rlen, t->left_r, 5, opt->mat,
+                          opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, aw0,
+                          opt->pen_clip5, opt->zdrop, t->h0, &x);
+            r->cells += x.cells; r->n_calls++;
+            reg_score = x.score;
+            if (reg_score == prev || x.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
+        }
+        r->score = reg_score;
+        if (x.gscore <= 0 || x.gscore <= reg_score - opt->pen_clip5) { /* local */
+            r->q_beg = t->q_beg - x.qle; r->r_beg = -x.tle; r->true_score = reg_score;
+        } else {                                                       /* to-end */
+            r->q_beg = 0; r->r_beg = -x.gtle; r->true_score = x.gscore;
+        }
+    }
+    if (t->right_qlen > 0) {        /* :844-876 */
+        const int sc0 = reg_score;
+        for (int i = 0; i < ORC_MAX_BAND_TRY; ++i) {
+            int prev = reg_score;
+            aw1 = opt->w << i;
+            orc_sw_extend(t->right_qlen, t->right_q, t->right_rlen, t->right_r, 5, opt->mat,
+                          opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, aw1,
+                          opt->pen_clip3, opt->zdrop, sc0, &x);
+            r->cells += x.cells; r->n_calls++;
+            reg_score = x.score;
+            if (reg_score == prev || x.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
+        }
+        r->score = reg_score;
+        if (x.gscore <= 0 || x.gscore <= reg_score - opt->pen_clip3) {
+            r->q_end = x.qle; r->r_end = x.tle; r->true_score += reg_score - sc0;
+        } else {
+            r->q_end = t->right_qlen; r->r_end = x.gtle; r->true_score += x.gscore - sc0;
+        }
+    }
+    r->width = aw0 > aw1 ? aw0 : aw1; /* :877-878 */
+    r->idx = t->idx;
+}
+
+/* ------------------------------------------------------------------------- */
+/* SWAlign  (S/util/SWUtil.scala:417-570)                                     */
+/* ------------------------------------------------------------------------- */
+#define ORC_MINUS_INF (-0x40000000) /* SWUtil.scala:28 */
+
+void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  int m, const orc_opt_t *opt, int xtra, orc_aln_t *out)
+{
+    const int oe_del = opt->o_del + opt->e_del, oe_ins = opt->o_ins + opt->e_ins;
+    const int e_del = opt->e_del, e_ins = opt->e_ins;
+    const int sat = 255 - abs(opt->b);                  /* maxScore (:423) */
+    const int qmax = opt->a;                            /* (:424) */
+    const int min_sc = (xtra & ORC_XSUBO) ? (xtra & 0xffff) : 0x10000; /* (:434-435) */
+    const int end_sc = (xtra & ORC_XSTOP) ? (xtra & 0xffff) : 0x10000; /* (:436-437) */
+    const int qn = qlen > 0 ? qlen : 0;
+
+    int32_t *H = (int32_t *)calloc((size_t)qn + 1, sizeof(int32_t));
+    int32_t *E = (int32_t *)calloc((size_t)qn + 1, sizeof(int32_t));
+    int8_t *prof = (int8_t *)malloc(((size_t)qn + 1) * (size_t)m);
+    int32_t *bsc = (int32_t *)malloc(((size_t)(tlen > 0 ? tlen : 0) + 1) * sizeof(int32_t));
+    int32_t *bte = (int32_t *)malloc(((size_t)(tlen > 0 ? tlen : 0) + 1) * sizeof(int32_t));
+    int nb = 0;
+    int64_t cells = 0;
+
+    for (int k = 0; k < m; ++k)                         /* profile (:446-461) */
+        for (int j = 0; j < qn; ++j) prof[(size_t)k * qn + j] = opt->mat[k * m + query[j]];
+
+    int best = ORC_MINUS_INF, best_i = -1, best_j = -1;
+    for (int i = 0; i < tlen; ++i) {                    /* (:469-542) */
+        const int8_t *srow = prof + (size_t)target[i] * qn;
+        int f = 0, h1 = 0, rm = 0, rmj = -1;
+        for (int j = 0; j < qn; ++j) {                  /* (:484-505) */
+            int h = H[j] + srow[j];
+            int e = E[j];
+            H[j] = h1;
+            if (h < e) h = e;
+            if (h < f) h = f;
+            h1 = h;
+            if (rm < h) { rmj = j; rm = h; }            /* first j wins ties (:493) */
+            int t = h - oe_del; if (t < 0) t = 0;
+            e -= e_del;         if (e < t) e = t;
+            E[j] = e;
+            t = h - oe_ins;     if (t < 0) t = 0;
+            f -= e_ins;         if (f < t) f = t;
+        }
+        cells += qn;
+        if (rm >= min_sc) {                             /* b-array (:517-529) */
+            if (nb == 0 || bte[nb - 1] + 1 != i) { bsc[nb] = rm; bte[nb] = i; ++nb; }
+            else if (bsc[nb - 1] < rm) { bsc[nb - 1] = rm; bte[nb - 1] = i; }
+        }
+        if (rm > best) {                                /* (:532-538) */
+            best = rm; best_i = i; best_j = rmj;
+            if (best >= end_sc || best >= sat) break;
+        }
+    }
+    if (best >= sat) best = 255;                        /* QUIRK: no 16-bit fallback (:544) */
+
+    out->score = best; out->te = best_i;
+    out->qe = -1; out->score2 = -1; out->te2 = -1; out->tb = -1; out->qb = -1;
+    if (best != 255) {                                  /* (:549-567) */
+        out->qe = best_j;
+        if (nb > 0) {
+            int tmp = (best + qmax - 1) / qmax;
+            int low = best_i - tmp, high = best_i + tmp;
+            for (int k = 0; k < nb; ++k)
+                if ((bte[k] < low || bte[k] > high) && bsc[k] > out->score2) {
+                    out->score2 = bsc[k]; out->te2 = bte[k];
+                }
+        }
+    }
+    out->cells = cells;
+    free(H); free(E); free(prof); free(bsc); free(bte);
+}
+
+static void flip(int n, uint8_t *s)                     /* revSeq (:572-581) */
+{
+    for (int i = 0; i < (n >> 1); ++i) { uint8_t c = s[i]; s[i] = s[n - 1 - i]; s[n - 1 - i] = c; }
+}
+
+/* SWAlign2  (S/util/SWUtil.scala:583-601) */
+void orc_sw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target,
+                   int m, const orc_opt_t *opt, int xtra, orc_aln_t *out)
+{
+    orc_sw_align(qlen, query, tlen, target, m, opt, xtra, out);
+    if ((xtra & ORC_XSTART) == 0 || ((xtra & ORC_XSUBO) && out->score < (xtra & 0xffff))) return;
+    orc_aln_t rev;
+    flip(out->qe + 1, query);
+    flip(out->te + 1, target);
+    /* QUIRK: the reverse pass keeps the FULL tlen (:590) */
+    orc_sw_align(out->qe + 1, query, tlen, target, m, opt, ORC_XSTOP | out->score, &rev);
+    flip(out->qe + 1, query);
+    flip(out->te + 1, target);
+    out->cells += rev.cells;
+    if (out->score == rev.score) { out->tb = out->te - rev.te; out->qb = out->qe - rev.qe; }
+}
+
+/* ------------------------------------------------------------------------- */
+/* tiny pthread parallel-for (this image has no libgomp)                      */
+/* ------------------------------------------------------------------------- */
+typedef void (*orc_body_fn)(int32_t k, void *ctx);
+typedef struct { orc_body_fn fn; void *ctx; int32_t n, chunk; volatile int32_t next; } orc_pf_t;
+
+static void *orc_pf_worker(void *arg)
+{
+    orc_pf_t *pf = (orc_pf_t *)arg;
+    for (;;) {
+        int32_t s = __sync_fetch_and_add(&pf->next, pf->chunk);
+        if (s >= pf->n) break;
+        int32_t e = s + pf->chunk < pf->n ? s + pf->chunk : pf->n;
+        for (int32_t k = s; k < e; ++k) pf->fn(k, pf->ctx);
+    }
+    return NULL;
+}
+
+static void orc_parallel_for(int32_t n, int n_threads, int32_t chunk, orc_body_fn fn, void *ctx)
+{
+    orc_pf_t pf = { fn, ctx, n, chunk < 1 ? 1 : chunk, 0 };
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads <= 1 || n <= pf.chunk) { for (int32_t k = 0; k < n; ++k) fn(k, ctx); return; }
+    pthread_t th[256];
+    int started = 0;
+    for (int i = 0; i < n_threads - 1; ++i)
+        if (pthread_create(&th[started], NULL, orc_pf_worker, &pf) == 0) ++started;
+    orc_pf_worker(&pf);
+    for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Seam drivers                                                               */
+/* ------------------------------------------------------------------------- */
+static inline int16_t rd16(const uint8_t *p) { return (int16_t)(p[0] | (p[1] << 8)); }
+static inline int32_t rd32(const uint8_t *p)
+{
+    return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+}
+
+/* nibble n of the block starting at word `pos`: 8 per int32, first base in the
+ * most significant nibble, word little-endian (MemChainToAlignBatched.scala:63-69,130-131) */
+static inline uint8_t nib(const uint8_t *buf, int32_t pos, int n)
+{
+    uint32_t wv = (uint32_t)rd32(buf + ((size_t)pos + (size_t)(n >> 3)) * 4);
+    return (uint8_t)((wv >> (28 - 4 * (n & 7))) & 0xf);
+}
+
+int orc_max_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (int)n;
+}
+
+typedef struct {
+    const uint8_t *in; int32_t in_bytes; int16_t *out; int64_t *cells; int32_t *calls;
+    orc_opt_t opt; volatile int err;
+} orc_ew_ctx;
+
+static void orc_ew_body(int32_t k, void *vctx)
+{
+    orc_ew_ctx *c = (orc_ew_ctx *)vctx;
+    const uint8_t *in = c->in;
+    const uint8_t *rec = in + 32 + (size_t)32 * k;
+    orc_task_t t;
+    t.left_qlen = rd16(rec + 0); t.left_rlen = rd16(rec + 2);
+    t.right_qlen = rd16(rec + 4); t.right_rlen = rd16(rec + 6);
+    const int32_t pos = rd32(rec + 8);
+    t.reg_score = rd16(rec + 12); t.q_beg = rd16(rec + 14);
+    t.h0 = rd16(rec + 16);
+    t.idx = rd32(rec + 28);
+    const int tot = t.left_qlen + t.left_rlen + t.right_qlen + t.right_rlen;
+    if (t.left_qlen < 0 || t.left_rlen < 0 || t.right_qlen < 0 || t.right_rlen < 0 ||
+        pos < 8 || ((int64_t)pos + (((tot + 1) / 2) + 3) / 4) * 4 > c->in_bytes) {
+        c->err = -4;
+        return;
+    }
+    uint8_t *seq = (uint8_t *)malloc((size_t)tot + 4);
+    for (int q = 0; q < tot; ++q) seq[q] = nib(in, pos, q);
+    /* segment order on the wire: leftQ, rightQ, leftR, rightR (:125-161) */
+    t.left_q = seq;
+    t.right_q = seq + t.left_qlen;
+    t.left_r = t.right_q + t.right_qlen;
+    t.right_r = t.left_r + t.left_rlen;
+    orc_extret_t r;
+    orc_extension(&t, &c->opt, &r);
+    int16_t *o = c->out + (size_t)10 * k;    /* reply layout (:178-190) */
+    o[0] = (int16_t)(r.idx & 0xffff); o[1] = (int16_t)((uint32_t)r.idx >> 16);
+    o[2] = (int16_t)r.q_beg; o[3] = (int16_t)r.q_end;
+    o[4] = (int16_t)r.r_beg; o[5] = (int16_t)r.r_end;
+    o[6] = (int16_t)r.score; o[7] = (int16_t)r.true_score;
+    o[8] = (int16_t)r.width; o[9] = 0;
+    if (c->cells) c->cells[k] = r.cells;
+    if (c->calls) c->calls[k] = r.n_calls;
+    free(seq);
+}
+
+int orc_extend_wire(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
+                    int64_t *cells_per_task, int32_t *calls_per_task, int n_threads)
+{
+    if (!in || in_bytes < 32) return -1;
+    orc_ew_ctx c;
+    c.in = in; c.in_bytes = in_bytes; c.out = out; c.cells = cells_per_task; c.calls = calls_per_task;
+    c.err = 0;
+    orc_default_opt(&c.opt);                 /* zdrop and mat are NOT on the wire */
+    c.opt.o_del = in[0]; c.opt.e_del = in[1]; c.opt.o_ins = in[2]; c.opt.e_ins = in[3];
+    c.opt.pen_clip5 = in[4]; c.opt.pen_clip3 = in[5]; c.opt.w = in[6];
+    if (in[7] & 1) c.opt.zdrop = rd16(in + 12); /* optional extension, see include/csbwa_sw.h */
+    const int32_t n = rd32(in + 8);
+    if (n < 0 || (int64_t)32 + (int64_t)32 * n > in_bytes) return -2;
+    if (out_shorts < 10 * n) return -3;
+    orc_parallel_for(n, n_threads, 64, orc_ew_body, &c);
+    return c.err;
+}
+
+typedef struct {
+    const orc_job_t *jobs; const uint8_t *seqs; int32_t *out7; int64_t *cells; orc_opt_t opt;
+} orc_al_ctx;
+
+static void orc_al_body(int32_t k, void *vctx)
+{
+    orc_al_ctx *c = (orc_al_ctx *)vctx;
+    const orc_job_t *jb = &c->jobs[k];
+    uint8_t *q = (uint8_t *)malloc((size_t)jb->q_len + 1);
+    uint8_t *t = (uint8_t *)malloc((size_t)jb->t_len + 1);
+    memcpy(q, c->seqs + jb->q_off, (size_t)jb->q_len);
+    memcpy(t, c->seqs + jb->t_off, (size_t)jb->t_len);
+    orc_aln_t a;
+    orc_sw_align2(jb->q_len, q, jb->t_len, t, 5, &c->opt, jb->xtra, &a);
+    int32_t *o = c->out7 + (size_t)7 * k;
+    o[0] = a.score; o[1] = a.te; o[2] = a.qe; o[3] = a.score2; o[4] = a.te2; o[5] = a.tb; o[6] = a.qb;
+    if (c->cells) c->cells[k] = a.cells;
+    free(q); free(t);
+}
+
+int orc_align2_batch(const orc_job_t *jobs, int32_t n_jobs, const uint8_t *seqs,
+                     int32_t *out7, int64_t *cells_per_job, int n_threads)
+{
+    if (n_jobs < 0) return -1;
+    orc_al_ctx c;
+    c.jobs = jobs; c.seqs = seqs; c.out7 = out7; c.cells = cells_per_job;
+    orc_default_opt(&c.opt);
+    orc_parallel_for(n_jobs, n_threads, 4, orc_al_body, &c);
+    return 0;
+}

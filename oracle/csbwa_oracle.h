@@ -1,0 +1,110 @@
+/*
+ * csbwa_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Scalar C restatement of the *Scala* semantics of CS-BWAMEM's Smith-Waterman
+ * hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may link or call this.  The product library
+ * (libcsbwa_sw.so) never does.
+ *
+ * Parity pinning: the reference ships NO golden vectors / unit tests for this
+ * path, and its Scala truth cannot run here (no JVM).
+ * The restatement is therefore pinned against the reference's own bundled C
+ * (src/main/native/ksw.c, compiled out-of-tree into oracle/_ref/ by
+ * oracle/Makefile) in the regimes where Scala and C provably agree
+ * (zdrop<=0 for extension; qlen*a<250 for align2) -- see tests/test_oracle_vs_ref.py.
+ * Where Scala and C differ (the z-drop dangling else), the Scala text wins.
+ *
+ * Reference citations use S/ = src/main/scala/cs/ucla/edu/bwaspark/.
+ */
+#ifndef CSBWA_ORACLE_H
+#define CSBWA_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* KSW_X* flags, S/util/SWUtil.scala:29-32 */
+#define ORC_XBYTE  0x10000
+#define ORC_XSTOP  0x20000
+#define ORC_XSUBO  0x40000
+#define ORC_XSTART 0x80000
+
+/* scoring / option block: the subset of MemOptType (S/datatype/MemOptType.scala:28-56)
+ * the path reads. */
+typedef struct {
+    int32_t a, b;               /* match score, mismatch penalty (for SWAlign maxScore/qMax) */
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t pen_clip5, pen_clip3;
+    int32_t w, zdrop;
+    int8_t  mat[25];            /* 5x5 */
+} orc_opt_t;
+
+/* default options + bwaFillScmat (S/datatype/MemOptType.scala:58-75) */
+void orc_default_opt(orc_opt_t *o);
+
+/* SWExtend result: retArray(0..5) of S/util/SWUtil.scala:222-227 + exact cell count */
+typedef struct {
+    int32_t score, qle, tle, gtle, gscore, max_off;
+    int64_t cells;              /* number of inner-loop bodies executed (SWUtil.scala:151-171) */
+} orc_ext_t;
+
+void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                   int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                   int w, int end_bonus, int zdrop, int h0, orc_ext_t *out);
+
+/* One extension task = ExtParam (S/datatype/ExtensionParameters.scala:21-46) */
+typedef struct {
+    const uint8_t *left_q, *left_r, *right_q, *right_r; /* left_* already reversed by the caller */
+    int32_t left_qlen, left_rlen, right_qlen, right_rlen;
+    int32_t h0, reg_score, q_beg, idx;
+} orc_task_t;
+
+/* ExtRet (S/datatype/ExtensionParameters.scala:79-87) + stats */
+typedef struct {
+    int32_t q_beg, r_beg, q_end, r_end, score, true_score, width, idx;
+    int64_t cells;
+    int32_t n_calls;            /* SWExtend invocations incl. band retries */
+} orc_extret_t;
+
+/* S/worker1/MemChainToAlignBatched.scala:789-883 */
+void orc_extension(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r);
+
+/* SWAlnType (S/datatype/SWAlnType.scala:21-29) */
+typedef struct {
+    int32_t score, te, qe, score2, te2, tb, qb;
+    int64_t cells;
+} orc_aln_t;
+
+/* S/util/SWUtil.scala:417-570 ; read-only on query/target */
+void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  int m, const orc_opt_t *opt, int xtra, orc_aln_t *out);
+/* S/util/SWUtil.scala:583-601 ; reverses in place and restores, like the Scala */
+void orc_sw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target,
+                   int m, const orc_opt_t *opt, int xtra, orc_aln_t *out);
+
+/* ---- batch drivers over the two seam formats (same bytes the product consumes) ---- */
+
+/* Decode the runOnFPGAJNI byte buffer (S/worker1/MemChainToAlignBatched.scala:76-172),
+ * run orc_extension per task with n_threads OpenMP threads, encode the short[] reply
+ * (:178-190).  cells_per_task / calls_per_task may be NULL.  Returns 0 or <0. */
+int orc_extend_wire(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
+                    int64_t *cells_per_task, int32_t *calls_per_task, int n_threads);
+
+/* flat mate-SW job (same layout as csbwa_job in include/csbwa_sw.h) */
+typedef struct {
+    int64_t q_off, t_off;       /* byte offsets into seqs[] (1 base per byte, codes 0..4) */
+    int32_t q_len, t_len;
+    int32_t xtra, pad;
+} orc_job_t;
+
+int orc_align2_batch(const orc_job_t *jobs, int32_t n_jobs, const uint8_t *seqs,
+                     int32_t *out7 /* n_jobs x {score,te,qe,score2,te2,tb,qb} */,
+                     int64_t *cells_per_job, int n_threads);
+
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,161 @@
+// tests/emu/emu.cu -- TEST INFRASTRUCTURE.  Runs the product's host+device algorithm cores
+// (csrc/ext_core.cuh, csrc/aln_core.cuh: the very functions the CUDA kernels call) on the CPU,
+// with the kernels' per-task dispatch (bin -> fast/generic core) and the warp systolic
+// schedule of k_aln_warp restated as plain loops over lanes.  It exists so that parity bugs
+// in the cores are found here, without a GPU; it is never part of the product path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#define CSBWA_E_BADWIRE_DEV (-3)
+#include "../../cloud-scale-bwamem_b200/csrc/ext_kernels.cuh"
+#include "../../cloud-scale-bwamem_b200/csrc/aln_kernels.cuh"
+
+using namespace csw;
+
+extern "C" int emu_extend_wire(const uint8_t *in, int in_bytes, int16_t *out, int64_t *cells_per_task,
+                               int32_t *fast_sides, int force_generic)
+{
+    SwOpt o;
+    ext_parse_header(in, o);
+    int n;
+    memcpy(&n, in + 8, 4);
+    const int stride = 4;   // any stride works on the host
+    std::vector<uint32_t> col;
+    std::vector<int> HE;
+    int nfast = 0;
+    for (int k = 0; k < n; ++k) {
+        ExtTask t = read_task(in, k);
+        if (!ext_task_ok(t, n, in_bytes)) return -3;
+        int bl = ext_side_bin(o, t.lq, t.h0);
+        const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
+        int br = ext_side_bin(o, t.rq, h0r);
+        if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+        if (force_generic) { if (bl) bl = 256; if (br) br = 256; }
+        const uint32_t *words = (const uint32_t *)in + t.pos;
+        const int qm = t.lq > t.rq ? t.lq : t.rq;
+        col.assign((size_t)(qm + 2) * stride, 0xdeadbeefu);
+        HE.assign((size_t)2 * (qm + 2), -12345);
+        int *H = HE.data(), *E = HE.data() + (qm + 2);
+        SideRes L, R;
+        memset(&L, 0, sizeof L); memset(&R, 0, sizeof R);
+        L.aw = R.aw = (int16_t)o.w;
+        int64_t cells = 0;
+        if (bl) {
+            if (bl != 256) { ext_run_side<true>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, col.data(), stride, H, E, L); ++nfast; }
+            else ext_run_side<false>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, col.data(), stride, H, E, L);
+            cells += L.cells;
+        }
+        if (t.rq > 0) {
+            const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
+            if (br != 256) { ext_run_side<true>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, col.data(), stride, H, E, R); ++nfast; }
+            else ext_run_side<false>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, col.data(), stride, H, E, R);
+            cells += R.cells;
+        }
+        ext_finalize(o, t, &L, &R, out + (size_t)10 * k);
+        if (cells_per_task) cells_per_task[k] = cells;
+    }
+    if (fast_sides) *fast_sides = nfast;
+    return 0;
+}
+
+template <int C>
+static void emu_warp_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, int qn, int tlen, bool rev,
+                          int qe, int te, int xtra, int *bsc, int *bte, AlnBook &bk, int &rows_done)
+{
+    AlnLane<C> L[32];
+    for (int l = 0; l < 32; ++l) L[l].setup(o, q, qn, rev, qe, l);
+    bk.init(o, xtra);
+    AlnMsg out[32], nout[32];
+    memset(out, 0, sizeof out);
+    const int LQ = (qn - 1) / C;
+    rows_done = 0;
+    for (int s = 0; s < tlen + LQ; ++s) {
+        for (int l = 0; l < 32; ++l) {
+            AlnMsg in;
+            if (l == 0) {
+                int t0 = s < tlen ? t[aln_tidx(rev, te, s)] : 0;
+                if (t0 > 4) t0 = 4;
+                in.h = 0; in.ft = t0 << 16; in.key = 0;
+            } else in = out[l - 1];
+            nout[l] = out[l];
+            const int row = s - l;
+            if (row >= 0 && row < tlen && l <= LQ) {
+                L[l].step(o, in, nout[l]);
+                if (l == LQ) {
+                    int m, mj;
+                    aln_decode_key(nout[l].key, m, mj);
+                    bk.row(row, m, mj, bsc, bte);
+                    rows_done = row + 1;
+                }
+            }
+        }
+        memcpy(out, nout, sizeof out);
+        if (bk.stop) break;
+    }
+}
+
+template <int C>
+static long long emu_align2_warp(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int xtra, AlnRes &r)
+{
+    std::vector<int> b((size_t)2 * (tlen / 2 + 2));
+    int *bsc = b.data(), *bte = b.data() + (tlen / 2 + 2);
+    AlnBook bk;
+    int rows = 0;
+    emu_warp_pass<C>(o, q, t, qlen, tlen, false, 0, 0, xtra, bsc, bte, bk, rows);
+    aln_finish_head(bk, r);
+    aln_second_best_serial(o, bk, bsc, bte, r);
+    long long cells = (long long)qlen * rows;
+    if (!((xtra & XSTART) == 0 || ((xtra & XSUBO) && r.score < (xtra & 0xffff)))) {
+        AlnRes rr;
+        const int qn2 = r.qe + 1;
+        if (qn2 >= 1) {
+            AlnBook bk2;
+            int rows2 = 0;
+            emu_warp_pass<C>(o, q, t, qn2, tlen, true, r.qe, r.te, XSTOP | r.score, bsc, bte, bk2, rows2);
+            aln_finish_head(bk2, rr);
+            cells += (long long)qn2 * rows2;
+        } else {
+            AlnBook bk2;
+            bk2.init(o, XSTOP | r.score);
+            if (tlen > 0) { bk2.best = 0; bk2.best_i = 0; bk2.best_j = -1; }
+            aln_finish_head(bk2, rr);
+        }
+        if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    }
+    return cells;
+}
+
+extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, int32_t *out7, int64_t *cells,
+                                int32_t *n_fast, int force_generic)
+{
+    SwOpt o;
+    fill_default_opt(o);
+    finish_opt(o);
+    int nf = 0;
+    for (int k = 0; k < n; ++k) {
+        const AlnJob &jb = jobs[k];
+        const uint8_t *q = seqs + jb.q_off, *t = seqs + jb.t_off;
+        int cls = aln_class_of(o, jb.q_len, jb.t_len);
+        if (force_generic) cls = 0;
+        AlnRes r;
+        long long c = 0;
+        if (cls == 0) {
+            const int qn = jb.q_len > 0 ? jb.q_len : 0, tn = jb.t_len > 0 ? jb.t_len : 0;
+            std::vector<int> buf((size_t)2 * (tn / 2 + 2) + 2 * (qn + 2));
+            int *bsc = buf.data(), *bte = bsc + (tn / 2 + 2), *H = bte + (tn / 2 + 2), *E = H + (qn + 2);
+            c = sw_align2_generic(o, q, qn, t, tn, jb.xtra, H, E, bsc, bte, r);
+        } else {
+            ++nf;
+            if (cls == 1) c = emu_align2_warp<8>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else if (cls == 2) c = emu_align2_warp<5>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else if (cls == 3) c = emu_align2_warp<4>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else c = emu_align2_warp<2>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+        }
+        int32_t *o7 = out7 + (size_t)7 * k;
+        o7[0] = r.score; o7[1] = r.te; o7[2] = r.qe; o7[3] = r.score2; o7[4] = r.te2; o7[5] = r.tb; o7[6] = r.qb;
+        if (cells) cells[k] = c;
+    }
+    if (n_fast) *n_fast = nf;
+    return 0;
+}
