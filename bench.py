@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 SW hot path (driver contract in the task brief).
+
+Workload (BASELINE.json configs[1]): pair-end 1M x 2 reads of 151 bp simulated from
+a 100 Mbp synthetic reference (eps = 1 %, insert N(400, 50)); seed-extension tasks for the longest
+seed of every read, one seam call per 4096 reads (-bSWExtSize 4096).  One "step" = one pass of the
+batched-extension hot path over ALL seam calls of the rank's shard.
+
+  value : GCUPS, whole job, inputs resident in HBM, CUDA-event timed (exact DP cells counted by
+          the kernels, checked against the oracle on the cpu_baseline sample)
+  e2e   : same metric through the reference-facing C ABI (csbwa_extend_batch) with HOST buffers,
+          H2D / D2H inside the timed region, several caller threads like Spark task threads
+  N > 1 : weak scaling -- every rank owns a full shard (its own 1M pairs), no collective on the
+          data path (reads shard naturally); time = max over ranks.
+
+`--impl reference` times the reference's own CPU implementation of the path (its bwa-0.7.8 C
+ksw_extend2, compiled from /root/reference into oracle/_ref, driven with the extension() control
+flow; the oracle port when _ref is absent) on all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OPS_PER_CELL = 13          # BASELINE.md section 2 / SURVEY.md 8(d)
+READS_PER_CALL = 4096
+CFG = dict(L=151, ref_bp=100_000_000, eps=0.01, mu=400, sigma=50, seed=20260103)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def task_count(buf):
+    return int(np.frombuffer(buf[8:12].tobytes(), dtype="<i4")[0])
+
+
+def gen_workload(pkg, n_pairs, rank, ref=None):
+    return pkg.workload.ext_workload(n_pairs, CFG["L"], CFG["ref_bp"], CFG["eps"], CFG["mu"], CFG["sigma"],
+                                     CFG["seed"] + 1000 * rank, reads_per_call=READS_PER_CALL, ref=ref)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        for line in open(self.f.name):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 9:
+                rows.append(parts)
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in rows:
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        out.update(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(rows[0][2]) if rows[0][2].isdigit() else None,
+                   reasons=sorted(reasons), samples=len(rows),
+                   power_w_max=max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit()) if rows else None)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY places that execute oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_extension_run(bufs, n_threads, use_ref):
+    """Time the CPU implementation over the given seam calls.  Returns (seconds, kind):
+    kind "reference" = the reference's compiled ksw_extend2 (oracle/_ref) under the extension()
+    control flow, "port" = the oracle's restatement of the Scala."""
+    from oracle import oracle as O
+    kind = "reference" if (use_ref and O.ref_available()) else "port"
+    t0 = time.perf_counter()
+    for b in bufs:
+        if kind == "reference":
+            O.extend_wire_ref(b, n_threads=n_threads)
+        else:
+            O.extend_wire(b, n_threads=n_threads, want_stats=False)
+    return time.perf_counter() - t0, kind
+
+
+def count_cells(bufs, n_threads):
+    """Exact DP cells of the given calls, counted by the oracle (untimed)."""
+    from oracle import oracle as O
+    return sum(int(O.extend_wire(b, n_threads=n_threads)[1].sum()) for b in bufs)
+
+
+def size_cpu_sample(bufs, n_threads, use_ref, target_s):
+    """Pick how many seam calls make ~target_s seconds of CPU work (calibrated on the first call)."""
+    dt, _ = cpu_extension_run(bufs[:1], n_threads, use_ref)
+    n = int(max(1, min(len(bufs), round(target_s / max(dt, 1e-4)))))
+    return n
+
+
+def run_reference_arm(args, pkg):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_pairs = min(args.pairs, 262144)
+    w = gen_workload(pkg, n_pairs, 0)
+    n_calls = size_cpu_sample(w["bufs"], cores, True, args.cpu_step_seconds)
+    sample = w["bufs"][:n_calls]
+    for _ in range(args.warmup):
+        cpu_extension_run(sample[:max(1, n_calls // 4)], cores, True)
+    cells_sample = count_cells(sample, cores)
+    t_total, cells_total, kind = 0.0, 0, "port"
+    for _ in range(args.steps):
+        dt, kind = cpu_extension_run(sample, cores, True)
+        t_total += dt
+        cells_total += cells_sample
+    gcups = cells_total / t_total / 1e9
+    n_tasks = sum(task_count(b) for b in sample)
+    line = {
+        "impl": "reference", "metric": "seed-extension SW throughput (whole job)", "value": gcups, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": config_block(args, n_pairs),
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
+                         "sample": "%d seam calls (%d tasks) of the C2 workload per step" % (n_calls, n_tasks)},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "read_pairs_per_s": (n_calls * READS_PER_CALL / 2) / (t_total / args.steps),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_block(args, n_pairs):
+    return {"workload": "C2: pair-end %dx2 %d bp reads vs %d Mbp synthetic reference, eps=%.2f, seed extension, "
+                        "%d reads per seam call" % (n_pairs, CFG["L"], CFG["ref_bp"] // 1000000, CFG["eps"], READS_PER_CALL),
+            "pairs_per_gpu": n_pairs, "reads_per_call": READS_PER_CALL,
+            "l2_policy": "inputs larger than L2 (all seam-call buffers of the shard stay resident, > 126 MB)",
+            "parallelism": "reads sharded per GPU, no collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU")
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--threads", type=int, default=0, help="caller threads of the e2e leg (0 = auto)")
+    ap.add_argument("--cpu-step-seconds", type=float, default=6.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    pkg = importlib.import_module("cloud-scale-bwamem_b200")
+    if args.impl == "reference":
+        run_reference_arm(args, pkg)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = pkg.lib()
+    if L.csbwa_init(0) < 1:
+        raise SystemExit("csbwa_init failed: " + L.csbwa_last_error().decode())
+
+    # ---- workload (untimed) ----
+    w = gen_workload(pkg, args.pairs, rank)
+    bufs = w["bufs"]
+    ntasks = [task_count(b) for b in bufs]
+    total_tasks = sum(ntasks)
+    in_bytes = sum(b.size for b in bufs)
+    out_bytes = 20 * total_tasks
+
+    # ---- device-resident state ----
+    offs, pos = [], 0
+    for b in bufs:
+        offs.append(pos)
+        pos += (b.size + 255) & ~255
+    d_in = torch.empty(pos, dtype=torch.uint8, device=dev)
+    for b, o in zip(bufs, offs):
+        d_in[o:o + b.size].copy_(torch.from_numpy(b))
+    ooffs = np.concatenate([[0], np.cumsum([10 * n for n in ntasks])]).astype(np.int64)
+    d_out = torch.zeros(int(ooffs[-1]), dtype=torch.int16, device=dev)
+    d_cells = torch.zeros(1, dtype=torch.int64, device=dev)
+    nstreams = max(1, args.streams)
+    scr_bytes = max(L.csbwa_extend_scratch_bytes(n, b.size) for n, b in zip(ntasks, bufs))
+    scratch = [torch.empty(scr_bytes, dtype=torch.uint8, device=dev) for _ in range(nstreams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+    main_stream = torch.cuda.current_stream()
+
+    def enqueue_step(main_stream):
+        """All seam calls of the shard, round-robin over the streams (fork/join on main_stream)."""
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        for s in streams:
+            s.wait_event(fork)
+        for i, (b, n) in enumerate(zip(bufs, ntasks)):
+            s = streams[i % nstreams]
+            rc = L.csbwa_extend_batch_device(d_in.data_ptr() + offs[i], b.size, n,
+                                             d_out.data_ptr() + 2 * int(ooffs[i]), d_cells.data_ptr(),
+                                             scratch[i % nstreams].data_ptr(), scr_bytes, C.c_void_p(s.cuda_stream))
+            if rc != 0:
+                raise RuntimeError("csbwa_extend_batch_device: %d %s" % (rc, L.csbwa_last_error().decode()))
+        for s in streams:
+            j = torch.cuda.Event()
+            j.record(s)
+            main_stream.wait_event(j)
+
+    # warm-up (also sets kernel attributes before any capture)
+    enqueue_step(main_stream)
+    torch.cuda.synchronize()
+    cells_per_step = int(d_cells.item())
+    graph = None
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.graph(g, stream=cap_stream):
+                enqueue_step(torch.cuda.current_stream())
+            graph = g
+        except Exception as e:   # capture unsupported -> plain launches
+            graph = None
+            sys.stderr.write("bench: CUDA graph capture failed (%s); using direct launches\n" % e)
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            enqueue_step(main_stream)
+
+    for _ in range(args.warmup - 1):
+        run_step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = pkg.stats()["kernel_launches"]
+    d_cells.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    cells_total = int(d_cells.item())
+    assert cells_total == cells_per_step * args.steps, (cells_total, cells_per_step)
+    kernels_per_step = len(bufs) * L.csbwa_extend_launches_per_call()
+    result_dev = d_out.cpu().numpy()
+
+    # ---- e2e through the C ABI with host buffers ----
+    nthreads = args.threads or max(2, min(16, (os.cpu_count() or 4) // max(1, world)))
+    outs = [np.zeros(10 * n, dtype=np.int16) for n in ntasks]
+    errs = []
+
+    def caller(tid):
+        for i in range(tid, len(bufs), nthreads):
+            rc = L.csbwa_extend_batch(bufs[i].ctypes.data, bufs[i].size, outs[i].ctypes.data, outs[i].size, local)
+            if rc != 0:
+                errs.append((i, rc))
+
+    def e2e_step():
+        th = [threading.Thread(target=caller, args=(t,)) for t in range(nthreads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    for _ in range(2):
+        e2e_step()
+    if errs:
+        raise RuntimeError("e2e call failed: %r" % errs[:3])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    same = np.array_equal(np.concatenate(outs), result_dev)
+    if not same:
+        raise RuntimeError("device-resident and host-buffer paths disagree")
+
+    # ---- phase split of the dominant kernel (roofline) ----
+    ms3 = (C.c_float * 3)()
+    prep = left = right = 0.0
+    sample_calls = range(0, len(bufs), max(1, len(bufs) // 32))
+    sample_cells0 = int(d_cells.item())
+    for i in sample_calls:
+        L.csbwa_extend_profile_device(d_in.data_ptr() + offs[i], bufs[i].size, ntasks[i], d_out.data_ptr() + 2 * int(ooffs[i]),
+                                      d_cells.data_ptr(), scratch[0].data_ptr(), scr_bytes, C.c_void_p(0), ms3)
+        prep += ms3[0]; left += ms3[1]; right += ms3[2]
+    torch.cuda.synchronize()
+    sample_cells = int(d_cells.item()) - sample_cells0
+
+    # ---- reduce over ranks ----
+    ms_t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    agg = torch.tensor([cells_total, total_tasks, w["n_reads"], in_bytes, out_bytes], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms_total_max, e2e_ms_max = float(ms_t[0]), float(ms_t[1])
+    cells_all, tasks_all, reads_all, inb_all, outb_all = [float(x) for x in agg]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = pkg._lib.int_peak(local)
+        except Exception as e:
+            sys.stderr.write("int_peak failed: %s\n" % e)
+        mp = {}
+        mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp_path):
+            mp = json.load(open(mp_path))
+        gcups = cells_all / (ms_total_max * 1e-3) / 1e9
+        e2e_gcups = cells_all / (e2e_ms_max * 1e-3) / 1e9
+        alu_peak = peaks.get("VIADDMNMX")                      # 1e9 ALU-pipe thread-instr/s (max-class ops)
+        dual_peak = peaks.get("IADD3")                         # adds dual-issue onto the FMA pipe as IMAD.IADD
+        side_ms = left + right
+        side_gops = sample_cells * OPS_PER_CELL / (side_ms * 1e-3) / 1e9 if side_ms > 0 else None
+        hbm_peak = mp.get("hbm_gbs", 6650.0)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "seed-extension SW throughput (whole job)", "value": gcups, "unit": "GCUPS",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (u8-range scores, DPX)",
+            "data": "synthetic", "config": config_block(args, args.pairs),
+            "read_pairs_per_s": (reads_all / 2) * args.steps / (ms_total_max * 1e-3),
+            "tasks_per_step": tasks_all, "cells_per_step": cells_all / args.steps,
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": inb_all, "d2h_bytes_per_step": outb_all,
+                    "read_pairs_per_s": (reads_all / 2) * args.steps / (e2e_ms_max * 1e-3),
+                    "ms_per_step": e2e_ms_max / args.steps, "caller_threads_per_gpu": nthreads,
+                    "api": "csbwa_extend_batch (host buffers, pinned staging, H2D+kernels+D2H per call)"},
+            "gpu_launches": int(kernels_per_step * args.steps * world),
+            "cuda_graph": graph is not None, "streams": nstreams,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "int_alu", "kernel": "k_ext_side (left + right, all size classes)",
+                "achieved": side_gops, "peak": (alu_peak or 0) , "unit": "Gop/s",
+                "frac": (side_gops / alu_peak) if (side_gops and alu_peak) else None,
+                "ops_per_cell": OPS_PER_CELL,
+                "achieved_gcups": (side_gops / OPS_PER_CELL) if side_gops else None,
+                "peak_source": "measured here: dependent-free VIADDMNMX stream on all SMs (csbwa_int_peak), 1e9 thread-instr/s",
+                "frac_vs_dual_pipe_iadd3": (side_gops / dual_peak) if (side_gops and dual_peak) else None,
+                "whole_step_frac": (gcups * OPS_PER_CELL / alu_peak) if alu_peak else None,
+                "phase_ms_sample": {"prepare": prep, "left": left, "right": right, "calls": len(list(sample_calls))},
+                "traffic": traffic,
+                "hbm": {"achieved": (inb_all + outb_all) / world * args.steps / (ms_total_max * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if mp else "fallback"},
+            },
+            "int_peaks_ginstr_per_s": peaks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            cores = os.cpu_count() or 1
+            n_calls = size_cpu_sample(bufs, cores, True, 15.0)
+            dt, kind = cpu_extension_run(bufs[:n_calls], cores, True)
+            ccells = count_cells(bufs[:n_calls], cores)
+            # the kernels' cell counter must agree with the oracle's on the same calls
+            ocells = count_cells(bufs[:min(4, n_calls)], cores)
+            d_cells.zero_()
+            for i in range(min(4, n_calls)):
+                L.csbwa_extend_profile_device(d_in.data_ptr() + offs[i], bufs[i].size, ntasks[i], d_out.data_ptr() + 2 * int(ooffs[i]),
+                                              d_cells.data_ptr(), scratch[0].data_ptr(), scr_bytes, C.c_void_p(0), ms3)
+            torch.cuda.synchronize()
+            line["cells_match_oracle"] = bool(int(d_cells.item()) == ocells)
+            line["cpu_baseline"] = {"value": ccells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+                                    "sample": "first %d seam calls (%d tasks) of the same workload, %.1f s" %
+                                              (n_calls, sum(ntasks[:n_calls]), dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@ EXPORTS = [
     "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
-    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device",
 ]
 
 
@@ -65,6 +65,9 @@ def lib():
     L.csbwa_pack_ext_bytes.argtypes = [i32, vp]; L.csbwa_pack_ext_bytes.restype = i64
     L.csbwa_pack_ext_tasks.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64]; L.csbwa_pack_ext_tasks.restype = i64
     L.csbwa_pack_ext_from_seeds.argtypes = [i32, vp, i32, vp, i64, vp, vp, vp, i64]; L.csbwa_pack_ext_from_seeds.restype = i64
+    L.csbwa_extend_profile_device.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, C.POINTER(C.c_float)]
+    L.csbwa_extend_profile_device.restype = C.c_int
+    L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L
 
@@ -80,3 +83,16 @@ def stats():
     s = Stats()
     check(lib().csbwa_get_stats(C.byref(s)))
     return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+
+PEAK_OPS = ["IADD3", "VIMNMX", "VIADDMNMX", "VIMNMX3", "VIADDMNMX.S16x2", "PRMT", "IMAD"]
+
+
+def int_peak(device=0):
+    """Measured integer-pipe issue rates, 1e9 thread-instructions/s per op (needs a GPU)."""
+    out = {}
+    for i, name in enumerate(PEAK_OPS):
+        v = C.c_double(0)
+        check(lib().csbwa_int_peak(device, i, C.byref(v)))
+        out[name] = v.value
+    return out

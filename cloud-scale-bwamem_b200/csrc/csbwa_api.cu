@@ -20,6 +20,7 @@
 #define CSBWA_E_BADWIRE_DEV CSBWA_E_BADWIRE
 #include "ext_kernels.cuh"
 #include "aln_kernels.cuh"
+#include "peak_kernels.cuh"
 
 using namespace csw;
 
@@ -154,6 +155,45 @@ extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int
         g_stats.kernel_launches += kExtLaunches;
     }
     return rc;
+}
+
+// Same launch sequence as csbwa_extend_batch_device, but with CUDA events between the phases and
+// a final synchronise: ms3 = {prepare (hist/scan/scatter), left side kernels, right side kernels}.
+// Profiling aid for bench.py's roofline object; not used on the product path.
+extern "C" int csbwa_extend_profile_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
+                                           void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream,
+                                           float *ms3)
+{
+    if (!d_in || !d_out || !d_scratch || !ms3 || in_bytes < 32 || n_tasks <= 0) return fail(CSBWA_E_BADARG, "bad argument");
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if ((int64_t)ext_scratch_bytes(n_tasks, in_bytes) > scratch_bytes) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
+    int rc = ensure_dev_attrs(dev);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[4];
+    for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
+    ExtScratch sc = ext_carve(d_scratch, n_tasks);
+    const uint8_t *in = (const uint8_t *)d_in;
+    CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
+    const int tb = 256, gb = (n_tasks + tb - 1) / tb;
+    CU_TRY(cudaEventRecord(ev[0], st));
+    k_ext_hist<<<gb, tb, 0, st>>>(in, in_bytes, n_tasks, sc.hdr);
+    k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
+    k_ext_scatter<<<gb, tb, 0, st>>>(in, in_bytes, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
+    CU_TRY(cudaEventRecord(ev[1], st));
+    launch_ext_side<0>(in, in_bytes, sc, (int16_t *)d_out, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    CU_TRY(cudaEventRecord(ev[2], st));
+    launch_ext_side<1>(in, in_bytes, sc, (int16_t *)d_out, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    CU_TRY(cudaEventRecord(ev[3], st));
+    CU_TRY(cudaEventSynchronize(ev[3]));
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.kernel_launches += kExtLaunches;
+    }
+    return CSBWA_OK;
 }
 
 extern "C" int64_t csbwa_align2_scratch_bytes(int32_t n_jobs, int64_t total_q_len, int64_t total_t_len)
@@ -630,4 +670,32 @@ extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *rea
     }
     return need;
 }
+// ------------------------------------------------------------------------------------
+// integer-pipe peak microbenchmark (roofline denominator)
+// ------------------------------------------------------------------------------------
+extern "C" int csbwa_int_peak(int device, int op, double *giga_instr_per_s)
+{
+    if (!giga_instr_per_s || op < 0 || op >= PEAK_NOPS) return fail(CSBWA_E_BADARG, "bad argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(CSBWA_E_NODEVICE, "no CUDA devices"); }
+    if (device < 0) device = 0;
+    if (device >= n) return fail(CSBWA_E_BADARG, "device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU_TRY(cudaGetDeviceProperties(&p, device));
+    const int sms = p.multiProcessorCount, iters = 4096;
+    cudaError_t e = cudaSuccess;
+    switch (op) {
+    case PEAK_IADD: e = run_peak<PEAK_IADD>(sms, iters, giga_instr_per_s); break;
+    case PEAK_VIMNMX: e = run_peak<PEAK_VIMNMX>(sms, iters, giga_instr_per_s); break;
+    case PEAK_VIADDMNMX: e = run_peak<PEAK_VIADDMNMX>(sms, iters, giga_instr_per_s); break;
+    case PEAK_VIMNMX3: e = run_peak<PEAK_VIMNMX3>(sms, iters, giga_instr_per_s); break;
+    case PEAK_VIADDMNMX16X2: e = run_peak<PEAK_VIADDMNMX16X2>(sms, iters, giga_instr_per_s); break;
+    case PEAK_PRMT: e = run_peak<PEAK_PRMT>(sms, iters, giga_instr_per_s); break;
+    default: e = run_peak<PEAK_IMAD>(sms, iters, giga_instr_per_s); break;
+    }
+    if (e != cudaSuccess) return fail(CSBWA_E_CUDA, "peak kernel: %s", cudaGetErrorString(e));
+    return CSBWA_OK;
+}
+
 #include "csbwa_jni.inc"

@@ -125,6 +125,12 @@ int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int32_t n_task
                               void *d_cells, void *d_scratch, int64_t scratch_bytes,
                               void *stream);
 
+/* profiling aid: same launches with events between phases and a final sync;
+ * ms3 = {prepare kernels, left-side kernels, right-side kernels} */
+int csbwa_extend_profile_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
+                                void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream,
+                                float *ms3);
+
 int64_t csbwa_align2_scratch_bytes(int32_t n_jobs, int64_t total_q_len, int64_t total_t_len);
 int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs,
                               void *d_out /* csbwa_kswr[n_jobs] */,
@@ -156,6 +162,12 @@ int64_t csbwa_pack_ext_tasks(int32_t n_tasks, const uint8_t *seqs, const int64_t
 int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *reads, int32_t read_len,
                                   const uint8_t *ref, int64_t ref_len, const int64_t *seed6,
                                   const int32_t *opt7, uint8_t *out, int64_t cap);
+
+
+/* ---- roofline denominator: measured integer-pipe issue rate ----------------
+ * op: 0 IADD3, 1 VIMNMX, 2 VIADDMNMX, 3 VIMNMX3, 4 VIADDMNMX.S16x2, 5 PRMT, 6 IMAD.
+ * Result: 1e9 thread-instructions per second over the whole GPU (dependent-free streams). */
+int csbwa_int_peak(int device, int op, double *giga_instr_per_s);
 
 #ifdef __cplusplus
 }

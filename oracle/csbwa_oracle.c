@@ -145,7 +145,30 @@ void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
 /* ------------------------------------------------------------------------- */
 #define ORC_MAX_BAND_TRY 2 /* :50 */
 
+/* SW call used by extension(): the restatement above, or (for the "reference" CPU baseline)
+ * the reference's own compiled ksw_extend2 from oracle/_ref passed in as a function pointer. */
+static void orc_sw_call(orc_ksw_extend2_fn fn, int qlen, const uint8_t *q, int tlen, const uint8_t *t,
+                        const orc_opt_t *opt, int w, int end_bonus, int h0, orc_ext_t *x)
+{
+    if (!fn) {
+        orc_sw_extend(qlen, q, tlen, t, 5, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w,
+                      end_bonus, opt->zdrop, h0, x);
+        return;
+    }
+    int qle = 0, tle = 0, gtle = 0, gscore = 0, max_off = 0;
+    x->score = fn(qlen, q, tlen, t, 5, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w,
+                  end_bonus, opt->zdrop, h0, &qle, &tle, &gtle, &gscore, &max_off);
+    x->qle = qle; x->tle = tle; x->gtle = gtle; x->gscore = gscore; x->max_off = max_off; x->cells = 0;
+}
+
+static void orc_extension_with(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r, orc_ksw_extend2_fn fn);
+
 void orc_extension(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r)
+{
+    orc_extension_with(t, opt, r, NULL);
+}
+
+static void orc_extension_with(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r, orc_ksw_extend2_fn fn)
 {
     int aw0 = opt->w, aw1 = opt->w;
     int reg_score = t->reg_score;
@@ -162,9 +185,7 @@ void orc_extension(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r)
         for (int i = 0; i < ORC_MAX_BAND_TRY; ++i) {
             int prev = reg_score;
             aw0 = opt->w << i;
-            orc_sw_extend(t->left_qlen, t->left_q, t->left_rlen, t->left_r, 5, opt->mat,
-                          opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, aw0,
-                          opt->pen_clip5, opt->zdrop, t->h0, &x);
+            orc_sw_call(fn, t->left_qlen, t->left_q, t->left_rlen, t->left_r, opt, aw0, opt->pen_clip5, t->h0, &x);
             r->cells += x.cells; r->n_calls++;
             reg_score = x.score;
             if (reg_score == prev || x.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
@@ -181,9 +202,7 @@ void orc_extension(const orc_task_t *t, const orc_opt_t *opt, orc_extret_t *r)
         for (int i = 0; i < ORC_MAX_BAND_TRY; ++i) {
             int prev = reg_score;
             aw1 = opt->w << i;
-            orc_sw_extend(t->right_qlen, t->right_q, t->right_rlen, t->right_r, 5, opt->mat,
-                          opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, aw1,
-                          opt->pen_clip3, opt->zdrop, sc0, &x);
+            orc_sw_call(fn, t->right_qlen, t->right_q, t->right_rlen, t->right_r, opt, aw1, opt->pen_clip3, sc0, &x);
             r->cells += x.cells; r->n_calls++;
             reg_score = x.score;
             if (reg_score == prev || x.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
@@ -351,7 +370,7 @@ int orc_max_threads(void)
 
 typedef struct {
     const uint8_t *in; int32_t in_bytes; int16_t *out; int64_t *cells; int32_t *calls;
-    orc_opt_t opt; volatile int err;
+    orc_opt_t opt; volatile int err; orc_ksw_extend2_fn fn;
 } orc_ew_ctx;
 
 static void orc_ew_body(int32_t k, void *vctx)
@@ -380,7 +399,7 @@ static void orc_ew_body(int32_t k, void *vctx)
     t.left_r = t.right_q + t.right_qlen;
     t.right_r = t.left_r + t.left_rlen;
     orc_extret_t r;
-    orc_extension(&t, &c->opt, &r);
+    orc_extension_with(&t, &c->opt, &r, c->fn);
     int16_t *o = c->out + (size_t)10 * k;    /* reply layout (:178-190) */
     o[0] = (int16_t)(r.idx & 0xffff); o[1] = (int16_t)((uint32_t)r.idx >> 16);
     o[2] = (int16_t)r.q_beg; o[3] = (int16_t)r.q_end;
@@ -395,8 +414,16 @@ static void orc_ew_body(int32_t k, void *vctx)
 int orc_extend_wire(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
                     int64_t *cells_per_task, int32_t *calls_per_task, int n_threads)
 {
+    return orc_extend_wire_fn(in, in_bytes, out, out_shorts, cells_per_task, calls_per_task, n_threads, NULL);
+}
+
+int orc_extend_wire_fn(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
+                       int64_t *cells_per_task, int32_t *calls_per_task, int n_threads,
+                       orc_ksw_extend2_fn fn)
+{
     if (!in || in_bytes < 32) return -1;
     orc_ew_ctx c;
+    c.fn = fn;
     c.in = in; c.in_bytes = in_bytes; c.out = out; c.cells = cells_per_task; c.calls = calls_per_task;
     c.err = 0;
     orc_default_opt(&c.opt);                 /* zdrop and mat are NOT on the wire */

@@ -91,6 +91,17 @@ void orc_sw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target,
 int orc_extend_wire(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
                     int64_t *cells_per_task, int32_t *calls_per_task, int n_threads);
 
+/* Same driver, but every SWExtend call goes to `fn` -- the reference's own compiled ksw_extend2
+ * (src/main/native/ksw.c:379-476, built into oracle/_ref by oracle/Makefile).  Used only as the
+ * "reference" CPU baseline; C and Scala differ where the z-drop quirk fires. */
+typedef int (*orc_ksw_extend2_fn)(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m,
+                                  const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w,
+                                  int end_bonus, int zdrop, int h0, int *qle, int *tle, int *gtle,
+                                  int *gscore, int *max_off);
+int orc_extend_wire_fn(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts,
+                       int64_t *cells_per_task, int32_t *calls_per_task, int n_threads,
+                       orc_ksw_extend2_fn fn);
+
 /* flat mate-SW job (same layout as csbwa_job in include/csbwa_sw.h) */
 typedef struct {
     int64_t q_off, t_off;       /* byte offsets into seqs[] (1 base per byte, codes 0..4) */

@@ -82,6 +82,8 @@ def lib():
         _lib.orc_sw_align2.argtypes = _lib.orc_sw_align.argtypes
         _lib.orc_extend_wire.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
         _lib.orc_extend_wire.restype = C.c_int
+        _lib.orc_extend_wire_fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_extend_wire_fn.restype = C.c_int
         _lib.orc_align2_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib.orc_align2_batch.restype = C.c_int
         _lib.orc_default_opt.argtypes = [C.POINTER(Opt)]
@@ -146,6 +148,19 @@ def extend_wire(buf, n_threads=1, want_stats=True):
     if rc != 0:
         raise RuntimeError("orc_extend_wire failed: %d" % rc)
     return out, cells, calls
+
+
+def extend_wire_ref(buf, n_threads=1):
+    """Same seam driver, SW calls served by the reference's own compiled ksw_extend2 (oracle/_ref).
+    Timing baseline only: results differ from the Scala truth where the z-drop quirk fires."""
+    b, bp = _u8(buf)
+    n = int(np.frombuffer(b[8:12].tobytes(), dtype="<i4")[0])
+    out = np.zeros(10 * n, dtype=np.int16)
+    fn = C.cast(ref().ksw_extend2, C.c_void_p)
+    rc = lib().orc_extend_wire_fn(bp, b.size, out.ctypes.data, out.size, None, None, n_threads, fn)
+    if rc != 0:
+        raise RuntimeError("orc_extend_wire_fn failed: %d" % rc)
+    return out
 
 
 def align2_batch(jobs, seqs, n_threads=1):

@@ -1,0 +1,244 @@
+"""GPU parity tests proper: everything goes through the C ABI of libcsbwa_sw.so (the host-side
+mirror in cloud-scale-bwamem_b200/jni.py) and is compared bit-for-bit with the CPU oracle."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    L = pkg.lib()
+    n = L.csbwa_init(0)
+    assert n >= 1, "csbwa_init failed: %d (%s)" % (n, L.csbwa_last_error().decode())
+    return L
+
+
+def _ext_gpu(pkg, wire, device=-1):
+    n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
+    return pkg.jni.SWExtendFPGAJNI(device).swExtendFPGAJNI(10 * n, wire)
+
+
+def _check_ext(pkg, oracle, wire):
+    ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
+    before = pkg.stats()["ext_cells"]
+    got = _ext_gpu(pkg, wire)
+    bad = np.flatnonzero((got.reshape(-1, 10) != ref.reshape(-1, 10)).any(axis=1))
+    assert len(bad) == 0, (len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
+    assert pkg.stats()["ext_cells"] - before == int(rcells.sum())      # exact DP cell count
+    return ref
+
+
+def test_ext_golden(pkg, oracle, gpu):
+    g = np.load(os.path.join(GOLD, "ext_golden.npz"))
+    got = _ext_gpu(pkg, g["wire"])
+    assert np.array_equal(got, g["reply"])
+
+
+def test_ext_random_and_adversarial(pkg, oracle, gpu):
+    rng = np.random.default_rng(51)
+    for L in (101, 151, 250):
+        tuples = [util.rand_ext_task(rng, L=L) for _ in range(1500)]
+        _check_ext(pkg, oracle, pkg.jni.packTasks(util.make_ext_params(pkg, tuples)))
+    _check_ext(pkg, oracle, pkg.jni.packTasks(util.make_ext_params(pkg, util.adversarial_ext_tasks(rng))))
+
+
+def test_ext_mirror_api(pkg, oracle, gpu):
+    """runOnFPGAJNI mirror: ExtParam in, ExtRet out, same fields as extension()."""
+    rng = np.random.default_rng(52)
+    tuples = [util.rand_ext_task(rng, L=151) for _ in range(64)]
+    tasks = util.make_ext_params(pkg, tuples)
+    res = pkg.jni.runOnFPGAJNI(len(tasks), tasks, [None] * len(tasks))
+    for k, t in enumerate(tuples):
+        e = oracle.extension(*t[:7], idx=k)
+        assert res[k].astuple() == (e["q_beg"], e["r_beg"], e["q_end"], e["r_end"], e["score"], e["true_score"],
+                                    e["width"], e["idx"])
+
+
+def test_ext_zdrop_and_optional_header(pkg, oracle, gpu):
+    rng = np.random.default_rng(53)
+    z = np.zeros(0, np.uint8)
+    tuples = []
+    for _ in range(2000):
+        n = int(rng.integers(100, 128)); p = int(rng.integers(5, 60))
+        q = rng.integers(0, 4, n).astype(np.uint8)
+        t = rng.integers(0, 4, n + 100).astype(np.uint8); t[:p] = q[:p]
+        h0 = int(rng.integers(100, 127))
+        tuples.append((q, t, z, z, h0, h0, n) if rng.random() < 0.5 else (z, z, q, t, h0, h0, 0))
+    wire = pkg.jni.packTasks(util.make_ext_params(pkg, tuples))
+    _check_ext(pkg, oracle, wire)
+    w2 = wire.copy()                       # optional header extension: zdrop = 0 (C and Scala agree)
+    w2[7] = 1; w2[12] = 0; w2[13] = 0
+    _check_ext(pkg, oracle, w2)
+
+
+def test_ext_workloads_full_calls(pkg, oracle, gpu):
+    """BASELINE.md C1/C2/C5 task shapes at seam-call granularity (4096 reads per call)."""
+    for (L, eps, seed) in ((101, 0.01, 20260102), (151, 0.01, 20260103), (250, 0.05, 20260106)):
+        w = pkg.workload.ext_workload(8192, L, 2000000, eps, 400, 50, seed, reads_per_call=4096)
+        assert len(w["bufs"]) == 4
+        for wire in w["bufs"]:
+            _check_ext(pkg, oracle, wire)
+
+
+def test_ext_empty_and_errors(pkg, gpu):
+    L = pkg.lib()
+    hdr = np.zeros(32, dtype=np.uint8)
+    hdr[:7] = [6, 1, 6, 1, 5, 5, 100]
+    out = np.zeros(10, dtype=np.int16)
+    assert L.csbwa_extend_batch(hdr.ctypes.data, 32, out.ctypes.data, 0, -1) == 0          # zero tasks
+    assert L.csbwa_extend_batch(hdr.ctypes.data, 16, out.ctypes.data, 10, -1) == pkg._lib.E_BADWIRE
+    rng = np.random.default_rng(54)
+    wire = pkg.jni.packTasks(util.make_ext_params(pkg, [util.rand_ext_task(rng) for _ in range(8)]))
+    small = np.zeros(79, dtype=np.int16)
+    assert L.csbwa_extend_batch(wire.ctypes.data, wire.size, small.ctypes.data, small.size, -1) == pkg._lib.E_SHORTOUT
+    bad = wire.copy()
+    bad[32 + 8:32 + 12] = np.frombuffer(np.int32(1 << 28).tobytes(), dtype=np.uint8)       # taskPos out of range
+    out = np.zeros(80, dtype=np.int16)
+    assert L.csbwa_extend_batch(bad.ctypes.data, bad.size, out.ctypes.data, out.size, -1) == pkg._lib.E_BADWIRE
+    assert L.csbwa_extend_batch(None, 32, out.ctypes.data, out.size, -1) == pkg._lib.E_BADARG
+    with pytest.raises(pkg.CsbwaError):
+        pkg.jni.SWExtendFPGAJNI().swExtendFPGAJNI(80, bad)
+
+
+def test_ext_concurrent_callers(pkg, oracle, gpu):
+    """Many executor threads inside the seam at once (re-entrancy, per-thread contexts)."""
+    rng = np.random.default_rng(55)
+    wires = [pkg.jni.packTasks(util.make_ext_params(pkg, [util.rand_ext_task(rng) for _ in range(700)]))
+             for _ in range(8)]
+    refs = [oracle.extend_wire(w, n_threads=8)[0] for w in wires]
+    errs = []
+
+    def work(i):
+        for _ in range(5):
+            got = _ext_gpu(pkg, wires[i])
+            if not np.array_equal(got, refs[i]):
+                errs.append(i)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+
+
+def _aln_gpu(pkg, jobs, seqs):
+    return pkg.jni.swAlign2Batch(jobs, seqs)
+
+
+def test_aln_golden(pkg, gpu):
+    g = np.load(os.path.join(GOLD, "aln_golden.npz"))
+    assert np.array_equal(_aln_gpu(pkg, g["jobs"], g["seqs"]), g["out"])
+
+
+def test_aln_random_and_edges(pkg, oracle, gpu):
+    rng = np.random.default_rng(56)
+    pairs = [util.rand_aln_job(rng) for _ in range(600)]
+    r = lambda n: rng.integers(0, 4, n).astype(np.uint8)
+    q255 = r(255)
+    pairs += [(r(1), r(50)), (r(151), r(1)), (r(151), np.zeros(0, np.uint8)), (np.zeros(0, np.uint8), r(100)),
+              (q255, np.concatenate([r(30), q255, r(30)])), (np.full(100, 4, np.uint8), r(300)),
+              (r(100), np.full(300, 4, np.uint8)), (np.zeros(64, np.uint8), np.zeros(500, np.uint8)),
+              (r(300), r(700)), (r(700), r(300)), (r(151), r(5000))]
+    for n in (32, 33, 64, 65, 128, 129, 160, 161, 256, 257):
+        pairs.append((r(n), r(400)))
+    xt = []
+    for q, _ in pairs:
+        xt.append(pkg.jni.mateXtra(len(q)) if rng.random() < 0.7 else
+                  int(rng.choice([0, util.XSTART | 7, util.XSUBO | 25, util.XSTART | util.XSUBO | util.XSTOP | 40])))
+    jobs, seqs = util.build_jobs(pairs, xt, pkg._lib.JOB_DTYPE)
+    ref, rcells = oracle.align2_batch(jobs, seqs, n_threads=8)
+    before = pkg.stats()["aln_cells"]
+    got = _aln_gpu(pkg, jobs, seqs)
+    bad = np.flatnonzero((got != ref).any(axis=1))
+    assert len(bad) == 0, (len(bad), bad[:5], got[bad[:3]], ref[bad[:3]])
+    assert pkg.stats()["aln_cells"] - before == int(rcells.sum())
+    one = pkg.jni.SWAlign2(pairs[0][0], pairs[0][1], xt[0])
+    assert one.astuple() == tuple(int(v) for v in ref[0])
+
+
+def test_aln_workloads(pkg, oracle, gpu):
+    """BASELINE.md C1 (windows ~620) and C3 (wide insert spread, windows ~4 kb) shapes."""
+    for (mu, sigma, n) in ((400, 50, 1024), (1500, 500, 384)):
+        w = pkg.workload.matesw_workload(n, 151, 3000000, 0.01, mu, sigma, 1.0, seed=20260104, pairs_per_call=512)
+        for jobs, seqs in w["calls"]:
+            ref, rcells = oracle.align2_batch(jobs, seqs, n_threads=8)
+            got = _aln_gpu(pkg, jobs, seqs)
+            assert np.array_equal(got, ref)
+        assert (ref[:, 6] >= 0).mean() > 0.9
+
+
+def test_device_resident_api(pkg, oracle, gpu):
+    """csbwa_*_batch_device on torch-owned device memory and torch's current stream."""
+    import torch
+    L = pkg.lib()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    w = pkg.workload.ext_workload(2048, 151, 1000000, 0.01, 400, 50, 20260105, reads_per_call=4096)
+    wire = w["bufs"][0]
+    n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
+    ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
+    d_in = torch.from_numpy(wire).to(dev)
+    d_out = torch.zeros(10 * n, dtype=torch.int16, device=dev)
+    d_cells = torch.zeros(1, dtype=torch.int64, device=dev)
+    scr = torch.empty(L.csbwa_extend_scratch_bytes(n, wire.size), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        rc = L.csbwa_extend_batch_device(d_in.data_ptr(), wire.size, n, d_out.data_ptr(), d_cells.data_ptr(),
+                                         scr.data_ptr(), scr.numel(), C.c_void_p(st))
+        assert rc == 0, L.csbwa_last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), ref)
+    assert int(d_cells.item()) == 2 * int(rcells.sum())
+    # too-small scratch is refused, not overrun
+    rc = L.csbwa_extend_batch_device(d_in.data_ptr(), wire.size, n, d_out.data_ptr(), None, scr.data_ptr(), 1024, C.c_void_p(st))
+    assert rc == pkg._lib.E_SCRATCH
+    # mate-SW
+    mw = pkg.workload.matesw_workload(256, 151, 1000000, 0.01, 400, 50, 1.0, seed=7, pairs_per_call=256)
+    jobs, seqs = mw["calls"][0]
+    aref, acells = oracle.align2_batch(jobs, seqs, n_threads=8)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(dev)
+    d_seqs = torch.from_numpy(seqs).to(dev)
+    d_o = torch.zeros(7 * len(jobs), dtype=torch.int32, device=dev)
+    d_cells.zero_()
+    nb = L.csbwa_align2_scratch_bytes(len(jobs), int(jobs["q_len"].sum()), int(jobs["t_len"].sum()))
+    scr2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+    rc = L.csbwa_align2_batch_device(d_jobs.data_ptr(), len(jobs), d_seqs.data_ptr(), d_o.data_ptr(), d_cells.data_ptr(),
+                                     scr2.data_ptr(), scr2.numel(), C.c_void_p(st))
+    assert rc == 0, L.csbwa_last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy().reshape(-1, 7), aref)
+    assert int(d_cells.item()) == int(acells.sum())
+
+
+def test_large_batch_properties(pkg, oracle, gpu):
+    """Size-independent properties at a BASELINE-scale call (32768 reads in one call):
+    determinism, exact cell count, every task answered exactly once, invariants of ExtRet."""
+    w = pkg.workload.ext_workload(16384, 151, 4000000, 0.01, 400, 50, 20260107, reads_per_call=32768)
+    wire = w["bufs"][0]
+    n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
+    a = _ext_gpu(pkg, wire).reshape(n, 10)
+    b = _ext_gpu(pkg, wire).reshape(n, 10)
+    assert np.array_equal(a, b)
+    idx = (a[:, 0].astype(np.int64) & 0xffff) | (a[:, 1].astype(np.int64) << 16)
+    assert np.array_equal(np.sort(idx), np.arange(n))
+    rec = np.frombuffer(wire[32:32 + 32 * n].tobytes(), dtype="<i2").reshape(n, 16)
+    h0 = rec[:, 8]
+    assert (a[:, 6] >= h0).all()                       # extension never lowers the seed score
+    assert (a[:, 2] >= 0).all() and (a[:, 2] <= rec[:, 7]).all()      # 0 <= qBeg <= seed qBeg
+    assert (a[:, 3] >= 0).all() and (a[:, 3] <= rec[:, 2]).all()      # 0 <= qEnd <= rightQlen
+    assert (a[:, 4] <= 0).all() and (a[:, 5] >= 0).all()
+    assert np.isin(a[:, 8], (100, 200)).all()
+    ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
+    assert np.array_equal(a.reshape(-1), ref)
+
+
+def test_int_peak_microbench(pkg, gpu):
+    p = pkg._lib.int_peak(0)
+    assert p["VIMNMX"] > 1000 and p["VIADDMNMX"] > 1000    # > 1 T thread-instr/s on any B200
