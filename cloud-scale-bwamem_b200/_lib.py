@@ -12,19 +12,22 @@ OK, E_NODEVICE, E_BADARG, E_BADWIRE, E_SHORTOUT, E_CUDA, E_NOMEM, E_SCRATCH = 0,
 JOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"),
                       ("xtra", "<i4"), ("pad", "<i4")])
 
+CALL_DTYPE = np.dtype([("in_off", "<i8"), ("in_bytes", "<i4"), ("n_tasks", "<i4"), ("out_off", "<i8"),
+                       ("task_base", "<i4"), ("pad", "<i4")])
+
 EXPORTS = [
     "csbwa_init", "csbwa_shutdown", "csbwa_device_count", "csbwa_strerror", "csbwa_last_error", "csbwa_version",
     "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
-    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device",
 ]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("ext_calls", "ext_tasks", "ext_cells", "ext_in_bytes", "ext_out_bytes",
                                          "aln_calls", "aln_jobs", "aln_cells", "aln_in_bytes", "aln_out_bytes",
-                                         "kernel_launches")] + \
+                                         "kernel_launches", "ext_groups")] + \
                [(n, C.c_double) for n in ("h2d_ms", "kernel_ms", "d2h_ms", "host_ms")]
 
 
@@ -65,8 +68,10 @@ def lib():
     L.csbwa_pack_ext_bytes.argtypes = [i32, vp]; L.csbwa_pack_ext_bytes.restype = i64
     L.csbwa_pack_ext_tasks.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64]; L.csbwa_pack_ext_tasks.restype = i64
     L.csbwa_pack_ext_from_seeds.argtypes = [i32, vp, i32, vp, i64, vp, vp, vp, i64]; L.csbwa_pack_ext_from_seeds.restype = i64
-    L.csbwa_extend_profile_device.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, C.POINTER(C.c_float)]
+    L.csbwa_extend_profile_device.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp, C.POINTER(C.c_float)]
     L.csbwa_extend_profile_device.restype = C.c_int
+    L.csbwa_extend_multi_device.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp]
+    L.csbwa_extend_multi_device.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

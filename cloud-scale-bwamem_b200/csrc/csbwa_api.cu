@@ -21,10 +21,12 @@
 #include "ext_kernels.cuh"
 #include "aln_kernels.cuh"
 #include "peak_kernels.cuh"
+#include "coalesce.hpp"
 
 using namespace csw;
 
 static_assert(sizeof(csbwa_job) == sizeof(AlnJob), "job layout");
+static_assert(sizeof(csbwa_ext_call) == sizeof(ExtCall) && sizeof(CoCall) == sizeof(ExtCall), "call table layout");
 static_assert(sizeof(csbwa_kswr) == 7 * sizeof(int32_t), "kswr layout");
 
 // ------------------------------------------------------------------------------------
@@ -100,14 +102,14 @@ extern "C" int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes)
 }
 
 template <int SIDE>
-static void launch_ext_side(const uint8_t *d_in, int in_bytes, ExtScratch &sc, int16_t *d_out,
+static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch &sc, int16_t *d_out,
                             unsigned long long *d_cells, int n, int sms, cudaStream_t st)
 {
     for (int cls = 0; cls < EXT_NCLS; ++cls) {
         if (cls == 0) {
             int grid = (n + EXT_BD - 1) / EXT_BD;
             if (grid > sms * 8) grid = sms * 8;
-            k_ext_side<SIDE, false><<<grid, EXT_BD, 0, st>>>(d_in, in_bytes, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+            k_ext_side<SIDE, false><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                               d_out, d_cells, cls);
         } else {
             const int cap = ext_class_cap(cls);
@@ -116,30 +118,41 @@ static void launch_ext_side(const uint8_t *d_in, int in_bytes, ExtScratch &sc, i
             const int per_sm = cls == 1 ? 3 : (cls == 2 ? 3 : 7);
             int grid = (n + bd - 1) / bd;
             if (grid > sms * per_sm) grid = sms * per_sm;
-            k_ext_side<SIDE, true><<<grid, bd, smem, st>>>(d_in, in_bytes, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+            k_ext_side<SIDE, true><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                             d_out, d_cells, cls);
         }
     }
 }
 
-static int launch_extend(const uint8_t *d_in, int in_bytes, int n, int16_t *d_out,
+// d_in: base of the input region; cs: the calls inside it; n: total tasks
+static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t *d_out,
                          unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
                          cudaStream_t st, int dev)
 {
     if (n <= 0) return CSBWA_OK;
-    if ((int64_t)ext_scratch_bytes(n, in_bytes) > scratch_bytes) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
+    const int64_t fixed = (int64_t)ext_scratch_fixed(n);
+    if (scratch_bytes < fixed + (int64_t)EXT_MIN_EH_BYTES) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
     int rc = ensure_dev_attrs(dev);
     if (rc) return rc;
     ExtScratch sc = ext_carve(d_scratch, n);
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
     const int tb = 256, gb = (n + tb - 1) / tb;
-    k_ext_hist<<<gb, tb, 0, st>>>(d_in, in_bytes, n, sc.hdr);
+    k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed));
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
-    k_ext_scatter<<<gb, tb, 0, st>>>(d_in, in_bytes, n, sc.hdr, sc.order[0], sc.order[1]);
-    launch_ext_side<0>(d_in, in_bytes, sc, d_out, d_cells, n, g_dev[dev].sms, st);
-    launch_ext_side<1>(d_in, in_bytes, sc, d_out, d_cells, n, g_dev[dev].sms, st);
+    k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
+    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st);
+    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st);
     CU_TRY(cudaGetLastError());
     return CSBWA_OK;
+}
+
+static ExtCalls single_call(int32_t in_bytes, int32_t n_tasks)
+{
+    ExtCalls cs;
+    cs.tab = nullptr; cs.n_calls = 1;
+    cs.single.in_off = 0; cs.single.in_bytes = in_bytes; cs.single.n_tasks = n_tasks;
+    cs.single.out_off = 0; cs.single.task_base = 0; cs.single.pad = 0;
+    return cs;
 }
 
 extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
@@ -148,7 +161,7 @@ extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int
     if (!d_in || !d_out || !d_scratch || in_bytes < 32 || n_tasks < 0) return fail(CSBWA_E_BADARG, "bad argument");
     int dev = 0;
     CU_TRY(cudaGetDevice(&dev));
-    int rc = launch_extend((const uint8_t *)d_in, in_bytes, n_tasks, (int16_t *)d_out,
+    int rc = launch_extend((const uint8_t *)d_in, single_call(in_bytes, n_tasks), n_tasks, (int16_t *)d_out,
                            (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
     if (rc == CSBWA_OK && n_tasks > 0) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
@@ -157,34 +170,73 @@ extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int
     return rc;
 }
 
-// Same launch sequence as csbwa_extend_batch_device, but with CUDA events between the phases and
+// Several seam calls in ONE launch sequence (call coalescing).  h_calls: host copy of the table
+// (sizes the launch); d_calls: the same table in device memory.  Calls must carry identical
+// option bytes (checked on the device).  in_off are byte offsets from d_in_base (256-B aligned),
+// out_off short offsets from d_out_base; task_base must be the running sum of n_tasks.
+extern "C" int csbwa_extend_multi_device(const void *d_in_base, const csbwa_ext_call *h_calls,
+                                         const csbwa_ext_call *d_calls, int32_t n_calls, void *d_out_base,
+                                         void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    if (!d_in_base || !h_calls || !d_calls || !d_out_base || !d_scratch || n_calls < 1) return fail(CSBWA_E_BADARG, "bad argument");
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    int64_t n = 0;
+    for (int c = 0; c < n_calls; ++c) {
+        if (h_calls[c].n_tasks < 0 || h_calls[c].in_bytes < 32 || h_calls[c].task_base != n || (h_calls[c].in_off & 3))
+            return fail(CSBWA_E_BADARG, "inconsistent call table");
+        n += h_calls[c].n_tasks;
+    }
+    if (n > 0x7fffffff) return fail(CSBWA_E_BADARG, "too many tasks");
+    ExtCalls cs;
+    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls;
+    memcpy(&cs.single, &h_calls[0], sizeof(ExtCall));
+    int rc = launch_extend((const uint8_t *)d_in_base, cs, (int)n, (int16_t *)d_out_base,
+                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
+    if (rc == CSBWA_OK && n > 0) {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.kernel_launches += kExtLaunches;
+    }
+    return rc;
+}
+
+// Same launch sequence as csbwa_extend_multi_device, but with CUDA events between the phases and
 // a final synchronise: ms3 = {prepare (hist/scan/scatter), left side kernels, right side kernels}.
 // Profiling aid for bench.py's roofline object; not used on the product path.
-extern "C" int csbwa_extend_profile_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
+extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ext_call *h_calls,
+                                           const csbwa_ext_call *d_calls, int32_t n_calls, void *d_out_base,
                                            void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream,
                                            float *ms3)
 {
-    if (!d_in || !d_out || !d_scratch || !ms3 || in_bytes < 32 || n_tasks <= 0) return fail(CSBWA_E_BADARG, "bad argument");
+    if (!d_in_base || !h_calls || !d_calls || !d_out_base || !d_scratch || !ms3 || n_calls < 1) return fail(CSBWA_E_BADARG, "bad argument");
     int dev = 0;
     CU_TRY(cudaGetDevice(&dev));
-    if ((int64_t)ext_scratch_bytes(n_tasks, in_bytes) > scratch_bytes) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
+    int64_t n64 = 0;
+    for (int c = 0; c < n_calls; ++c) n64 += h_calls[c].n_tasks;
+    if (n64 <= 0 || n64 > 0x7fffffff) return fail(CSBWA_E_BADARG, "bad task count");
+    const int n_tasks = (int)n64;
+    const int64_t fixed = (int64_t)ext_scratch_fixed(n_tasks);
+    if (scratch_bytes < fixed + (int64_t)EXT_MIN_EH_BYTES) return fail(CSBWA_E_SCRATCH, "extension scratch too small");
     int rc = ensure_dev_attrs(dev);
     if (rc) return rc;
+    ExtCalls cs;
+    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls;
+    memcpy(&cs.single, &h_calls[0], sizeof(ExtCall));
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev[4];
     for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
     ExtScratch sc = ext_carve(d_scratch, n_tasks);
-    const uint8_t *in = (const uint8_t *)d_in;
+    const uint8_t *in = (const uint8_t *)d_in_base;
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
     const int tb = 256, gb = (n_tasks + tb - 1) / tb;
     CU_TRY(cudaEventRecord(ev[0], st));
-    k_ext_hist<<<gb, tb, 0, st>>>(in, in_bytes, n_tasks, sc.hdr);
+    k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed));
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
-    k_ext_scatter<<<gb, tb, 0, st>>>(in, in_bytes, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
+    k_ext_scatter<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
     CU_TRY(cudaEventRecord(ev[1], st));
-    launch_ext_side<0>(in, in_bytes, sc, (int16_t *)d_out, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
     CU_TRY(cudaEventRecord(ev[2], st));
-    launch_ext_side<1>(in, in_bytes, sc, (int16_t *)d_out, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    launch_ext_side<1>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
     CU_TRY(cudaEventRecord(ev[3], st));
     CU_TRY(cudaEventSynchronize(ev[3]));
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]);
@@ -288,6 +340,8 @@ static int grow_dev(Buf &b, size_t need)
     return CSBWA_OK;
 }
 
+static void destroy_coalescers();
+
 extern "C" int csbwa_init(int n_gpus)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -329,6 +383,7 @@ static void destroy_ctx(Ctx *c)
 
 extern "C" int csbwa_shutdown(void)
 {
+    destroy_coalescers();
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return CSBWA_OK;
     for (auto &v : g_free) { for (Ctx *c : v) destroy_ctx(c); v.clear(); }
@@ -393,15 +448,172 @@ static int check_ext_wire(const uint8_t *in, int32_t in_bytes, int32_t *n_out)
     return CSBWA_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// coalesced host path: CUDA executor for Coalescer<> (csrc/coalesce.hpp)
+// ------------------------------------------------------------------------------------
+struct CudaCoExec {
+    struct Slot {
+        cudaStream_t st = nullptr;
+        uint8_t *h_in = nullptr; uint8_t *h_out = nullptr;     // pinned
+        uint8_t *d_in = nullptr; uint8_t *d_out = nullptr; void *d_scratch = nullptr;
+        int32_t *h_err = nullptr;
+    };
+    int dev = 0;
+    size_t in_cap = 0, out_cap = 0, scratch_cap = 0;
+    std::vector<Slot> slots;
+
+    int init(int device, int n_slots, size_t max_bytes, int max_tasks)
+    {
+        dev = device;
+        in_cap = max_bytes;
+        out_cap = (size_t)max_tasks * 20 + 64;
+        scratch_cap = ext_scratch_fixed(max_tasks) + (size_t)32 * 1024 * 1024;
+        CU_TRY(cudaSetDevice(dev));
+        slots.resize(n_slots);
+        for (auto &s : slots) {
+            CU_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            CU_TRY(cudaMallocHost((void **)&s.h_in, in_cap));
+            CU_TRY(cudaMallocHost((void **)&s.h_out, out_cap));
+            CU_TRY(cudaMallocHost((void **)&s.h_err, 16));
+            CU_TRY(cudaMalloc((void **)&s.d_in, in_cap));
+            CU_TRY(cudaMalloc((void **)&s.d_out, out_cap));
+            CU_TRY(cudaMalloc(&s.d_scratch, scratch_cap));
+        }
+        return CSBWA_OK;
+    }
+    void destroy()
+    {
+        cudaSetDevice(dev);
+        for (auto &s : slots) {
+            if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            if (s.h_in) cudaFreeHost(s.h_in);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.h_err) cudaFreeHost(s.h_err);
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.d_scratch) cudaFree(s.d_scratch);
+        }
+        slots.clear();
+    }
+    uint8_t *in_staging(int slot) { return slots[slot].h_in; }
+    int16_t *out_staging(int slot) { return (int16_t *)slots[slot].h_out; }
+
+    // one H2D, one multi-call launch sequence, one D2H (+4 bytes of status) for the whole group
+    int run(int slot, const CoCall *calls, int n_calls, size_t span, int n_tasks)
+    {
+        const double t0 = now_ms();
+        Slot &s = slots[slot];
+        CU_TRY(cudaSetDevice(dev));
+        const size_t reply = (size_t)n_tasks * 20;
+        const size_t tail = (reply + 15) & ~(size_t)15;            // cells accumulator after the replies
+        CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, span, cudaMemcpyHostToDevice, s.st));
+        CU_TRY(cudaMemsetAsync(s.d_out + tail, 0, 8, s.st));
+        ExtCalls cs;
+        cs.tab = (const ExtCall *)s.d_in; cs.n_calls = n_calls;
+        memcpy(&cs.single, &calls[0], sizeof(ExtCall));
+        int rc = launch_extend(s.d_in, cs, n_tasks, (int16_t *)s.d_out, (unsigned long long *)(s.d_out + tail),
+                               s.d_scratch, (int64_t)scratch_cap, s.st, dev);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, tail + 8, cudaMemcpyDeviceToHost, s.st));
+        CU_TRY(cudaMemcpyAsync(s.h_err, &((ExtHdr *)s.d_scratch)->err, 4, cudaMemcpyDeviceToHost, s.st));
+        CU_TRY(cudaStreamSynchronize(s.st));
+        const int err = *s.h_err;
+        if (err == CSBWA_E_SCRATCH) return fail(CSBWA_E_SCRATCH, "generic-row scratch exhausted");
+        if (err != 0) return fail(CSBWA_E_BADWIRE, "a task record points outside its buffer, or coalesced headers differ");
+        unsigned long long cells = 0;
+        memcpy(&cells, s.h_out + tail, 8);
+        size_t in_b = 0;
+        for (int c = 0; c < n_calls; ++c) in_b += (size_t)calls[c].in_bytes;
+        {
+            std::lock_guard<std::mutex> lk(g_stats_mu);
+            g_stats.ext_calls += n_calls; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)cells;
+            g_stats.ext_in_bytes += (int64_t)in_b; g_stats.ext_out_bytes += (int64_t)reply;
+            g_stats.kernel_launches += kExtLaunches;
+            g_stats.ext_groups += 1;
+            g_stats.host_ms += now_ms() - t0;
+        }
+        return CSBWA_OK;
+    }
+};
+
+struct CoDev {
+    CudaCoExec exec;
+    Coalescer<CudaCoExec> *co = nullptr;
+};
+static CoDev *g_co[64] = {nullptr};
+static std::mutex g_co_mu;
+static const size_t kCoMaxBytes = (size_t)32 * 1024 * 1024;
+static const int kCoMaxTasks = 262144, kCoMaxCalls = 256, kCoSlots = 4, kCoWorkers = 3;
+
+static bool coalescing_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CSBWA_COALESCE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static int get_coalescer(int dev, Coalescer<CudaCoExec> **out)
+{
+    std::lock_guard<std::mutex> lk(g_co_mu);
+    if (!g_co[dev]) {
+        int rc = ensure_dev_attrs(dev);
+        if (rc) return rc;
+        CoDev *d = new CoDev();
+        rc = d->exec.init(dev, kCoSlots, kCoMaxBytes, kCoMaxTasks);
+        if (rc) { d->exec.destroy(); delete d; return rc; }
+        Coalescer<CudaCoExec>::Limits lim{kCoMaxBytes, kCoMaxTasks, kCoMaxCalls};
+        d->co = new Coalescer<CudaCoExec>(&d->exec, kCoSlots, kCoWorkers, lim);
+        g_co[dev] = d;
+    }
+    *out = g_co[dev]->co;
+    return CSBWA_OK;
+}
+
+static void destroy_coalescers()
+{
+    std::lock_guard<std::mutex> lk(g_co_mu);
+    for (auto &d : g_co)
+        if (d) { delete d->co; d->exec.destroy(); delete d; d = nullptr; }
+}
+
+static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t n, int device);
+
 extern "C" int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t out_shorts, int device)
 {
-    const double t0 = now_ms();
     if (!in || !out || in_bytes < 0 || out_shorts < 0) return fail(CSBWA_E_BADARG, "null buffer or negative size");
     int32_t n = 0;
     int rc = check_ext_wire(in, in_bytes, &n);
     if (rc) return rc;
     if (out_shorts < CSBWA_EXT_RET_SHORTS * n) return fail(CSBWA_E_SHORTOUT, "reply array too small");
     if (n == 0) return CSBWA_OK;
+    if (coalescing_enabled()) {
+        if (!g_inited) {
+            rc = csbwa_init(0);
+            if (rc < 0) return rc;
+        }
+        int dev = device;
+        if (dev < 0) dev = (int)(g_rr.fetch_add(1) % (unsigned)g_ndev);
+        if (dev >= g_ndev) return fail(CSBWA_E_BADARG, "device index out of range");
+        Coalescer<CudaCoExec> *co = nullptr;
+        rc = get_coalescer(dev, &co);
+        if (rc) return rc;
+        if (co->fits(in_bytes, n)) {
+            rc = co->submit(in, in_bytes, out, n);
+            if (rc != CSBWA_E_SCRATCH) return rc;      // outlier-heavy call: redo alone with the safe scratch size
+        }
+        device = dev;
+    }
+    return extend_batch_direct(in, in_bytes, out, n, device);
+}
+
+// one call = one submission (large calls, CSBWA_COALESCE=0, or scratch fallback)
+static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t n, int device)
+{
+    const double t0 = now_ms();
+    int rc = 0;
     Ctx *c = nullptr;
     rc = acquire_ctx(device, &c);
     if (rc) return rc;
@@ -417,7 +629,7 @@ extern "C" int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes, int16_t *
     CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
     CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
     CU_TRY(cudaEventRecord(c->ev[1], c->st));
-    rc = launch_extend((const uint8_t *)c->d_in.p, in_bytes, n, (int16_t *)c->d_out.p, c->d_cells,
+    rc = launch_extend((const uint8_t *)c->d_in.p, single_call(in_bytes, n), n, (int16_t *)c->d_out.p, c->d_cells,
                        c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(c->ev[2], c->st));
@@ -426,6 +638,7 @@ extern "C" int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes, int16_t *
     CU_TRY(cudaMemcpyAsync(c->h_err, &((ExtHdr *)c->d_scratch.p)->err, 4, cudaMemcpyDeviceToHost, c->st));
     CU_TRY(cudaEventRecord(c->ev[3], c->st));
     CU_TRY(cudaStreamSynchronize(c->st));
+    if (*c->h_err == CSBWA_E_SCRATCH) return fail(CSBWA_E_SCRATCH, "generic-row scratch exhausted");
     if (*c->h_err != 0) return fail(CSBWA_E_BADWIRE, "a task record points outside the buffer");
     memcpy(out, c->h_out.p, out_bytes);
     float a = 0, b = 0, d = 0;

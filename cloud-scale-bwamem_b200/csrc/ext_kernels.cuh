@@ -15,6 +15,33 @@
 
 namespace csw {
 
+// One launch sequence can serve SEVERAL seam calls at once (call coalescing): the calls' wire
+// buffers sit at byte offsets of one device region and a small table describes them.
+struct ExtCall {
+    long long in_off;     // byte offset of this call's wire buffer inside the input region (256-B aligned)
+    int in_bytes;
+    int n_tasks;
+    long long out_off;    // offset of this call's reply inside the output region, in shorts
+    int task_base;        // global index of this call's first task
+    int pad;
+};
+struct ExtCalls {         // passed to the kernels by value
+    const ExtCall *tab;   // device table (unused when n_calls == 1)
+    int n_calls;
+    ExtCall single;
+};
+CSW_HD const ExtCall &ext_call(const ExtCalls &cs, int c) { return cs.n_calls == 1 ? cs.single : cs.tab[c]; }
+// global task index -> call index (largest c with task_base <= g)
+CSW_HD int ext_locate(const ExtCalls &cs, int g)
+{
+    int lo = 0, hi = cs.n_calls - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ext_call(cs, mid).task_base <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty side, 256 = generic
 constexpr int EXT_NCLS = 4;            // 0: generic, 1: cap 256, 2: cap 128, 3: cap 64
 constexpr int EXT_BD = 128;            // threads per block of the side kernels
@@ -28,6 +55,8 @@ struct ExtHdr {
     uint32_t cursor[2][EXT_NBIN];
     uint32_t cls_beg[2][EXT_NCLS + 1]; // job range of each class inside order[side]
     uint32_t work[2][EXT_NCLS];        // dynamic chunk cursors
+    unsigned long long eh_bump;        // bytes handed out of the generic H/E region
+    unsigned long long eh_cap;         // its capacity
 };
 
 // scratch layout helpers ----------------------------------------------------------
@@ -43,10 +72,13 @@ __host__ __device__ inline size_t ext_scratch_fixed(int n)
     return ext_align256(sizeof(ExtHdr)) + 2 * ext_align256((size_t)n * 4) +
            ext_align256((size_t)n * sizeof(SideRes));
 }
+// safe size: the generic int32 H/E rows (outlier tasks only) are bump-allocated, two
+// allocations of 8*(max(lq,rq)+2) bytes per task at most
 __host__ __device__ inline size_t ext_scratch_bytes(int n, int64_t in_bytes)
 {
-    return ext_scratch_fixed(n) + (size_t)16 * (size_t)in_bytes + (size_t)32 * n + 256;
+    return ext_scratch_fixed(n) + (size_t)32 * (size_t)in_bytes + (size_t)64 * n + 256;
 }
+constexpr size_t EXT_MIN_EH_BYTES = 64 * 1024;
 __host__ __device__ inline ExtScratch ext_carve(void *p, int n)
 {
     ExtScratch s;
@@ -96,21 +128,34 @@ CSW_HD int ext_side_bin(const SwOpt &o, int qlen, int h0)
     return u8_eligible(o, qlen, h0) ? qlen : 256;
 }
 
-__global__ void k_ext_hist(const uint8_t *__restrict__ in, int in_bytes, int n, ExtHdr *hdr)
+__global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr,
+                           unsigned long long eh_cap)
 {
     __shared__ uint32_t sh[2][EXT_NBIN];
     __shared__ SwOpt sopt;
     for (int i = threadIdx.x; i < 2 * EXT_NBIN; i += blockDim.x) (&sh[0][0])[i] = 0;
     if (threadIdx.x == 0) {
-        ext_parse_header(in, sopt);
-        if (blockIdx.x == 0) { hdr->opt = sopt; hdr->n_tasks = n; }
+        const uint8_t *in0 = base + ext_call(cs, 0).in_off;
+        ext_parse_header(in0, sopt);
+        if (blockIdx.x == 0) {
+            hdr->opt = sopt; hdr->n_tasks = n; hdr->eh_cap = eh_cap;
+            // coalesced calls must carry the same options (header bytes other than taskNum)
+            for (int c = 1; c < cs.n_calls; ++c) {
+                const uint8_t *inc = base + ext_call(cs, c).in_off;
+                bool same = true;
+                for (int b = 0; b < 32; ++b) if ((b < 8 || b >= 12) && inc[b] != in0[b]) same = false;
+                if (!same) atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
+            }
+        }
     }
     __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
-        ExtTask t = read_task(in, k);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) {
+        const ExtCall &cl = ext_call(cs, ext_locate(cs, g));
+        const uint8_t *in = base + cl.in_off;
+        ExtTask t = read_task(in, g - cl.task_base);
         int bl = 0, br = 0;
-        if (!ext_task_ok(t, n, in_bytes)) {
+        if (!ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
             atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
         } else {
             // the right side's h0 is the left score, bounded by h0 + lq * max(mat)
@@ -149,15 +194,16 @@ __global__ void k_ext_scan(ExtHdr *hdr)
     }
 }
 
-__global__ void k_ext_scatter(const uint8_t *__restrict__ in, int in_bytes, int n, ExtHdr *hdr,
+__global__ void k_ext_scatter(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr,
                               uint32_t *__restrict__ order_l, uint32_t *__restrict__ order_r)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;      // global task index
     if (k >= n) return;
     const SwOpt &o = hdr->opt;
-    ExtTask t = read_task(in, k);
+    const ExtCall &cl = ext_call(cs, ext_locate(cs, k));
+    ExtTask t = read_task(base + cl.in_off, k - cl.task_base);
     int bl = 0, br = 0;
-    if (ext_task_ok(t, n, in_bytes)) {
+    if (ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
         bl = ext_side_bin(o, t.lq, t.h0);
         const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
         br = ext_side_bin(o, t.rq, h0r);
@@ -196,13 +242,12 @@ CSW_HD void ext_run_side(const SwOpt &o, const uint32_t *words, int q_nib, int q
 // SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range; FAST = u8 core.
 template <int SIDE, bool FAST>
 __global__ void __launch_bounds__(EXT_BD)
-k_ext_side(const uint8_t *__restrict__ in, int in_bytes, ExtHdr *hdr, const uint32_t *__restrict__ order,
+k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
            SideRes *__restrict__ left, int *__restrict__ ehbase, int16_t *__restrict__ out,
            unsigned long long *cells_acc, int cls)
 {
     extern __shared__ uint32_t smem[];
     const SwOpt &o = hdr->opt;
-    const int n = hdr->n_tasks;
     const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;
@@ -215,16 +260,24 @@ k_ext_side(const uint8_t *__restrict__ in, int in_bytes, ExtHdr *hdr, const uint
         if (chunk >= jend) break;
         const uint32_t job = chunk + lane;
         if (job < jend) {
-            const int k = (int)order[job];
-            ExtTask t = read_task(in, k);
-            if (!ext_task_ok(t, n, in_bytes)) { t.lq = t.lr = t.rq = t.rr = 0; t.pos = 8 + 8 * n; }
+            const int k = (int)order[job];                 // global task index
+            const ExtCall &cl = ext_call(cs, ext_locate(cs, k));
+            const uint8_t *in = base + cl.in_off;
+            const int n = cl.n_tasks;
+            ExtTask t = read_task(in, k - cl.task_base);
+            if (!ext_task_ok(t, n, cl.in_bytes)) { t.lq = t.lr = t.rq = t.rr = 0; t.pos = 8 + 8 * n; }
             const uint32_t *words = (const uint32_t *)in + t.pos;
             int *H = nullptr, *E = nullptr;
             if (!FAST) {
-                const long long boff = (long long)t.pos * 4 - (32 + 32LL * n);
-                int *reg = (int *)((char *)ehbase + 16 * boff + 32LL * k);
                 const int qm = t.lq > t.rq ? t.lq : t.rq;
-                H = reg; E = reg + (qm + 2);
+                const unsigned long long need = ((unsigned long long)(qm + 2) * 8 + 15) & ~15ull;
+                const unsigned long long off = atomicAdd(&hdr->eh_bump, need);
+                if (off + need > hdr->eh_cap) {            // scratch exhausted: report, do not overrun
+                    atomicExch(&hdr->err, -7);
+                    t.lq = t.lr = t.rq = t.rr = 0;
+                } else {
+                    H = (int *)((char *)ehbase + off); E = H + (qm + 2);
+                }
             }
             if (SIDE == 0) {
                 SideRes L;
@@ -245,7 +298,7 @@ k_ext_side(const uint8_t *__restrict__ in, int in_bytes, ExtHdr *hdr, const uint
                 }
                 int16_t rec[10];
                 ext_finalize(o, t, &L, &R, rec);
-                uint32_t *dst = (uint32_t *)(out + (size_t)10 * k);
+                uint32_t *dst = (uint32_t *)(out + cl.out_off + (size_t)10 * (k - cl.task_base));
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);

@@ -84,6 +84,7 @@ typedef struct {
     int64_t ext_calls, ext_tasks, ext_cells, ext_in_bytes, ext_out_bytes;
     int64_t aln_calls, aln_jobs, aln_cells, aln_in_bytes, aln_out_bytes;
     int64_t kernel_launches;     /* our kernels only */
+    int64_t ext_groups;          /* coalesced device submissions that served ext_calls */
     double  h2d_ms, kernel_ms, d2h_ms, host_ms; /* CUDA-event / wall split, summed over calls */
 } csbwa_stats;
 
@@ -118,16 +119,33 @@ int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs,
  * kernels are enqueued on `stream` and the call returns.
  * d_cells (nullable): uint64 accumulator, += exact DP cells computed.
  * Scratch must hold csbwa_*_scratch_bytes(); it may be reused between calls
- * on the same stream.                                                        */
+ * on the same stream.  csbwa_extend_scratch_bytes is the SAFE size (every task an outlier that
+ * needs int32 rows); a smaller scratch is accepted, and if the outlier rows do not fit the call
+ * reports CSBWA_E_SCRATCH through the header's status word instead of overrunning.          */
 int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes);
 int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int32_t n_tasks,
                               void *d_out /* int16[10*n_tasks] */,
                               void *d_cells, void *d_scratch, int64_t scratch_bytes,
                               void *stream);
 
-/* profiling aid: same launches with events between phases and a final sync;
- * ms3 = {prepare kernels, left-side kernels, right-side kernels} */
-int csbwa_extend_profile_device(const void *d_in, int32_t in_bytes, int32_t n_tasks, void *d_out,
+/* Several seam calls in ONE launch sequence (what the host path's call coalescing uses).
+ * The calls' wire buffers live at byte offsets of one device region. */
+typedef struct {
+    int64_t in_off;      /* byte offset of the call's wire buffer from d_in_base (multiple of 4) */
+    int32_t in_bytes;
+    int32_t n_tasks;
+    int64_t out_off;     /* offset of the call's reply from d_out_base, in shorts */
+    int32_t task_base;   /* running sum of n_tasks of the preceding calls */
+    int32_t pad;
+} csbwa_ext_call;
+int csbwa_extend_multi_device(const void *d_in_base, const csbwa_ext_call *h_calls,
+                              const csbwa_ext_call *d_calls, int32_t n_calls, void *d_out_base,
+                              void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream);
+
+/* profiling aid: same launches as csbwa_extend_multi_device with events between phases and a
+ * final sync; ms3 = {prepare kernels, left-side kernels, right-side kernels} */
+int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ext_call *h_calls,
+                                const csbwa_ext_call *d_calls, int32_t n_calls, void *d_out_base,
                                 void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream,
                                 float *ms3);
 

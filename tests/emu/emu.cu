@@ -159,3 +159,65 @@ extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, 
     if (n_fast) *n_fast = nf;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// the product's call coalescer (csrc/coalesce.hpp) driven by a HOST executor: same queueing code
+// as the CUDA path, the "device" is the emulation above.  Tests the group-commit logic (slot
+// reuse, parallel staging copies, per-call reply routing) with many threads and no GPU.
+// ---------------------------------------------------------------------------------------------
+#include <chrono>
+#include <thread>
+#include "../../cloud-scale-bwamem_b200/csrc/coalesce.hpp"
+
+struct HostCoExec {
+    std::vector<std::vector<uint8_t>> hin;
+    std::vector<std::vector<int16_t>> hout;
+    int delay_us;
+    uint8_t *in_staging(int slot) { return hin[slot].data(); }
+    int16_t *out_staging(int slot) { return hout[slot].data(); }
+    int run(int slot, const CoCall *calls, int n_calls, size_t span, int n_tasks)
+    {
+        (void)span; (void)n_tasks;
+        if (delay_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));
+        // the device reads the call table from the start of the staging buffer
+        const CoCall *tab = (const CoCall *)hin[slot].data();
+        for (int c = 0; c < n_calls; ++c) {
+            if (memcmp(&tab[c], &calls[c], sizeof(CoCall)) != 0) return -100;
+            int rc = emu_extend_wire(hin[slot].data() + tab[c].in_off, tab[c].in_bytes,
+                                     hout[slot].data() + tab[c].out_off, nullptr, nullptr, 0);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+};
+struct EmuCo {
+    HostCoExec ex;
+    Coalescer<HostCoExec> *co;
+};
+
+extern "C" void *emu_co_create(int n_slots, int n_workers, long long max_bytes, int max_tasks, int max_calls, int delay_us)
+{
+    EmuCo *e = new EmuCo();
+    e->ex.delay_us = delay_us;
+    e->ex.hin.assign(n_slots, std::vector<uint8_t>((size_t)max_bytes));
+    e->ex.hout.assign(n_slots, std::vector<int16_t>((size_t)max_tasks * 10 + 32));
+    Coalescer<HostCoExec>::Limits lim{(size_t)max_bytes, max_tasks, max_calls};
+    e->co = new Coalescer<HostCoExec>(&e->ex, n_slots, n_workers, lim);
+    return e;
+}
+extern "C" int emu_co_fits(void *h, int in_bytes, int n) { return ((EmuCo *)h)->co->fits(in_bytes, n) ? 1 : 0; }
+extern "C" int emu_co_submit(void *h, const uint8_t *in, int in_bytes, int16_t *out, int n)
+{
+    return ((EmuCo *)h)->co->submit(in, in_bytes, out, n);
+}
+extern "C" void emu_co_stats(void *h, long long *groups, long long *calls)
+{
+    *groups = ((EmuCo *)h)->co->groups_run();
+    *calls = ((EmuCo *)h)->co->calls_run();
+}
+extern "C" void emu_co_destroy(void *h)
+{
+    EmuCo *e = (EmuCo *)h;
+    delete e->co;
+    delete e;
+}

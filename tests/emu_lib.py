@@ -65,3 +65,39 @@ def load():
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
                                "-Xcompiler", "-fPIC", "-shared", "-o", LIB, SRC])
     return Emu(C.CDLL(LIB))
+
+
+class EmuCoalescer:
+    """The product's Coalescer<> template instantiated with a host executor (tests/emu/emu.cu)."""
+
+    def __init__(self, emu, n_slots=3, n_workers=2, max_bytes=1 << 22, max_tasks=20000, max_calls=16, delay_us=2000):
+        L = emu.lib
+        L.emu_co_create.restype = C.c_void_p
+        L.emu_co_create.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int]
+        L.emu_co_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.emu_co_fits.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.emu_co_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.emu_co_destroy.argtypes = [C.c_void_p]
+        self.L = L
+        self.h = L.emu_co_create(n_slots, n_workers, max_bytes, max_tasks, max_calls, delay_us)
+
+    def submit(self, wire):
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
+        out = np.zeros(10 * n, dtype=np.int16)
+        rc = self.L.emu_co_submit(self.h, wire.ctypes.data, wire.size, out.ctypes.data, n)
+        return rc, out
+
+    def fits(self, wire):
+        n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
+        return bool(self.L.emu_co_fits(self.h, wire.size, n))
+
+    def stats(self):
+        g, c = C.c_longlong(0), C.c_longlong(0)
+        self.L.emu_co_stats(self.h, C.byref(g), C.byref(c))
+        return g.value, c.value
+
+    def close(self):
+        if self.h:
+            self.L.emu_co_destroy(self.h)
+            self.h = None

@@ -217,6 +217,78 @@ def test_device_resident_api(pkg, oracle, gpu):
     assert int(d_cells.item()) == int(acells.sum())
 
 
+def test_multi_call_device_api(pkg, oracle, gpu):
+    """Several seam calls in ONE launch sequence (the coalesced path), device-resident."""
+    import torch
+    L = pkg.lib()
+    dev = torch.device("cuda:0")
+    w = pkg.workload.ext_workload(6000, 151, 1000000, 0.01, 400, 50, 20260108, reads_per_call=1500)
+    bufs = w["bufs"]
+    assert len(bufs) == 8
+    nt = [int(np.frombuffer(b[8:12].tobytes(), dtype="<i4")[0]) for b in bufs]
+    tab = np.zeros(len(bufs), dtype=pkg._lib.CALL_DTYPE)
+    pos = opos = tb = 0
+    for i, b in enumerate(bufs):
+        tab[i] = (pos, b.size, nt[i], opos, tb, 0)
+        pos += (b.size + 255) & ~255; opos += 10 * nt[i]; tb += nt[i]
+    h_in = np.zeros(pos, dtype=np.uint8)
+    for i, b in enumerate(bufs):
+        h_in[tab[i]["in_off"]:tab[i]["in_off"] + b.size] = b
+    d_in = torch.from_numpy(h_in).to(dev)
+    d_tab = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+    d_out = torch.zeros(opos, dtype=torch.int16, device=dev)
+    d_cells = torch.zeros(1, dtype=torch.int64, device=dev)
+    scr = torch.empty(L.csbwa_extend_scratch_bytes(tb, pos), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.csbwa_extend_multi_device(d_in.data_ptr(), tab.ctypes.data, d_tab.data_ptr(), len(bufs), d_out.data_ptr(),
+                                     d_cells.data_ptr(), scr.data_ptr(), scr.numel(), C.c_void_p(st))
+    assert rc == 0, L.csbwa_last_error()
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    cells = 0
+    for i, b in enumerate(bufs):
+        ref, rcells, _ = oracle.extend_wire(b, n_threads=8)
+        assert np.array_equal(got[tab[i]["out_off"]:tab[i]["out_off"] + 10 * nt[i]], ref), i
+        cells += int(rcells.sum())
+    assert int(d_cells.item()) == cells
+    # outlier-heavy input with a deliberately tiny scratch -> status word says E_SCRATCH, nothing overruns
+    rng = np.random.default_rng(5)
+    z = np.zeros(0, np.uint8)
+    big = [(rng.integers(0, 4, 400).astype(np.uint8), rng.integers(0, 4, 600).astype(np.uint8), z, z, 30, 30, 400)
+           for _ in range(300)]
+    wire = pkg.jni.packTasks(util.make_ext_params(pkg, big))
+    ref = oracle.extend_wire(wire, n_threads=8)[0]
+    got = pkg.jni.SWExtendFPGAJNI(0).swExtendFPGAJNI(3000, wire)      # host path grows/falls back as needed
+    assert np.array_equal(got, ref)
+    d_w = torch.from_numpy(wire).to(dev)
+    d_o = torch.zeros(3000, dtype=torch.int16, device=dev)
+    small = torch.empty(L.csbwa_extend_scratch_bytes(300, 0) + (96 << 10), dtype=torch.uint8, device=dev)
+    rc = L.csbwa_extend_batch_device(d_w.data_ptr(), wire.size, 300, d_o.data_ptr(), None, small.data_ptr(), small.numel(), C.c_void_p(st))
+    assert rc == 0
+    torch.cuda.synchronize()
+    err = small[:2048].cpu().numpy().view(np.int32)
+    assert (err == -7).any()
+
+
+def test_direct_path_subprocess(pkg, oracle, gpu):
+    """CSBWA_COALESCE=0 selects the one-call-per-submission path; same bits."""
+    import subprocess, sys, os
+    code = (
+        "import importlib,sys,numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "pkg=importlib.import_module('cloud-scale-bwamem_b200')\n"
+        "from oracle import oracle as O\n"
+        "w=pkg.workload.ext_workload(2048,151,500000,0.01,400,50,3,reads_per_call=4096)['bufs'][0]\n"
+        "n=int(np.frombuffer(w[8:12].tobytes(),dtype='<i4')[0])\n"
+        "got=pkg.jni.SWExtendFPGAJNI(0).swExtendFPGAJNI(10*n,w)\n"
+        "assert np.array_equal(got,O.extend_wire(w,n_threads=4)[0])\n"
+        "assert pkg.stats()['ext_groups']==0\n"
+        "print('direct-ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSBWA_COALESCE="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "direct-ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_large_batch_properties(pkg, oracle, gpu):
     """Size-independent properties at a BASELINE-scale call (32768 reads in one call):
     determinism, exact cell count, every task answered exactly once, invariants of ExtRet."""
