@@ -20,7 +20,7 @@ EXPORTS = [
     "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
-    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls",
 ]
 
 
@@ -72,6 +72,7 @@ def lib():
     L.csbwa_extend_profile_device.restype = C.c_int
     L.csbwa_extend_multi_device.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp]
     L.csbwa_extend_multi_device.restype = C.c_int
+    L.csbwa_extend_calls.argtypes = [vp, vp, vp, vp, i32, i32, C.c_int]; L.csbwa_extend_calls.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/csbwa_sw.h"
@@ -101,11 +102,55 @@ extern "C" int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes)
     return (int64_t)ext_scratch_bytes(n_tasks, in_bytes);
 }
 
+// Auxiliary streams of one submission stream: the per-class side kernels of a phase are
+// independent, so they are forked onto aux streams and joined before the next phase; their
+// tails (each is bounded by its longest job) then overlap instead of adding up.
+struct AuxSet {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork[2] = {nullptr, nullptr};
+    cudaEvent_t join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool ok = false;
+    int init()
+    {
+        for (auto &x : s) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (auto &x : fork) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        for (auto &r : join) for (auto &x : r) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        ok = true;
+        return CSBWA_OK;
+    }
+    void destroy()
+    {
+        for (auto &x : s) if (x) { cudaStreamDestroy(x); x = nullptr; }
+        for (auto &x : fork) if (x) { cudaEventDestroy(x); x = nullptr; }
+        for (auto &r : join) for (auto &x : r) if (x) { cudaEventDestroy(x); x = nullptr; }
+        ok = false;
+    }
+};
+// aux sets of caller-provided streams (device-resident API), created on first use
+static std::mutex g_aux_mu;
+static std::vector<std::pair<std::pair<int, cudaStream_t>, AuxSet *>> g_aux;
+static AuxSet *aux_for_stream(int dev, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_aux_mu);
+    for (auto &e : g_aux) if (e.first.first == dev && e.first.second == st) return e.second;
+    AuxSet *a = new AuxSet();
+    if (a->init() != CSBWA_OK) { a->destroy(); delete a; return nullptr; }
+    g_aux.push_back({{dev, st}, a});
+    return a;
+}
+
 template <int SIDE>
 static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch &sc, int16_t *d_out,
-                            unsigned long long *d_cells, int n, int sms, cudaStream_t st)
+                            unsigned long long *d_cells, int n, int sms, cudaStream_t st_main, AuxSet *aux)
 {
+    if (aux) {
+        cudaEventRecord(aux->fork[SIDE], st_main);
+        cudaStreamWaitEvent(aux->s[0], aux->fork[SIDE], 0);
+        cudaStreamWaitEvent(aux->s[1], aux->fork[SIDE], 0);
+    }
     for (int cls = 0; cls < EXT_NCLS; ++cls) {
+        // classes 0 (generic) and 1 on the main stream, 2 and 3 on the aux streams
+        cudaStream_t st = (aux && cls >= 2) ? aux->s[cls - 2] : st_main;
         if (cls == 0) {
             int grid = (n + EXT_BD - 1) / EXT_BD;
             if (grid > sms * 8) grid = sms * 8;
@@ -122,12 +167,18 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
                                                             d_out, d_cells, cls);
         }
     }
+    if (aux) {
+        for (int a = 0; a < 2; ++a) {
+            cudaEventRecord(aux->join[SIDE][a], aux->s[a]);
+            cudaStreamWaitEvent(st_main, aux->join[SIDE][a], 0);
+        }
+    }
 }
 
 // d_in: base of the input region; cs: the calls inside it; n: total tasks
 static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t *d_out,
                          unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
-                         cudaStream_t st, int dev)
+                         cudaStream_t st, int dev, AuxSet *aux)
 {
     if (n <= 0) return CSBWA_OK;
     const int64_t fixed = (int64_t)ext_scratch_fixed(n);
@@ -140,8 +191,8 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed));
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
-    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st);
-    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st);
+    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux);
+    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux);
     CU_TRY(cudaGetLastError());
     return CSBWA_OK;
 }
@@ -162,7 +213,8 @@ extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int
     int dev = 0;
     CU_TRY(cudaGetDevice(&dev));
     int rc = launch_extend((const uint8_t *)d_in, single_call(in_bytes, n_tasks), n_tasks, (int16_t *)d_out,
-                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
+                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev,
+                           aux_for_stream(dev, (cudaStream_t)stream));
     if (rc == CSBWA_OK && n_tasks > 0) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
         g_stats.kernel_launches += kExtLaunches;
@@ -192,7 +244,8 @@ extern "C" int csbwa_extend_multi_device(const void *d_in_base, const csbwa_ext_
     cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls;
     memcpy(&cs.single, &h_calls[0], sizeof(ExtCall));
     int rc = launch_extend((const uint8_t *)d_in_base, cs, (int)n, (int16_t *)d_out_base,
-                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev);
+                           (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev,
+                           aux_for_stream(dev, (cudaStream_t)stream));
     if (rc == CSBWA_OK && n > 0) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
         g_stats.kernel_launches += kExtLaunches;
@@ -234,9 +287,9 @@ extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ex
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
     CU_TRY(cudaEventRecord(ev[1], st));
-    launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr);
     CU_TRY(cudaEventRecord(ev[2], st));
-    launch_ext_side<1>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st);
+    launch_ext_side<1>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr);
     CU_TRY(cudaEventRecord(ev[3], st));
     CU_TRY(cudaEventSynchronize(ev[3]));
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]);
@@ -311,6 +364,7 @@ struct Ctx {
     unsigned long long *d_cells = nullptr;
     unsigned long long *h_cells = nullptr;   // pinned
     int32_t *h_err = nullptr;                // pinned
+    AuxSet aux;
 };
 
 static std::mutex g_mu;
@@ -367,6 +421,7 @@ static void destroy_ctx(Ctx *c)
 {
     cudaSetDevice(c->dev);
     if (c->st) cudaStreamSynchronize(c->st);
+    c->aux.destroy();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->h_in.p) cudaFreeHost(c->h_in.p);
     if (c->h_out.p) cudaFreeHost(c->h_out.p);
@@ -415,6 +470,7 @@ static int acquire_ctx(int device, Ctx **out)
     for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { destroy_ctx(c); return fail(CSBWA_E_CUDA, "event create failed"); }
     if (cudaMalloc(&c->d_cells, 8) != cudaSuccess || cudaMallocHost(&c->h_cells, 8) != cudaSuccess ||
         cudaMallocHost(&c->h_err, 8) != cudaSuccess) { destroy_ctx(c); return fail(CSBWA_E_NOMEM, "context allocation failed"); }
+    if (c->aux.init() != CSBWA_OK) { destroy_ctx(c); return fail(CSBWA_E_CUDA, "aux stream create failed"); }
     *out = c;
     return CSBWA_OK;
 }
@@ -457,6 +513,7 @@ struct CudaCoExec {
         uint8_t *h_in = nullptr; uint8_t *h_out = nullptr;     // pinned
         uint8_t *d_in = nullptr; uint8_t *d_out = nullptr; void *d_scratch = nullptr;
         int32_t *h_err = nullptr;
+        AuxSet aux;
     };
     int dev = 0;
     size_t in_cap = 0, out_cap = 0, scratch_cap = 0;
@@ -478,6 +535,7 @@ struct CudaCoExec {
             CU_TRY(cudaMalloc((void **)&s.d_in, in_cap));
             CU_TRY(cudaMalloc((void **)&s.d_out, out_cap));
             CU_TRY(cudaMalloc(&s.d_scratch, scratch_cap));
+            if (s.aux.init() != CSBWA_OK) return CSBWA_E_CUDA;
         }
         return CSBWA_OK;
     }
@@ -486,6 +544,7 @@ struct CudaCoExec {
         cudaSetDevice(dev);
         for (auto &s : slots) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            s.aux.destroy();
             if (s.h_in) cudaFreeHost(s.h_in);
             if (s.h_out) cudaFreeHost(s.h_out);
             if (s.h_err) cudaFreeHost(s.h_err);
@@ -512,7 +571,7 @@ struct CudaCoExec {
         cs.tab = (const ExtCall *)s.d_in; cs.n_calls = n_calls;
         memcpy(&cs.single, &calls[0], sizeof(ExtCall));
         int rc = launch_extend(s.d_in, cs, n_tasks, (int16_t *)s.d_out, (unsigned long long *)(s.d_out + tail),
-                               s.d_scratch, (int64_t)scratch_cap, s.st, dev);
+                               s.d_scratch, (int64_t)scratch_cap, s.st, dev, &s.aux);
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, tail + 8, cudaMemcpyDeviceToHost, s.st));
         CU_TRY(cudaMemcpyAsync(s.h_err, &((ExtHdr *)s.d_scratch)->err, 4, cudaMemcpyDeviceToHost, s.st));
@@ -543,7 +602,14 @@ struct CoDev {
 static CoDev *g_co[64] = {nullptr};
 static std::mutex g_co_mu;
 static const size_t kCoMaxBytes = (size_t)32 * 1024 * 1024;
-static const int kCoMaxTasks = 262144, kCoMaxCalls = 256, kCoSlots = 4, kCoWorkers = 3;
+static const int kCoMaxTasks = 262144, kCoMaxCalls = 256;
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
 
 static bool coalescing_enabled()
 {
@@ -562,10 +628,13 @@ static int get_coalescer(int dev, Coalescer<CudaCoExec> **out)
         int rc = ensure_dev_attrs(dev);
         if (rc) return rc;
         CoDev *d = new CoDev();
-        rc = d->exec.init(dev, kCoSlots, kCoMaxBytes, kCoMaxTasks);
+        // group buffers / submission threads per GPU (CSBWA_CO_SLOTS / CSBWA_CO_WORKERS to tune)
+        const int n_slots = env_int("CSBWA_CO_SLOTS", 8, 2, 32);
+        const int n_workers = env_int("CSBWA_CO_WORKERS", n_slots - 1, 1, n_slots);
+        rc = d->exec.init(dev, n_slots, kCoMaxBytes, kCoMaxTasks);
         if (rc) { d->exec.destroy(); delete d; return rc; }
         Coalescer<CudaCoExec>::Limits lim{kCoMaxBytes, kCoMaxTasks, kCoMaxCalls};
-        d->co = new Coalescer<CudaCoExec>(&d->exec, kCoSlots, kCoWorkers, lim);
+        d->co = new Coalescer<CudaCoExec>(&d->exec, n_slots, n_workers, lim);
         g_co[dev] = d;
     }
     *out = g_co[dev]->co;
@@ -630,7 +699,7 @@ static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out
     CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
     CU_TRY(cudaEventRecord(c->ev[1], c->st));
     rc = launch_extend((const uint8_t *)c->d_in.p, single_call(in_bytes, n), n, (int16_t *)c->d_out.p, c->d_cells,
-                       c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev);
+                       c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev, &c->aux);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(c->ev[2], c->st));
     CU_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
@@ -713,6 +782,31 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
         g_stats.host_ms += now_ms() - t0;
     }
     return CSBWA_OK;
+}
+
+// Many seam calls, T caller threads: what an executor JVM with T task threads does, for C hosts.
+// Each call goes through csbwa_extend_batch (so concurrent calls are coalesced).  Returns the
+// first error code, or 0.
+extern "C" int csbwa_extend_calls(const uint8_t *const *ins, const int32_t *in_bytes, int16_t *const *outs,
+                                  const int32_t *out_shorts, int32_t n_calls, int32_t n_threads, int device)
+{
+    if (n_calls < 0 || (n_calls > 0 && (!ins || !in_bytes || !outs || !out_shorts))) return fail(CSBWA_E_BADARG, "bad argument");
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_calls) n_threads = n_calls > 0 ? n_calls : 1;
+    std::atomic<int> next{0}, first_err{0};
+    auto body = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n_calls) break;
+            const int rc = csbwa_extend_batch(ins[i], in_bytes[i], outs[i], out_shorts[i], device);
+            if (rc != 0) { int z = 0; first_err.compare_exchange_strong(z, rc); }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(body);
+    body();
+    for (auto &t : th) t.join();
+    return first_err.load();
 }
 
 extern "C" int csbwa_get_stats(csbwa_stats *out)

@@ -145,8 +145,12 @@ CSW_HD void sw_extend_u8(const SwOpt &o, uint32_t *col, int stride, int qlen,
         int key = 0;          // h << 20 | j << 10 | lz1
         int lz1 = beg;        // 1 + position of the last zero among stored H so far (else beg)
         uint32_t *p = col + beg * stride;
+        // software pipeline: the word of column j+1 is loaded before column j is stored, so the
+        // shared-memory latency overlaps the DPX chain (columns never alias: stride > 0)
+        uint32_t wnext = beg < end ? *p : 0u;
         for (int j = beg; j < end; ++j) {
-            const uint32_t wv = *p;
+            const uint32_t wv = wnext;
+            wnext = p[stride];                            // column j+1 <= qlen always exists
             const int s = (int)prmt(tlo, thi, wv);
             const int hd = (int)prmt(wv, 0u, 0x4442u);   // byte 2
             const int e = (int)(wv >> 24);

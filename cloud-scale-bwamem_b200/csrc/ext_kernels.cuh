@@ -281,8 +281,10 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
             }
             if (SIDE == 0) {
                 SideRes L;
-                ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
-                                   t.reg_score, col, stride, H, E, L);
+                L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
+                if (t.lq > 0)        // (0 only after a validation / scratch failure, already reported)
+                    ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
+                                       t.reg_score, col, stride, H, E, L);
                 left[k] = L;
                 my_cells += (unsigned)L.cells;
             } else {

@@ -106,6 +106,11 @@ int csbwa_reset_stats(void);
 int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes,
                        int16_t *out, int32_t out_shorts, int device);
 
+/* Many seam calls driven by n_threads caller threads (what an executor JVM with that many task
+ * threads does), for C/C++ hosts; every call goes through csbwa_extend_batch. */
+int csbwa_extend_calls(const uint8_t *const *ins, const int32_t *in_bytes, int16_t *const *outs,
+                       const int32_t *out_shorts, int32_t n_calls, int32_t n_threads, int device);
+
 /* ---- seam (2): host buffers in, host buffers out ------------------------
  * Replaces the ksw_align2 loop of mem_matesw (N/bwamem_pair.c:159-228) /
  * SWAlign2 at S/worker2/MemSamPe.scala:1190.  Scoring = MemOptType defaults. */
