@@ -52,7 +52,7 @@ def task_count(buf):
 
 def gen_workload(pkg, n_pairs, rank, ref=None):
     return pkg.workload.ext_workload(n_pairs, CFG["L"], CFG["ref_bp"], CFG["eps"], CFG["mu"], CFG["sigma"],
-                                     CFG["seed"] + 1000 * rank, reads_per_call=READS_PER_CALL, ref=ref,
+                                     pkg.shard.shard_seed(CFG["seed"], rank), reads_per_call=READS_PER_CALL, ref=ref,
                                      chunk_pairs=max(65536, READS_PER_CALL // 2))
 
 
@@ -374,13 +374,8 @@ def main():
     st_after = pkg.stats()
 
     # ---- reduce over ranks ----
-    ms_t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    agg = torch.tensor([cells_total, total_tasks, w["n_reads"], in_bytes, out_bytes], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max = float(ms_t[0]), float(ms_t[1])
-    cells_all, tasks_all, reads_all, inb_all, outb_all = [float(x) for x in agg]
+    (ms_total_max, e2e_ms_max), (cells_all, tasks_all, reads_all, inb_all, outb_all) = pkg.shard.reduce_job(
+        [ms_total, e2e_s * 1e3], [cells_total, total_tasks, w["n_reads"], in_bytes, out_bytes], device=dev)
 
     if rank == 0:
         peaks = {}
