@@ -12,6 +12,11 @@ OK, E_NODEVICE, E_BADARG, E_BADWIRE, E_SHORTOUT, E_CUDA, E_NOMEM, E_SCRATCH = 0,
 JOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"),
                       ("xtra", "<i4"), ("pad", "<i4")])
 
+ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                         ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"), ("seedcov", "<i4"),
+                         ("secondary", "<i4"), ("hash", "<i8")])
+PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+REFSW_DTYPE = np.dtype([("rb", "<i8", (4,)), ("re", "<i8", (4,)), ("len", "<i8", (4,)), ("off", "<i8", (4,))])
 CALL_DTYPE = np.dtype([("in_off", "<i8"), ("in_bytes", "<i4"), ("n_tasks", "<i4"), ("out_off", "<i8"),
                        ("task_base", "<i4"), ("pad", "<i4")])
 
@@ -20,7 +25,7 @@ EXPORTS = [
     "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
-    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group",
 ]
 
 
@@ -73,6 +78,8 @@ def lib():
     L.csbwa_extend_multi_device.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp]
     L.csbwa_extend_multi_device.restype = C.c_int
     L.csbwa_extend_calls.argtypes = [vp, vp, vp, vp, i32, i32, C.c_int]; L.csbwa_extend_calls.restype = C.c_int
+    L.csbwa_matesw_group.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_int]
+    L.csbwa_matesw_group.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

@@ -977,6 +977,8 @@ extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *rea
     }
     return need;
 }
+#include "matesw_group.inc"
+
 // ------------------------------------------------------------------------------------
 // integer-pipe peak microbenchmark (roofline denominator)
 // ------------------------------------------------------------------------------------

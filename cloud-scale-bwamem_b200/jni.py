@@ -155,3 +155,65 @@ def SWAlign2(query, target, xtra, device=-1):
     jobs = np.zeros(1, dtype=_lib.JOB_DTYPE)
     jobs[0] = (0, len(q), len(q), len(t), xtra, 0)
     return SWAlnType(swAlign2Batch(jobs, seqs, device)[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# MateSWJNI mirror (object seam b2, flattened): S/jni/MateSWJNI.scala:23-26
+# ---------------------------------------------------------------------------------------------
+def make_alnreg(rBeg=0, rEnd=0, qBeg=0, qEnd=0, score=0, trueScore=0, sub=0, csub=0, subNum=0, width=0,
+                seedCov=0, secondary=0, hash=0):
+    """One MemAlnRegType (S/datatype/MemAlnRegType.scala:25-38) as a numpy record."""
+    r = np.zeros(1, dtype=_lib.ALNREG_DTYPE)
+    r[0] = (rBeg, rEnd, qBeg, qEnd, score, trueScore, sub, csub, subNum, width, seedCov, secondary, hash)
+    return r[0]
+
+
+class MateSWJNI:
+    """mateSWJNI(opt, pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+      pes            : 4 x (low, high, failed, avg, std)
+      seqsPairs      : list of 2*groupSize uint8 arrays (SeqSWType.seqTrans), index 2k+i
+      mateSWArray    : list of 2*groupSize region lists (numpy ALNREG records), index 2k+i
+      refSWArray     : one entry per selected region in (k, i, j) order: list of 4 (rBeg, rEnd, len, bytes|None)
+      refSWArraySize : int[2*groupSize]
+    returns the updated region lists, same indexing (what mateSWArrayToAlnRegPairArray rebuilds)."""
+
+    def __init__(self, device=-1):
+        self.device = device
+
+    def mateSWJNI(self, pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+        G = int(groupSize)
+        pes_a = np.zeros(4, dtype=_lib.PESTAT_DTYPE)
+        for r in range(4):
+            pes_a[r] = (pes[r][0], pes[r][1], pes[r][2], 0, pes[r][3], pes[r][4])
+        seq_len = np.array([len(s) for s in seqsPairs], dtype=np.int32)
+        seq_off = np.concatenate([[0], np.cumsum(seq_len)[:-1]]).astype(np.int64) if 2 * G else np.zeros(0, np.int64)
+        seqs = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqsPairs]) if seq_len.sum() else np.zeros(1, np.uint8)
+        reg_start = np.zeros(2 * G + 1, dtype=np.int32)
+        for x in range(2 * G):
+            reg_start[x + 1] = reg_start[x] + len(mateSWArray[x])
+        regs = np.zeros(max(1, int(reg_start[-1])), dtype=_lib.ALNREG_DTYPE)
+        for x in range(2 * G):
+            for j, rg in enumerate(mateSWArray[x]):
+                regs[reg_start[x] + j] = rg
+        refs = np.zeros(max(1, len(refSWArray)), dtype=_lib.REFSW_DTYPE)
+        wins, wpos = [], 0
+        for x, four in enumerate(refSWArray):
+            for r in range(4):
+                rb, re, ln, data = four[r]
+                refs[x]["rb"][r], refs[x]["re"][r], refs[x]["len"][r] = rb, re, ln
+                if data is not None and ln > 0:
+                    refs[x]["off"][r] = wpos
+                    wins.append(np.asarray(data, dtype=np.uint8)); wpos += len(data)
+                else:
+                    refs[x]["off"][r] = -1
+        win_seqs = np.concatenate(wins) if wins else np.zeros(1, np.uint8)
+        ref_count = np.asarray(refSWArraySize, dtype=np.int32)
+        cap = int(reg_start[-1]) + 4 * len(refSWArray) + 8
+        out = np.zeros(cap, dtype=_lib.ALNREG_DTYPE)
+        out_start = np.zeros(2 * G + 1, dtype=np.int32)
+        n = _lib.check(_lib.lib().csbwa_matesw_group(int(pacLen), pes_a.ctypes.data, G, seqs.ctypes.data, seq_off.ctypes.data,
+                                                     seq_len.ctypes.data, regs.ctypes.data, reg_start.ctypes.data,
+                                                     refs.ctypes.data, ref_count.ctypes.data, win_seqs.ctypes.data,
+                                                     out.ctypes.data, cap, out_start.ctypes.data, self.device))
+        assert n == out_start[-1]
+        return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)]

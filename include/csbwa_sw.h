@@ -118,6 +118,33 @@ int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs,
                        const uint8_t *seqs, int64_t seq_bytes,
                        csbwa_kswr *out, int device);
 
+/* ---- seam (2), object form: the whole of MateSWJNI.mateSWJNI, flattened ----
+ * (S/jni/MateSWJNI.scala:23-26; N/jni_mate_sw.c:58-60).  Semantics = the SCALA driver
+ * memSamPeGroupMateSW / memMateSwPreCompute / memSortAndDedup (S/worker2/MemSamPe.scala:1335-1369,
+ * 1111-1238; S/worker1/MemSortAndDedup.scala:33-141): every SWAlign2 is computed speculatively in
+ * one GPU batch, the order-dependent skip / append / sort / dedup logic is replayed on the host.
+ *   csbwa_alnreg = MemAlnRegType (S/datatype/MemAlnRegType.scala:25-38)
+ *   csbwa_pestat = MemPeStat     (S/datatype/MemPeStat.scala)
+ *   csbwa_refsw  = RefSWType     (S/jni/RefSWType.scala:21-32): 4 orientation windows of one
+ *                  selected region; off[r] = offset of the window bases in win_seqs (len 0 = null)
+ * seqs/seq_off/seq_len: the 2*group_size reads (SeqSWType.seqTrans), index 2k+i.
+ * regs/reg_start: current regions of every (pair k, end i), CSR over 2k+i   (= mateSWArray).
+ * refs/ref_count: windows of the selected regions in (k, i, j) order        (= refSWArray, refSWArraySize).
+ * out_regs/out_start: complete updated region lists, CSR over 2k+i          (= returned MateSWType[]).
+ * Returns the number of regions written, or a negative code. */
+typedef struct {
+    int64_t rb, re;
+    int32_t qb, qe, score, truesc, sub, csub, sub_n, w, seedcov, secondary;
+    int64_t hash;
+} csbwa_alnreg;
+typedef struct { int32_t low, high, failed, pad; double avg, std; } csbwa_pestat;
+typedef struct { int64_t rb[4], re[4], len[4], off[4]; } csbwa_refsw;
+int csbwa_matesw_group(int64_t l_pac, const csbwa_pestat *pes, int32_t group_size,
+                       const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                       const csbwa_alnreg *regs, const int32_t *reg_start,
+                       const csbwa_refsw *refs, const int32_t *ref_count, const uint8_t *win_seqs,
+                       csbwa_alnreg *out_regs, int32_t out_cap, int32_t *out_start, int device);
+
 /* ---- device-resident variants (pipelines, benchmarking) -----------------
  * All pointers are DEVICE pointers on the current CUDA device; `stream` is a
  * cudaStream_t passed as void* (NULL = default stream).  Nothing is synchronised:

@@ -467,3 +467,219 @@ int orc_align2_batch(const orc_job_t *jobs, int32_t n_jobs, const uint8_t *seqs,
     orc_parallel_for(n_jobs, n_threads, 4, orc_al_body, &c);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Mate-rescue driver (S/worker2/MemSamPe.scala:1111-1238, 1335-1369;         */
+/* S/worker1/MemSortAndDedup.scala:33-141).  Regions live in a per-pair pool  */
+/* and lists hold pool indices, so that the in-place `qEnd = qBeg` marks of   */
+/* memSortAndDedup are seen through every list that shares the object, as     */
+/* with the reference's shared MemAlnRegType instances.                       */
+/* ------------------------------------------------------------------------- */
+typedef struct { orc_alnreg_t *pool; int n_pool, cap_pool; } orc_pool_t;
+
+static int pool_add(orc_pool_t *p, const orc_alnreg_t *r)
+{
+    if (p->n_pool == p->cap_pool) {
+        p->cap_pool = p->cap_pool ? p->cap_pool * 2 : 64;
+        p->pool = (orc_alnreg_t *)realloc(p->pool, (size_t)p->cap_pool * sizeof(orc_alnreg_t));
+    }
+    p->pool[p->n_pool] = *r;
+    return p->n_pool++;
+}
+
+/* stable insertion sort of idx[0..n) by a 3-key comparison */
+typedef struct { int64_t a, b, c; } orc_key3;
+static void stable_sort_idx(int *idx, orc_key3 *keys, int n)
+{
+    for (int i = 1; i < n; ++i) {
+        int v = idx[i];
+        orc_key3 kv = keys[i];
+        int j = i - 1;
+        while (j >= 0 && (keys[j].a > kv.a || (keys[j].a == kv.a && (keys[j].b > kv.b ||
+               (keys[j].b == kv.b && keys[j].c > kv.c))))) {
+            idx[j + 1] = idx[j]; keys[j + 1] = keys[j]; --j;
+        }
+        idx[j + 1] = v; keys[j + 1] = kv;
+    }
+}
+
+/* memSortAndDedup on a list of pool indices; returns the new length (list rewritten) */
+static int orc_sort_dedup(orc_pool_t *p, int *lst, int n, float mask_level_redun)
+{
+    if (n <= 1) return n;                                            /* :34-36 */
+    orc_alnreg_t *R = p->pool;
+    orc_key3 *keys = (orc_key3 *)malloc((size_t)n * sizeof(orc_key3));
+    for (int i = 0; i < n; ++i) { keys[i].a = R[lst[i]].re; keys[i].b = R[lst[i]].rb; keys[i].c = 0; }
+    stable_sort_idx(lst, keys, n);                                   /* sortBy (rEnd, rBeg) :40 */
+    for (int i = 1; i < n; ++i) {                                    /* :51-98 */
+        orc_alnreg_t *ri = &R[lst[i]];
+        if (ri->rb < R[lst[i - 1]].re) {
+            int j = i - 1, brk = 0;
+            while (j >= 0 && ri->rb < R[lst[j]].re && !brk) {
+                orc_alnreg_t *rj = &R[lst[j]];
+                if (rj->qe != rj->qb) {
+                    int oq; int64_t mr; int mq;
+                    int64_t orr = rj->re - ri->rb;
+                    if (rj->qb < ri->qb) oq = rj->qe - ri->qb; else oq = ri->qe - rj->qb;
+                    if (rj->re - rj->rb < ri->re - ri->rb) mr = rj->re - rj->rb; else mr = ri->re - ri->rb;
+                    if (rj->qe - rj->qb < ri->qe - ri->qb) mq = rj->qe - rj->qb; else mq = ri->qe - ri->qb;
+                    /* Long/Int compared with Float: both sides promoted to Float (:73) */
+                    if ((float)orr > mask_level_redun * (float)mr && (float)oq > mask_level_redun * (float)mq) {
+                        if (ri->score < rj->score) { ri->qe = ri->qb; brk = 1; }
+                        else rj->qe = rj->qb;
+                    }
+                }
+                --j;
+            }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (R[lst[i]].qe > R[lst[i]].qb) lst[m++] = lst[i];   /* :101 */
+    for (int i = 0; i < m; ++i) { keys[i].a = -(int64_t)R[lst[i]].score; keys[i].b = R[lst[i]].rb; keys[i].c = R[lst[i]].qb; }
+    stable_sort_idx(lst, keys, m);                                   /* sortBy (-score, rBeg, qBeg) :114 */
+    for (int i = 1; i < m; ++i) {                                    /* :117-122 */
+        orc_alnreg_t *a = &R[lst[i]], *b = &R[lst[i - 1]];
+        if (a->score == b->score && a->rb == b->rb && a->qb == b->qb) a->qe = a->qb;
+    }
+    int m2 = 0;
+    for (int i = 0; i < m; ++i) if (R[lst[i]].qe > R[lst[i]].qb) lst[m2++] = lst[i];  /* :124 */
+    free(keys);
+    return m2;
+}
+
+/* memMateSwPreCompute (:1111-1238).  mate list in/out: *plst / *pn (pool indices). */
+static void orc_mate_precompute(const orc_opt_t *opt, int64_t l_pac, const orc_pestat_t *pes,
+                                const orc_alnreg_t *a, int mate_len, const uint8_t *mate,
+                                orc_pool_t *p, int **plst, int *pn, int *pcap,
+                                const orc_refsw_t *w, const uint8_t *win_seqs, int64_t *n_sw)
+{
+    const int min_seed_len = 19;                     /* MemOptType.minSeedLen */
+    const float mask_level_redun = 0.95f;            /* MemOptType.maskLevelRedun */
+    int skip[4];
+    for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed > 0 ? 1 : 0;
+    const int n_in = *pn;
+    for (int i = 0; i < n_in; ++i) {                 /* :1127-1149, mem_infer_dir inlined */
+        const orc_alnreg_t *m = &p->pool[(*plst)[i]];
+        int r1 = a->rb >= l_pac, r2 = m->rb >= l_pac;
+        int64_t rbl = m->rb;
+        if (r1 != r2) rbl = (l_pac << 1) - 1 - m->rb;
+        int dist = (int)(a->rb - rbl);
+        if (rbl > a->rb) dist = (int)(rbl - a->rb);
+        int c1 = (r1 == r2) ? 0 : 1, c2 = (rbl > a->rb) ? 0 : 3;
+        int r = c1 ^ c2;
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+    }
+    /* mateRegsUpdated: sorted-but-not-deduped working vector (:1155-1161, 1224) */
+    int nu = n_in, capu = n_in + 8;
+    int *upd = (int *)malloc((size_t)capu * sizeof(int));
+    memcpy(upd, *plst, (size_t)n_in * sizeof(int));
+    int *last = NULL, nlast = 0;                     /* regArray.regs of the most recent dedup */
+    int n = 0;
+    uint8_t *rev = NULL;
+    for (int r = 0; r < 4; ++r) {
+        if (skip[r]) continue;
+        int is_rev = ((r >> 1) != (r & 1));
+        const uint8_t *seq = mate;
+        if (is_rev) {                                /* :1175-1184 */
+            if (!rev) rev = (uint8_t *)malloc((size_t)mate_len + 1);
+            for (int i = 0; i < mate_len; ++i) rev[mate_len - 1 - i] = mate[i] < 4 ? (uint8_t)(3 - mate[i]) : 4;
+            seq = rev;
+        }
+        if (w->len[r] == w->re[r] - w->rb[r]) {      /* :1186 */
+            int xtra = ORC_XSUBO | ORC_XSTART | ((mate_len * opt->a < 250) ? ORC_XBYTE : 0) | (min_seed_len * opt->a);
+            uint8_t *q = (uint8_t *)malloc((size_t)mate_len + 1);
+            uint8_t *t = (uint8_t *)malloc((size_t)w->len[r] + 1);
+            memcpy(q, seq, (size_t)mate_len);
+            if (w->len[r] > 0) memcpy(t, win_seqs + w->off[r], (size_t)w->len[r]);
+            orc_aln_t aln;
+            orc_sw_align2(mate_len, q, (int)w->len[r], t, 5, opt, xtra, &aln);
+            free(q); free(t);
+            if (n_sw) ++*n_sw;
+            if (aln.score >= min_seed_len && aln.qb >= 0) {          /* :1193 */
+                orc_alnreg_t b;
+                memset(&b, 0, sizeof b);
+                if (is_rev) {
+                    b.qb = mate_len - (aln.qe + 1); b.qe = mate_len - aln.qb;
+                    b.rb = (l_pac << 1) - (w->rb[r] + aln.te + 1);
+                    b.re = (l_pac << 1) - (w->rb[r] + aln.tb);
+                } else {                             /* QUIRK :1203-1204: rBeg = rEnd = rb + te + 1 */
+                    b.qb = aln.qb; b.qe = aln.qe + 1;
+                    b.rb = w->rb[r] + aln.te + 1; b.re = w->rb[r] + aln.te + 1;
+                }
+                b.score = aln.score; b.csub = aln.score2; b.secondary = -1;
+                if (b.re - b.rb < (int64_t)(b.qe - b.qb)) b.seedcov = (int)((uint64_t)(b.re - b.rb) >> 1);
+                else b.seedcov = (int)((uint32_t)(b.qe - b.qb) >> 1);
+                if (nu == capu) { capu *= 2; upd = (int *)realloc(upd, (size_t)capu * sizeof(int)); }
+                upd[nu++] = pool_add(p, &b);
+            }
+            ++n;
+        }
+        if (n > 0) {                                 /* :1221-1230 */
+            orc_key3 *keys = (orc_key3 *)malloc((size_t)(nu > 0 ? nu : 1) * sizeof(orc_key3));
+            for (int i = 0; i < nu; ++i) { keys[i].a = p->pool[upd[i]].score; keys[i].b = 0; keys[i].c = 0; }
+            stable_sort_idx(upd, keys, nu);          /* sortBy(score), ascending, stable */
+            free(keys);
+            free(last);
+            last = (int *)malloc((size_t)(nu > 0 ? nu : 1) * sizeof(int));
+            memcpy(last, upd, (size_t)nu * sizeof(int));
+            nlast = orc_sort_dedup(p, last, nu, mask_level_redun);
+        }
+    }
+    if (n > 0) {                                     /* :1236 */
+        if (nlast > *pcap) { *pcap = nlast + 8; *plst = (int *)realloc(*plst, (size_t)*pcap * sizeof(int)); }
+        memcpy(*plst, last, (size_t)nlast * sizeof(int));
+        *pn = nlast;
+    }
+    free(upd); free(last); free(rev);
+}
+
+int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
+                     const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                     const orc_alnreg_t *regs, const int32_t *reg_start,
+                     const orc_refsw_t *refs, const int32_t *ref_count, const uint8_t *win_seqs,
+                     orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start, int64_t *n_sw_calls)
+{
+    orc_opt_t opt;
+    orc_default_opt(&opt);
+    const int pen_unpaired = 17, max_matesw = 100;   /* MemOptType.scala:34,55 */
+    int64_t ref_pos = 0;
+    int32_t out_n = 0;
+    if (n_sw_calls) *n_sw_calls = 0;
+    for (int k = 0; k < group_size; ++k) {
+        orc_pool_t pool = {NULL, 0, 0};
+        int *cur[2]; int ncur[2], capcur[2];
+        int *sel[2]; int nsel[2];
+        for (int i = 0; i < 2; ++i) {
+            const int s = reg_start[2 * k + i], e = reg_start[2 * k + i + 1];
+            ncur[i] = e - s; capcur[i] = ncur[i] + 8;
+            cur[i] = (int *)malloc((size_t)capcur[i] * sizeof(int));
+            sel[i] = (int *)malloc((size_t)(ncur[i] + 1) * sizeof(int));
+            nsel[i] = 0;
+            for (int j = 0; j < ncur[i]; ++j) cur[i][j] = pool_add(&pool, &regs[s + j]);
+            for (int j = 0; j < ncur[i]; ++j)        /* memSamPeGroupPrepare :1279-1290 */
+                if (regs[s + j].score >= regs[s].score - pen_unpaired) sel[i][nsel[i]++] = cur[i][j];
+            int expect = nsel[i] > max_matesw ? max_matesw : nsel[i];
+            if (ref_count[2 * k + i] != expect) { free(cur[0]); if (i) free(cur[1]); return -10; }
+        }
+        for (int i = 0; i < 2; ++i) {                /* memSamPeGroupMateSW :1346-1364 */
+            const int ib = 1 - i;
+            for (int j = 0; j < ref_count[2 * k + i]; ++j) {
+                const orc_alnreg_t a = pool.pool[sel[i][j]];   /* anchor (only rBeg is read) */
+                orc_mate_precompute(&opt, l_pac, pes, &a, seq_len[2 * k + ib], seqs + seq_off[2 * k + ib],
+                                    &pool, &cur[ib], &ncur[ib], &capcur[ib], &refs[ref_pos], win_seqs, n_sw_calls);
+                ++ref_pos;
+            }
+        }
+        for (int i = 0; i < 2; ++i) {
+            out_start[2 * k + i] = out_n;
+            for (int j = 0; j < ncur[i]; ++j) {
+                if (out_n >= out_cap) return -11;
+                out_regs[out_n++] = pool.pool[cur[i][j]];
+            }
+            free(cur[i]); free(sel[i]);
+        }
+        free(pool.pool);
+    }
+    out_start[2 * group_size] = out_n;
+    return out_n;
+}

@@ -113,6 +113,29 @@ int orc_align2_batch(const orc_job_t *jobs, int32_t n_jobs, const uint8_t *seqs,
                      int32_t *out7 /* n_jobs x {score,te,qe,score2,te2,tb,qb} */,
                      int64_t *cells_per_job, int n_threads);
 
+/* ---- mate-rescue driver (the object seam, flattened) ------------------------------------
+ * MemAlnRegType (S/datatype/MemAlnRegType.scala:25-38), MemPeStat (S/datatype/MemPeStat.scala),
+ * and the four orientation windows of one selected region (RefSWType, S/jni/RefSWType.scala). */
+typedef struct {
+    int64_t rb, re;
+    int32_t qb, qe, score, truesc, sub, csub, sub_n, w, seedcov, secondary;
+    int64_t hash;
+} orc_alnreg_t;
+typedef struct { int32_t low, high, failed, pad; double avg, std; } orc_pestat_t;
+typedef struct { int64_t rb[4], re[4], len[4], off[4]; } orc_refsw_t;   /* off: into win_seqs, -1 = null */
+
+/* memSamPeGroupMateSW + memMateSwPreCompute + memSortAndDedup
+ * (S/worker2/MemSamPe.scala:1335-1369, 1111-1238; S/worker1/MemSortAndDedup.scala:33-141).
+ * regs/reg_start: current regions per (pair k, end i) in CSR form, index 2k+i.
+ * refs: windows of the selected regions, in (k, i, j) order; ref_count[2k+i] of them per (k,i).
+ * Returns the total number of output regions (out_start is the CSR), or <0. */
+int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
+                     const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                     const orc_alnreg_t *regs, const int32_t *reg_start,
+                     const orc_refsw_t *refs, const int32_t *ref_count, const uint8_t *win_seqs,
+                     orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start,
+                     int64_t *n_sw_calls);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -222,3 +222,58 @@ def ref_ksw_align2(query, target, xtra, opt=None):
     t, tp = _u8(np.array(target, dtype=np.uint8, copy=True))
     r = ref().ksw_align2(len(q), qp, len(t), tp, 5, C.addressof(o.mat), o.o_del, o.e_del, o.o_ins, o.e_ins, xtra, None)
     return {k: getattr(r, k) for k, _ in Kswr._fields_}
+
+
+# --------------------------------------------------------------------------
+# mate-rescue group driver (object seam, flattened) -- same flat layout as the product
+# --------------------------------------------------------------------------
+ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                         ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"), ("seedcov", "<i4"),
+                         ("secondary", "<i4"), ("hash", "<i8")])
+PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+REFSW_DTYPE = np.dtype([("rb", "<i8", (4,)), ("re", "<i8", (4,)), ("len", "<i8", (4,)), ("off", "<i8", (4,))])
+
+
+def matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+    """Oracle counterpart of jni.MateSWJNI.mateSWJNI (same arguments); also returns the number of
+    SWAlign2 calls the sequential driver actually made."""
+    G = int(groupSize)
+    pes_a = np.zeros(4, dtype=PESTAT_DTYPE)
+    for r in range(4):
+        pes_a[r] = (pes[r][0], pes[r][1], pes[r][2], 0, pes[r][3], pes[r][4])
+    seq_len = np.array([len(s) for s in seqsPairs], dtype=np.int32)
+    seq_off = np.concatenate([[0], np.cumsum(seq_len)[:-1]]).astype(np.int64) if 2 * G else np.zeros(0, np.int64)
+    seqs = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqsPairs]) if seq_len.sum() else np.zeros(1, np.uint8)
+    reg_start = np.zeros(2 * G + 1, dtype=np.int32)
+    for x in range(2 * G):
+        reg_start[x + 1] = reg_start[x] + len(mateSWArray[x])
+    regs = np.zeros(max(1, int(reg_start[-1])), dtype=ALNREG_DTYPE)
+    for x in range(2 * G):
+        for j, rg in enumerate(mateSWArray[x]):
+            regs[reg_start[x] + j] = rg
+    refs = np.zeros(max(1, len(refSWArray)), dtype=REFSW_DTYPE)
+    wins, wpos = [], 0
+    for x, four in enumerate(refSWArray):
+        for r in range(4):
+            rb, re, ln, data = four[r]
+            refs[x]["rb"][r], refs[x]["re"][r], refs[x]["len"][r] = rb, re, ln
+            if data is not None and ln > 0:
+                refs[x]["off"][r] = wpos
+                wins.append(np.asarray(data, dtype=np.uint8)); wpos += len(data)
+            else:
+                refs[x]["off"][r] = -1
+    win_seqs = np.concatenate(wins) if wins else np.zeros(1, np.uint8)
+    ref_count = np.asarray(refSWArraySize, dtype=np.int32)
+    cap = int(reg_start[-1]) + 4 * len(refSWArray) + 8
+    out = np.zeros(cap, dtype=ALNREG_DTYPE)
+    out_start = np.zeros(2 * G + 1, dtype=np.int32)
+    nsw = C.c_int64(0)
+    L = lib()
+    L.orc_matesw_group.argtypes = [C.c_int64, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.orc_matesw_group.restype = C.c_int
+    n = L.orc_matesw_group(int(pacLen), pes_a.ctypes.data, G, seqs.ctypes.data, seq_off.ctypes.data, seq_len.ctypes.data,
+                           regs.ctypes.data, reg_start.ctypes.data, refs.ctypes.data, ref_count.ctypes.data,
+                           win_seqs.ctypes.data, out.ctypes.data, cap, out_start.ctypes.data, C.addressof(nsw))
+    if n < 0:
+        raise RuntimeError("orc_matesw_group failed: %d" % n)
+    return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)], nsw.value

@@ -341,3 +341,206 @@ def build_jobs(pairs, xtras, dtype):
         chunks += [q, t]; off += len(q) + len(t)
     seqs = np.concatenate(chunks) if off else np.zeros(1, np.uint8)
     return jobs, seqs
+
+
+# ---------------------------------------------------------------------------------------
+# mate-rescue driver: literal transliteration with SHARED objects (like the Scala) + generator
+# ---------------------------------------------------------------------------------------
+class Reg:
+    """MemAlnRegType with reference semantics (S/datatype/MemAlnRegType.scala:25-38)."""
+    F = ("rb", "re", "qb", "qe", "score", "truesc", "sub", "csub", "sub_n", "w", "seedcov", "secondary", "hash")
+
+    def __init__(self, **kw):
+        for f in self.F:
+            setattr(self, f, int(kw.get(f, 0)))
+
+    def astuple(self):
+        return tuple(getattr(self, f) for f in self.F)
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def py_mem_sort_and_dedup(regs, mask_level_redun=0.95):
+    """S/worker1/MemSortAndDedup.scala:33-141 (mutates the shared Reg objects, returns a new list)."""
+    if len(regs) <= 1:
+        return regs
+    regs = sorted(regs, key=lambda r: (r.re, r.rb))
+    ml = np.float32(mask_level_redun)
+    i = 1
+    while i < len(regs):
+        if regs[i].rb < regs[i - 1].re:
+            j = i - 1
+            brk = False
+            while j >= 0 and regs[i].rb < regs[j].re and not brk:
+                if regs[j].qe != regs[j].qb:
+                    orr = regs[j].re - regs[i].rb
+                    oq = regs[j].qe - regs[i].qb if regs[j].qb < regs[i].qb else regs[i].qe - regs[j].qb
+                    mr = min(regs[j].re - regs[j].rb, regs[i].re - regs[i].rb)
+                    mq = min(regs[j].qe - regs[j].qb, regs[i].qe - regs[i].qb)
+                    if np.float32(orr) > ml * np.float32(mr) and np.float32(oq) > ml * np.float32(mq):
+                        if regs[i].score < regs[j].score:
+                            regs[i].qe = regs[i].qb
+                            brk = True
+                        else:
+                            regs[j].qe = regs[j].qb
+                j -= 1
+        i += 1
+    regs = [r for r in regs if r.qe > r.qb]
+    regs = sorted(regs, key=lambda r: (-r.score, r.rb, r.qb))
+    for i in range(1, len(regs)):
+        if regs[i].score == regs[i - 1].score and regs[i].rb == regs[i - 1].rb and regs[i].qb == regs[i - 1].qb:
+            regs[i].qe = regs[i].qb
+    return [r for r in regs if r.qe > r.qb]
+
+
+def py_mate_precompute(oracle, l_pac, pes, reg, mate, mate_regs, ref4):
+    """memMateSwPreCompute, S/worker2/MemSamPe.scala:1111-1238.  pes[r] = (low, high, failed, avg, std);
+    ref4[r] = (rBeg, rEnd, len, bytes|None).  SWAlign2 itself is served by the (separately pinned) oracle."""
+    L = len(mate)
+    skip = [1 if pes[r][2] > 0 else 0 for r in range(4)]
+    for m in (mate_regs or []):
+        r1 = reg.rb >= l_pac
+        r2 = m.rb >= l_pac
+        rbl = m.rb
+        if r1 != r2:
+            rbl = (l_pac << 1) - 1 - m.rb
+        dist = reg.rb - rbl
+        if rbl > reg.rb:
+            dist = rbl - reg.rb
+        r = (0 if r1 == r2 else 1) ^ (0 if rbl > reg.rb else 3)
+        if pes[r][0] <= dist <= pes[r][1]:
+            skip[r] = 1
+    upd = list(mate_regs or [])
+    n = 0
+    last = None
+    for r in range(4):
+        if skip[r] == 0:
+            seq = mate
+            is_rev = 1 if (r >> 1) != (r & 1) else 0
+            if is_rev:
+                seq = np.array([3 - b if b < 4 else 4 for b in mate[::-1]], dtype=np.uint8)
+            rb, re, ln, data = ref4[r]
+            if ln == re - rb:
+                xtra = XSUBO | XSTART | (XBYTE if L * 1 < 250 else 0) | 19
+                a = oracle.sw_align(seq, data if data is not None else np.zeros(0, np.uint8), xtra)
+                if a["score"] >= 19 and a["qb"] >= 0:
+                    t = Reg()
+                    if is_rev:
+                        t.qb = L - (a["qe"] + 1); t.qe = L - a["qb"]
+                        t.rb = (l_pac << 1) - (rb + a["te"] + 1); t.re = (l_pac << 1) - (rb + a["tb"])
+                    else:
+                        t.qb = a["qb"]; t.qe = a["qe"] + 1
+                        t.rb = rb + a["te"] + 1; t.re = rb + a["te"] + 1
+                    t.score = a["score"]; t.csub = a["score2"]; t.secondary = -1
+                    t.seedcov = ((t.re - t.rb) & 0xffffffffffffffff) >> 1 if (t.re - t.rb < t.qe - t.qb) else ((t.qe - t.qb) & 0xffffffff) >> 1
+                    upd = upd + [t]
+                n += 1
+            if n > 0:
+                upd = sorted(upd, key=lambda x: x.score)
+                last = py_mem_sort_and_dedup(list(upd))
+    return (n, last) if n > 0 else (n, mate_regs)
+
+
+def py_matesw_group(oracle, l_pac, pes, G, seqs, reg_lists, refs, ref_count):
+    """memSamPeGroupPrepare selection + memSamPeGroupMateSW (S/worker2/MemSamPe.scala:1279-1290, 1335-1369)."""
+    cur = [[Reg(**{f: int(r[f]) for f in Reg.F}) for r in lst] for lst in reg_lists]
+    x = 0
+    for k in range(G):
+        sel = []
+        for i in range(2):
+            lst = cur[2 * k + i]
+            s = [r for r in lst if r.score >= lst[0].score - 17] if lst else []
+            assert ref_count[2 * k + i] == min(len(s), 100)
+            sel.append(s)
+        for i in range(2):
+            ib = 1 - i
+            for j in range(ref_count[2 * k + i]):
+                n, new = py_mate_precompute(oracle, l_pac, pes, sel[i][j], seqs[2 * k + ib], cur[2 * k + ib], refs[x])
+                cur[2 * k + ib] = new
+                x += 1
+    return [[r.astuple() for r in lst] for lst in cur]
+
+
+def bns_get_seq(ref, beg, end):
+    """bnsGetSeq on a forward reference given 1 base/byte (S/util/BNTSeqUtil.scala:37-83)."""
+    l_pac = len(ref)
+    if end < beg:
+        beg, end = end, beg
+    end = min(end, 2 * l_pac)
+    beg = max(beg, 0)
+    if beg >= l_pac or end <= l_pac:
+        if beg >= l_pac:
+            bf, ef = 2 * l_pac - end, 2 * l_pac - beg
+            return (3 - ref[bf:ef][::-1]).astype(np.uint8), end - beg
+        return ref[beg:end].copy(), end - beg
+    return np.zeros(end - beg, np.uint8), 0
+
+
+def aln_reg_ref(ref, pes, reg_rb, mate_len):
+    """getAlnRegRefJNI window arithmetic (S/worker2/MemSamPe.scala:1810-1878)."""
+    l_pac = len(ref)
+    out = []
+    for r in range(4):
+        if pes[r][2] != 0:
+            out.append((-1, -1, 0, None))
+            continue
+        is_rev = (r >> 1) != (r & 1)
+        is_larger = not (r >> 1)
+        low, high = pes[r][0], pes[r][1]
+        if not is_rev:
+            rb = reg_rb + low if is_larger else reg_rb - high
+            re = reg_rb + high + mate_len if is_larger else reg_rb - low + mate_len
+        else:
+            rb = reg_rb + low - mate_len if is_larger else reg_rb - high - mate_len
+            re = reg_rb + high if is_larger else reg_rb - low
+        rb = max(rb, 0)
+        re = min(re, 2 * l_pac)
+        seq, ln = bns_get_seq(ref, rb, re)
+        out.append((rb, re, ln, seq if ln > 0 else None))
+    return out
+
+
+def gen_matesw_group(rng, pkg, ref, G, L, pes, p_anchor=0.85, p_mate_present=0.4):
+    """Synthetic input of the MateSWJNI seam: reads, current region lists, windows of the selected regions."""
+    l_pac = len(ref)
+    mk = pkg.jni.make_alnreg
+    seqs, reg_lists = [], []
+    for k in range(G):
+        ins = int(np.clip(rng.normal(400, 50), L, 2000))
+        p = int(rng.integers(3000, l_pac - 6000))
+        r1 = mutate(rng, ref[p:p + L], 0.01)[:L]
+        r1 = np.concatenate([r1, rng.integers(0, 4, L - len(r1)).astype(np.uint8)])
+        frag2 = ref[p + ins - L:p + ins]
+        r2 = mutate(rng, (3 - frag2[::-1]).astype(np.uint8), 0.01)[:L]
+        r2 = np.concatenate([r2, rng.integers(0, 4, L - len(r2)).astype(np.uint8)])
+        seqs += [r1, r2]
+        true = [mk(p, p + L, 0, L, L - int(rng.integers(0, 12)), L - 12, 0, 0, 0, 100, L - 20, -1, 7),
+                mk(2 * l_pac - (p + ins), 2 * l_pac - (p + ins) + L, 0, L, L - int(rng.integers(0, 12)), L - 12, 0, 0, 0, 100, L - 20, -1, 9)]
+        for i in range(2):
+            lst = []
+            present = rng.random() < (p_anchor if i == 0 else p_mate_present)
+            if present:
+                lst.append(true[i])
+            for _ in range(int(rng.integers(0, 3))):                 # decoys, some inside penUnpaired of the best
+                rb = int(rng.integers(1000, 2 * l_pac - 1000 - L))
+                if rb < l_pac < rb + L:
+                    rb = l_pac + 10
+                qb = int(rng.integers(0, 30)); qe = L - int(rng.integers(0, 30))
+                sc = int(rng.integers(40, L))
+                lst.append(mk(rb, rb + (qe - qb), qb, qe, sc, sc, 0, 0, 0, 100, 30, -1, 11))
+            if rng.random() < 0.15 and lst:                           # near-duplicate of an existing region
+                d = lst[0].copy(); d["rb"] += 2; d["re"] += 2; d["score"] -= 3
+                lst.append(d)
+            lst.sort(key=lambda r: (-int(r["score"]), int(r["rb"]), int(r["qb"])))
+            reg_lists.append(lst)
+    refs, ref_count = [], []
+    for k in range(G):
+        for i in range(2):
+            lst = reg_lists[2 * k + i]
+            sel = [r for r in lst if r["score"] >= lst[0]["score"] - 17][:100] if lst else []
+            ref_count.append(len(sel))
+            for r in sel:
+                refs.append(aln_reg_ref(ref, pes, int(r["rb"]), L))
+    return seqs, reg_lists, refs, ref_count
