@@ -343,6 +343,7 @@ def main():
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
+    st_e2e0 = pkg.stats()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -350,6 +351,7 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    st_e2e1 = pkg.stats()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
@@ -411,7 +413,10 @@ def main():
                     "api": "csbwa_extend_batch (host buffers, pinned staging, H2D+kernels+D2H per call)"},
             "gpu_launches": int(kernels_per_step * args.steps * world),
             "cuda_graph": graph is not None, "streams": nstreams, "calls_per_launch_sequence": gsz,
-            "e2e_calls_per_device_submission": (st_after["ext_calls"] / max(1, st_after["ext_groups"])),
+            "e2e_calls_per_device_submission": ((st_e2e1["ext_calls"] - st_e2e0["ext_calls"]) /
+                                                max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
+            "e2e_ms_per_device_submission": ((st_e2e1["host_ms"] - st_e2e0["host_ms"]) /
+                                             max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
             "clocks": clocks,
             "roofline": {
                 "bound": "int_alu", "kernel": "k_ext_side (left + right, all size classes)",
