@@ -17,6 +17,8 @@ ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i
                          ("secondary", "<i4"), ("hash", "<i8")])
 PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
 REFSW_DTYPE = np.dtype([("rb", "<i8", (4,)), ("re", "<i8", (4,)), ("len", "<i8", (4,)), ("off", "<i8", (4,))])
+GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"), ("w", "<i4"),
+                       ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
 CALL_DTYPE = np.dtype([("in_off", "<i8"), ("in_bytes", "<i4"), ("n_tasks", "<i4"), ("out_off", "<i8"),
                        ("task_base", "<i4"), ("pad", "<i4")])
 
@@ -25,14 +27,15 @@ EXPORTS = [
     "csbwa_get_stats", "csbwa_reset_stats", "csbwa_extend_batch", "csbwa_align2_batch",
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
-    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group",
+    "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
+    "csbwa_global_batch_device", "csbwa_global_launches_per_call",
 ]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("ext_calls", "ext_tasks", "ext_cells", "ext_in_bytes", "ext_out_bytes",
                                          "aln_calls", "aln_jobs", "aln_cells", "aln_in_bytes", "aln_out_bytes",
-                                         "kernel_launches", "ext_groups")] + \
+                                         "kernel_launches", "ext_groups", "glb_calls", "glb_jobs", "glb_cells")] + \
                [(n, C.c_double) for n in ("h2d_ms", "kernel_ms", "d2h_ms", "host_ms")]
 
 
@@ -80,6 +83,11 @@ def lib():
     L.csbwa_extend_calls.argtypes = [vp, vp, vp, vp, i32, i32, C.c_int]; L.csbwa_extend_calls.restype = C.c_int
     L.csbwa_matesw_group.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_int]
     L.csbwa_matesw_group.restype = C.c_int
+    L.csbwa_global_batch.argtypes = [vp, i32, vp, i64, vp, vp, i64, C.c_int]; L.csbwa_global_batch.restype = C.c_int
+    L.csbwa_global_scratch_bytes.argtypes = [i32, i32, i64]; L.csbwa_global_scratch_bytes.restype = i64
+    L.csbwa_global_batch_device.argtypes = [vp, i32, vp, i32, i64, vp, vp, vp, vp, i64, vp]
+    L.csbwa_global_batch_device.restype = C.c_int
+    L.csbwa_global_launches_per_call.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

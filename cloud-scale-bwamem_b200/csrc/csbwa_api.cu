@@ -21,6 +21,7 @@
 #define CSBWA_E_BADWIRE_DEV CSBWA_E_BADWIRE
 #include "ext_kernels.cuh"
 #include "aln_kernels.cuh"
+#include "glb_kernels.cuh"
 #include "peak_kernels.cuh"
 #include "coalesce.hpp"
 
@@ -978,6 +979,111 @@ extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *rea
     return need;
 }
 #include "matesw_group.inc"
+
+// ------------------------------------------------------------------------------------
+// SWGlobal (the "next" row of the hot path: CIGAR generation, S/util/SWUtil.scala:233-397,
+// driven by bwaGenCigar2, S/worker2/MemRegToADAMSAM.scala:738-893)
+// ------------------------------------------------------------------------------------
+static_assert(sizeof(csbwa_gjob) == sizeof(GlbJob), "gjob layout");
+static const int kGlbLaunches = 2;
+extern "C" int csbwa_global_launches_per_call(void) { return kGlbLaunches; }
+
+static int glb_grid_warps(int n, int sms)
+{
+    int warps = (n + 31) / 32;
+    const int cap = sms * 16;            // persistent: 4 blocks of 4 warps per SM
+    return warps < cap ? warps : cap;
+}
+
+extern "C" int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t max_z_cells)
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
+    } else cudaGetLastError();
+    const int warps = glb_grid_warps(n_jobs > 0 ? n_jobs : 1, sms);
+    const int blocks = (warps + 3) / 4;
+    return 256 + (int64_t)blocks * 4 * (int64_t)glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
+}
+
+extern "C" int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
+                                         int64_t max_z_cells, void *d_res, void *d_cigars, void *d_cells,
+                                         void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    if (!d_jobs || !d_seqs || !d_res || !d_cigars || !d_scratch || n_jobs < 0 || max_q_len < 0 || max_z_cells < 0)
+        return fail(CSBWA_E_BADARG, "bad argument");
+    if (n_jobs == 0) return CSBWA_OK;
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    int rc = ensure_dev_attrs(dev);
+    if (rc) return rc;
+    const int warps = glb_grid_warps(n_jobs, g_dev[dev].sms);
+    const int blocks = (warps + 3) / 4;
+    const size_t need = 256 + (size_t)blocks * 4 * glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
+    if ((int64_t)need > scratch_bytes) return fail(CSBWA_E_SCRATCH, "global-alignment scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    GlbHdr *hdr = (GlbHdr *)d_scratch;
+    k_glb_setup<<<1, 32, 0, st>>>(hdr);
+    k_glb<<<blocks, 128, 0, st>>>((const GlbJob *)d_jobs, n_jobs, (const uint8_t *)d_seqs, hdr, (char *)d_scratch + 256,
+                                  (long long)max_q_len + 1, max_z_cells, (int32_t *)d_res, (uint32_t *)d_cigars,
+                                  (unsigned long long *)d_cells);
+    CU_TRY(cudaGetLastError());
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.kernel_launches += kGlbLaunches;
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes,
+                                  csbwa_gres *res, uint32_t *cigars, int64_t cigar_words, int device)
+{
+    if (n_jobs < 0 || seq_bytes < 0 || cigar_words < 0 || (n_jobs > 0 && (!jobs || !seqs || !res || !cigars)))
+        return fail(CSBWA_E_BADARG, "null buffer or negative size");
+    if (n_jobs == 0) return CSBWA_OK;
+    int max_q = 0;
+    long long max_z = 0;
+    for (int32_t k = 0; k < n_jobs; ++k) {
+        const csbwa_gjob &j = jobs[k];
+        if (j.q_len < 0 || j.t_len < 0 || j.w < 0 || j.q_off < 0 || j.t_off < 0 || j.cigar_cap < 0 || j.cigar_off < 0 ||
+            j.q_off + j.q_len > seq_bytes || j.t_off + j.t_len > seq_bytes || j.cigar_off + j.cigar_cap > cigar_words)
+            return fail(CSBWA_E_BADARG, "job range outside seqs[] / cigars[]");
+        if (j.q_len > max_q) max_q = j.q_len;
+        const long long zc = glb_z_cells(j.q_len, j.t_len, j.w);
+        if (zc > max_z) max_z = zc;
+    }
+    Ctx *c = nullptr;
+    int rc = acquire_ctx(device, &c);
+    if (rc) return rc;
+    CtxGuard guard{c};
+    const size_t jb = ((size_t)n_jobs * sizeof(csbwa_gjob) + 255) & ~(size_t)255;
+    const size_t in_bytes = jb + (size_t)seq_bytes;
+    const size_t res_b = ((size_t)n_jobs * sizeof(csbwa_gres) + 255) & ~(size_t)255;
+    const size_t out_bytes = res_b + (size_t)cigar_words * 4;
+    const size_t scr = (size_t)csbwa_global_scratch_bytes(n_jobs, max_q, max_z);
+    if ((rc = grow_pinned(c->h_in, in_bytes)) || (rc = grow_pinned(c->h_out, out_bytes)) ||
+        (rc = grow_dev(c->d_in, in_bytes)) || (rc = grow_dev(c->d_out, out_bytes)) || (rc = grow_dev(c->d_scratch, scr)))
+        return rc;
+    memcpy(c->h_in.p, jobs, (size_t)n_jobs * sizeof(csbwa_gjob));
+    memcpy((char *)c->h_in.p + jb, seqs, (size_t)seq_bytes);
+    CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
+    CU_TRY(cudaMemsetAsync(c->d_out.p, 0, out_bytes, c->st));
+    rc = csbwa_global_batch_device(c->d_in.p, n_jobs, (const char *)c->d_in.p + jb, max_q, max_z, c->d_out.p,
+                                   (char *)c->d_out.p + res_b, c->d_cells, c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_cells, c->d_cells, 8, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    memcpy(res, c->h_out.p, (size_t)n_jobs * sizeof(csbwa_gres));
+    memcpy(cigars, (char *)c->h_out.p + res_b, (size_t)cigar_words * 4);
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.glb_calls++; g_stats.glb_jobs += n_jobs; g_stats.glb_cells += (int64_t)*c->h_cells;
+    }
+    return CSBWA_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // integer-pipe peak microbenchmark (roofline denominator)

@@ -217,3 +217,43 @@ class MateSWJNI:
                                                      out.ctypes.data, cap, out_start.ctypes.data, self.device))
         assert n == out_start[-1]
         return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)]
+
+
+# ---------------------------------------------------------------------------------------------
+# SWGlobal (next row: CIGAR generation) -- S/util/SWUtil.scala:233-397
+# ---------------------------------------------------------------------------------------------
+def cigarBandWidth(queryLen, rlen, opt=None):
+    """Band width bwaGenCigar2 hands to SWGlobal (S/worker2/MemRegToADAMSAM.scala:808-818)."""
+    opt = opt or MemOptType()
+    maxIns = int((((queryLen + 1) >> 1) * opt.a - opt.oIns) / float(opt.eIns) + 1.0)
+    maxDel = int((((queryLen + 1) >> 1) * opt.a - opt.oDel) / float(opt.eDel) + 1.0)
+    maxGap = max(maxIns, maxDel)
+    width = (maxGap + abs((rlen - queryLen) + 1)) >> 1
+    width = min(width, opt.w)
+    return max(width, abs(rlen - queryLen) + 3)
+
+
+def swGlobalBatch(jobs, seqs, device=-1):
+    """Batched SWGlobal.  jobs: structured array (_lib.GJOB_DTYPE).  Returns (int32[n,2] = score,
+    n_cigar ; uint32 cigars, BAM encoding len << 4 | op, at jobs['cigar_off'])."""
+    jobs = np.ascontiguousarray(jobs, dtype=_lib.GJOB_DTYPE)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    n = len(jobs)
+    total = int((jobs["cigar_off"] + jobs["cigar_cap"]).max()) if n else 0
+    res = np.zeros((n, 2), dtype=np.int32)
+    cig = np.zeros(max(1, total), dtype=np.uint32)
+    _lib.check(_lib.lib().csbwa_global_batch(jobs.ctypes.data, n, seqs.ctypes.data, seqs.size, res.ctypes.data,
+                                             cig.ctypes.data, cig.size, device))
+    return res, cig
+
+
+def SWGlobal(query, target, w, cap=512, device=-1):
+    """Single-call convenience: -> (score, [(op, len), ...]) with op 0 = M, 1 = I, 2 = D."""
+    q = np.asarray(query, dtype=np.uint8)
+    t = np.asarray(target, dtype=np.uint8)
+    seqs = np.concatenate([q, t]) if len(q) + len(t) else np.zeros(1, np.uint8)
+    jobs = np.zeros(1, dtype=_lib.GJOB_DTYPE)
+    jobs[0] = (0, len(q), len(q), len(t), w, cap, 0)
+    res, cig = swGlobalBatch(jobs, seqs, device)
+    nc = int(res[0, 1])
+    return int(res[0, 0]), [(int(c & 0xf), int(c >> 4)) for c in cig[:max(nc, 0)]]

@@ -85,6 +85,7 @@ typedef struct {
     int64_t aln_calls, aln_jobs, aln_cells, aln_in_bytes, aln_out_bytes;
     int64_t kernel_launches;     /* our kernels only */
     int64_t ext_groups;          /* coalesced device submissions that served ext_calls */
+    int64_t glb_calls, glb_jobs, glb_cells;
     double  h2d_ms, kernel_ms, d2h_ms, host_ms; /* CUDA-event / wall split, summed over calls */
 } csbwa_stats;
 
@@ -213,6 +214,31 @@ int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *reads, int32_t
                                   const uint8_t *ref, int64_t ref_len, const int64_t *seed6,
                                   const int32_t *opt7, uint8_t *out, int64_t cap);
 
+
+/* ---- next row of the path: SWGlobal (banded global alignment + backtrace -> CIGAR) ---------
+ * Reference: S/util/SWUtil.scala:233-397 (port of ksw_global2, N/ksw.c:501-584), called once per
+ * emitted alignment by bwaGenCigar2 (S/worker2/MemRegToADAMSAM.scala:738-893), which also chooses
+ * the band w (:808-818).  The reference has no native seam here; this one is ours.
+ * Job k aligns seqs[q_off, +q_len) (the read) against seqs[t_off, +t_len) (the reference window)
+ * and writes at most cigar_cap BAM-encoded operations (len << 4 | op, op 0 = M, 1 = I, 2 = D) at
+ * cigars[cigar_off ...].  res[k].n_cigar < 0: -1 = did not fit cigar_cap, -3 = larger than the
+ * scratch sizing.  Scoring = MemOptType defaults. */
+typedef struct {
+    int64_t q_off, t_off;
+    int32_t q_len, t_len;
+    int32_t w;
+    int32_t cigar_cap;
+    int64_t cigar_off;
+} csbwa_gjob;
+typedef struct { int32_t score, n_cigar; } csbwa_gres;
+int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes,
+                       csbwa_gres *res, uint32_t *cigars, int64_t cigar_words, int device);
+/* device-resident: max_q_len = max q_len, max_z_cells = max over jobs of min(q_len, 2w+1) * t_len */
+int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t max_z_cells);
+int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
+                              int64_t max_z_cells, void *d_res, void *d_cigars, void *d_cells,
+                              void *d_scratch, int64_t scratch_bytes, void *stream);
+int csbwa_global_launches_per_call(void);
 
 /* ---- roofline denominator: measured integer-pipe issue rate ----------------
  * op: 0 IADD3, 1 VIMNMX, 2 VIADDMNMX, 3 VIMNMX3, 4 VIADDMNMX.S16x2, 5 PRMT, 6 IMAD.

@@ -683,3 +683,111 @@ int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
     out_start[2 * group_size] = out_n;
     return out_n;
 }
+
+/* ------------------------------------------------------------------------- */
+/* SWGlobal  (S/util/SWUtil.scala:233-397)                                    */
+/* ------------------------------------------------------------------------- */
+typedef struct { uint32_t *cig; int cap, n, last_op, overflow; } orc_cigbuf;
+static void cigar_push(orc_cigbuf *b, int op, int len)
+{   /* pushCigar (:401-414): merge with the previous operation when it is the same */
+    if (b->n == 0 || op != b->last_op) {
+        if (b->n < b->cap) b->cig[b->n] = ((uint32_t)len << 4) | (uint32_t)op; else b->overflow = 1;
+        b->n++;
+        b->last_op = op;
+    } else if (b->n - 1 < b->cap) {
+        b->cig[b->n - 1] += (uint32_t)len << 4;
+    }
+}
+
+int orc_sw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  const orc_opt_t *opt, int w, int *n_cigar, uint32_t *cigar, int cigar_cap, int64_t *cells_out)
+{
+    const int o_del = opt->o_del, e_del = opt->e_del, o_ins = opt->o_ins, e_ins = opt->e_ins;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;          /* :245-247 */
+    int32_t *H = (int32_t *)malloc(((size_t)qlen + 2) * sizeof(int32_t));
+    int32_t *E = (int32_t *)malloc(((size_t)qlen + 2) * sizeof(int32_t));
+    uint8_t *z = (uint8_t *)malloc((size_t)(n_col > 0 ? n_col : 1) * (size_t)(tlen > 0 ? tlen : 1));
+    int64_t cells = 0;
+    H[0] = 0; E[0] = ORC_MINUS_INF;                                  /* first row (:271-285) */
+    int j = 1;
+    for (; j <= qlen && j <= w; ++j) { H[j] = -(o_ins + e_ins * j); E[j] = ORC_MINUS_INF; }
+    for (; j <= qlen; ++j) { H[j] = ORC_MINUS_INF; E[j] = ORC_MINUS_INF; }
+    for (int i = 0; i < tlen; ++i) {                                 /* DP (:288-344) */
+        const int8_t *srow = opt->mat + (target[i] > 4 ? 4 : target[i]) * 5;
+        int f = ORC_MINUS_INF, h1 = ORC_MINUS_INF;
+        int beg = 0, end = qlen;
+        if (i > w) beg = i - w;
+        if (i + w + 1 < qlen) end = i + w + 1;
+        if (beg == 0) h1 = -(o_del + e_del * (i + 1));
+        uint8_t *zi = z + (size_t)i * n_col;
+        for (j = beg; j < end; ++j) {
+            int m = H[j] + srow[query[j] > 4 ? 4 : query[j]];
+            int e = E[j];
+            H[j] = h1;
+            int d = (m >= e) ? 0 : 1;
+            int h = (m >= e) ? m : e;
+            if (h < f) { d = 2; h = f; }
+            h1 = h;
+            int t = m - oe_del;
+            e -= e_del;
+            if (e > t) d |= 1 << 2;
+            if (e < t) e = t;
+            E[j] = e;
+            t = m - oe_ins;
+            f -= e_ins;
+            if (f > t) d |= 2 << 4;
+            if (f < t) f = t;
+            zi[j - beg] = (uint8_t)d;
+        }
+        if (end > beg) cells += end - beg;
+        H[end] = h1; E[end] = ORC_MINUS_INF;
+    }
+    const int score = H[qlen];
+    orc_cigbuf cb = {cigar, cigar_cap, 0, -1, 0};                    /* backtrack (:349-377) */
+    int which = 0;
+    int i = tlen - 1, k = (i + w + 1 < qlen) ? i + w : qlen - 1;
+    while (i >= 0 && k >= 0) {
+        const int col = (i > w) ? k - (i - w) : k;
+        which = (z[(size_t)i * n_col + col] >> (which << 1)) & 3;
+        if (which == 0) { cigar_push(&cb, 0, 1); --i; --k; }
+        else if (which == 1) { cigar_push(&cb, 2, 1); --i; }
+        else { cigar_push(&cb, 1, 1); --k; }
+    }
+    if (i >= 0) cigar_push(&cb, 2, i + 1);
+    if (k >= 0) cigar_push(&cb, 1, k + 1);
+    if (!cb.overflow)
+        for (i = 0; i < (cb.n >> 1); ++i) { uint32_t tmp = cigar[i]; cigar[i] = cigar[cb.n - 1 - i]; cigar[cb.n - 1 - i] = tmp; }
+    *n_cigar = cb.overflow ? -1 : cb.n;
+    if (cells_out) *cells_out = cells;
+    free(H); free(E); free(z);
+    return score;
+}
+
+typedef struct {
+    const orc_gjob_t *jobs; const uint8_t *seqs; int32_t *res2; uint32_t *cigars; int64_t *cells; orc_opt_t opt;
+} orc_gl_ctx;
+
+static void orc_gl_body(int32_t k, void *vctx)
+{
+    orc_gl_ctx *c = (orc_gl_ctx *)vctx;
+    const orc_gjob_t *jb = &c->jobs[k];
+    int nc = 0;
+    int64_t cells = 0;
+    int sc = orc_sw_global(jb->q_len, c->seqs + jb->q_off, jb->t_len, c->seqs + jb->t_off, &c->opt, jb->w,
+                           &nc, c->cigars + jb->cigar_off, jb->cigar_cap, &cells);
+    c->res2[2 * (size_t)k] = sc;
+    c->res2[2 * (size_t)k + 1] = nc;
+    if (c->cells) c->cells[k] = cells;
+}
+
+int orc_global_batch(const orc_gjob_t *jobs, int32_t n, const uint8_t *seqs, int32_t *res2,
+                     uint32_t *cigars, int64_t *cells_per_job, int n_threads)
+{
+    if (n < 0) return -1;
+    orc_gl_ctx c;
+    c.jobs = jobs; c.seqs = seqs; c.res2 = res2; c.cigars = cigars; c.cells = cells_per_job;
+    orc_default_opt(&c.opt);
+    orc_parallel_for(n, n_threads, 16, orc_gl_body, &c);
+    return 0;
+}

@@ -136,6 +136,24 @@ int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
                      orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start,
                      int64_t *n_sw_calls);
 
+/* ---- SWGlobal (S/util/SWUtil.scala:233-397): banded global alignment + backtrace ----
+ * cigar: BAM encoding len << 4 | op (0 = M, 1 = I, 2 = D), forward order, at most cigar_cap
+ * entries written.  Returns the score; *n_cigar = number of CIGAR operations. */
+int orc_sw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  const orc_opt_t *opt, int w, int *n_cigar, uint32_t *cigar, int cigar_cap, int64_t *cells);
+
+typedef struct {
+    int64_t q_off, t_off;       /* byte offsets into seqs[] */
+    int32_t q_len, t_len;
+    int32_t w;                  /* band width handed to SWGlobal */
+    int32_t cigar_cap;          /* CIGAR slots reserved for this job */
+    int64_t cigar_off;          /* first slot of this job in cigars[] */
+} orc_gjob_t;
+
+/* res2: n x {score, n_cigar}  (n_cigar = -1: did not fit cigar_cap) */
+int orc_global_batch(const orc_gjob_t *jobs, int32_t n, const uint8_t *seqs, int32_t *res2,
+                     uint32_t *cigars, int64_t *cells_per_job, int n_threads);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -277,3 +277,62 @@ def matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, ref
     if n < 0:
         raise RuntimeError("orc_matesw_group failed: %d" % n)
     return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)], nsw.value
+
+
+# --------------------------------------------------------------------------
+# SWGlobal
+# --------------------------------------------------------------------------
+GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"), ("w", "<i4"),
+                       ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
+
+
+def sw_global(query, target, w, cap=512):
+    """SWUtil.SWGlobal -> (score, [(op, len), ...]) with op 0 = M, 1 = I, 2 = D."""
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    o = default_opt()
+    L = lib()
+    L.orc_sw_global.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Opt), C.c_int, C.POINTER(C.c_int),
+                                C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    L.orc_sw_global.restype = C.c_int
+    cig = np.zeros(cap, dtype=np.uint32)
+    nc, cells = C.c_int(0), C.c_int64(0)
+    sc = L.orc_sw_global(len(q), qp, len(t), tp, C.byref(o), int(w), C.byref(nc), cig.ctypes.data, cap, C.byref(cells))
+    return sc, [(int(c & 0xf), int(c >> 4)) for c in cig[:max(nc.value, 0)]], cells.value
+
+
+def global_batch(jobs, seqs, n_threads=1):
+    """-> (int32[n,2] = score, n_cigar ; uint32 cigars ; cells[n])"""
+    jobs = np.ascontiguousarray(jobs, dtype=GJOB_DTYPE)
+    s, sp = _u8(seqs)
+    n = len(jobs)
+    total = int((jobs["cigar_off"] + jobs["cigar_cap"]).max()) if n else 0
+    res = np.zeros((n, 2), dtype=np.int32)
+    cig = np.zeros(max(1, total), dtype=np.uint32)
+    cells = np.zeros(n, dtype=np.int64)
+    L = lib()
+    L.orc_global_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_global_batch.restype = C.c_int
+    rc = L.orc_global_batch(jobs.ctypes.data, n, sp, res.ctypes.data, cig.ctypes.data, cells.ctypes.data, n_threads)
+    if rc != 0:
+        raise RuntimeError("orc_global_batch failed: %d" % rc)
+    return res, cig, cells
+
+
+def ref_ksw_global2(query, target, w, opt=None):
+    """The reference's own ksw_global2 (oracle/_ref) -> (score, [(op, len), ...])."""
+    o = opt or default_opt()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    R = ref()
+    R.ksw_global2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + \
+        [C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32))]
+    R.ksw_global2.restype = C.c_int
+    nc = C.c_int(0)
+    cg = C.POINTER(C.c_uint32)()
+    sc = R.ksw_global2(len(q), qp, len(t), tp, 5, C.addressof(o.mat), o.o_del, o.e_del, o.o_ins, o.e_ins, int(w),
+                       C.byref(nc), C.byref(cg))
+    out = [(int(cg[i] & 0xf), int(cg[i] >> 4)) for i in range(nc.value)]
+    if nc.value:
+        C.CDLL(None).free(cg)
+    return sc, out

@@ -221,3 +221,26 @@ extern "C" void emu_co_destroy(void *h)
     delete e->co;
     delete e;
 }
+
+// ---------------------------------------------------------------------------------------------
+// SWGlobal core on the CPU (same function the k_glb kernel calls, stride 1)
+// ---------------------------------------------------------------------------------------------
+#include "../../cloud-scale-bwamem_b200/csrc/glb_kernels.cuh"
+extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, int32_t *res2, uint32_t *cigars, int64_t *cells)
+{
+    SwOpt o;
+    fill_default_opt(o);
+    finish_opt(o);
+    for (int k = 0; k < n; ++k) {
+        const GlbJob &jb = jobs[k];
+        std::vector<GlbInt2> he((size_t)glb_he_cols(jb.q_len) + 1);
+        std::vector<uint8_t> z((size_t)glb_z_cells(jb.q_len, jb.t_len, jb.w) + 1);
+        int nc = 0;
+        long long c = 0;
+        int sc = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he.data(), 1, z.data(), 1,
+                                  cigars + jb.cigar_off, jb.cigar_cap, nc, c);
+        res2[2 * k] = sc; res2[2 * k + 1] = nc;
+        if (cells) cells[k] = c;
+    }
+    return 0;
+}

@@ -101,3 +101,21 @@ class EmuCoalescer:
         if self.h:
             self.L.emu_co_destroy(self.h)
             self.h = None
+
+
+GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"), ("w", "<i4"),
+                       ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
+
+
+def emu_global_batch(emu, jobs, seqs):
+    jobs = np.ascontiguousarray(jobs, dtype=GJOB_DTYPE)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    n = len(jobs)
+    total = int((jobs["cigar_off"] + jobs["cigar_cap"]).max()) if n else 0
+    res = np.zeros((n, 2), dtype=np.int32)
+    cig = np.zeros(max(1, total), dtype=np.uint32)
+    cells = np.zeros(n, dtype=np.int64)
+    emu.lib.emu_global_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = emu.lib.emu_global_batch(jobs.ctypes.data, n, seqs.ctypes.data, res.ctypes.data, cig.ctypes.data, cells.ctypes.data)
+    assert rc == 0
+    return res, cig, cells

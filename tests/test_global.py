@@ -1,0 +1,99 @@
+"""SWGlobal (next row of the path): oracle pinned against the reference's own ksw_global2, the
+product core against the oracle on the CPU (emu) and on the GPU through the C ABI."""
+import numpy as np
+import pytest
+
+from tests import emu_lib, util
+
+
+def rand_global_job(rng, pkg, L=None):
+    L = L or int(rng.choice([30, 76, 101, 151, 250]))
+    q = rng.integers(0, 4, L).astype(np.uint8)
+    t = util.mutate(rng, q, float(rng.choice([0, 0.01, 0.03, 0.1])), indel=float(rng.choice([0.1, 0.5])))
+    if len(t) == 0:
+        t = q[:1].copy()
+    if rng.random() < 0.1:
+        q = q.copy(); q[int(rng.integers(0, L))] = 4
+    w = pkg.jni.cigarBandWidth(len(q), len(t)) if rng.random() < 0.7 else int(rng.choice([1, 5, 40, 100])) + abs(len(t) - len(q))
+    return q, t, int(w)
+
+
+def build_gjobs(triples, dtype, cap=None):
+    jobs = np.zeros(len(triples), dtype=dtype)
+    chunks, off, coff = [], 0, 0
+    for k, (q, t, w) in enumerate(triples):
+        c = cap if cap is not None else len(q) + len(t) + 2
+        jobs[k] = (off, off + len(q), len(q), len(t), w, c, coff)
+        chunks += [q, t]; off += len(q) + len(t); coff += c
+    return jobs, (np.concatenate(chunks) if off else np.zeros(1, np.uint8))
+
+
+def cig_of(res, cig, jobs, k):
+    nc = int(res[k, 1])
+    o = int(jobs[k]["cigar_off"])
+    return int(res[k, 0]), nc, [int(x) for x in cig[o:o + max(nc, 0)]]
+
+
+def test_oracle_vs_reference_c(pkg, oracle):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(91)
+    for it in range(600):
+        q, t, w = rand_global_job(rng, pkg)
+        a = oracle.sw_global(q, t, w)
+        b = oracle.ref_ksw_global2(q, t, w)
+        assert (a[0], a[1]) == b, it
+        ql = sum(n for op, n in a[1] if op in (0, 1)); tl = sum(n for op, n in a[1] if op in (0, 2))
+        assert (ql, tl) == (len(q), len(t))                     # CIGAR consumes both sequences
+
+
+def test_band_width_rule(pkg):
+    assert pkg.jni.cigarBandWidth(151, 151) == 36 and pkg.jni.cigarBandWidth(151, 160) == 40
+    assert pkg.jni.cigarBandWidth(101, 101) == 23 and pkg.jni.cigarBandWidth(30, 80) == 53
+
+
+def test_emu_vs_oracle(pkg, oracle, emu):
+    rng = np.random.default_rng(92)
+    triples = [rand_global_job(rng, pkg) for _ in range(300)]
+    triples += [(np.zeros(1, np.uint8), np.zeros(1, np.uint8), 3), (rng.integers(0, 4, 50).astype(np.uint8), rng.integers(0, 4, 2).astype(np.uint8), 51)]
+    jobs, seqs = build_gjobs(triples, oracle.GJOB_DTYPE)
+    ref, rcig, rcells = oracle.global_batch(jobs, seqs)
+    got, gcig, gcells = emu_lib.emu_global_batch(emu, jobs, seqs)
+    assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
+    small, _ = build_gjobs(triples[:50], oracle.GJOB_DTYPE, cap=2)   # CIGAR does not fit -> n_cigar = -1 on both
+    r2, _, _ = oracle.global_batch(small, seqs)
+    g2, _, _ = emu_lib.emu_global_batch(emu, small, seqs)
+    assert np.array_equal(r2, g2) and (r2[:, 1] == -1).any()
+
+
+@pytest.mark.gpu
+def test_gpu_vs_oracle(pkg, oracle):
+    rng = np.random.default_rng(93)
+    triples = [rand_global_job(rng, pkg) for _ in range(3000)]
+    jobs, seqs = build_gjobs(triples, pkg._lib.GJOB_DTYPE, cap=64)
+    ref, rcig, rcells = oracle.global_batch(jobs, seqs, n_threads=8)
+    before = pkg.stats()["glb_cells"]
+    got, gcig = pkg.jni.swGlobalBatch(jobs, seqs, device=0)
+    assert np.array_equal(got, ref)
+    for k in range(len(jobs)):
+        assert cig_of(got, gcig, jobs, k) == cig_of(ref, rcig, jobs, k)
+    assert pkg.stats()["glb_cells"] - before == int(rcells.sum())
+    sc, cg = pkg.jni.SWGlobal(triples[0][0], triples[0][1], triples[0][2])
+    assert (sc, cg) == oracle.sw_global(*triples[0])[:2]
+
+
+@pytest.mark.gpu
+def test_gpu_read_shaped_batch(pkg, oracle):
+    """151-bp reads against their reference spans with the bwaGenCigar2 band rule (C2 shape)."""
+    rng = np.random.default_rng(94)
+    ref = pkg.workload.make_reference(2000000, 94)
+    rb = pkg.workload.ReadBatch(ref, 4096, 151, 0.01, 400, 50, rng)
+    triples = []
+    for r in range(rb.n):
+        lo, hi = int(rb.ref_idx[r].min()), int(rb.ref_idx[r].max()) + 1
+        triples.append((rb.reads[r], ref[lo:hi], pkg.jni.cigarBandWidth(151, hi - lo)))
+    jobs, seqs = build_gjobs(triples, pkg._lib.GJOB_DTYPE, cap=32)
+    ref_res, rcig, _ = oracle.global_batch(jobs, seqs, n_threads=8)
+    got, gcig = pkg.jni.swGlobalBatch(jobs, seqs, device=0)
+    assert np.array_equal(got, ref_res) and np.array_equal(gcig, rcig)
+    assert (got[:, 1] >= 1).all() and (got[:, 0] > 100).mean() > 0.95
