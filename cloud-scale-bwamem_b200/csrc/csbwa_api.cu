@@ -87,6 +87,7 @@ static int ensure_dev_attrs(int dev)
     const int big = 128 * 1024;
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     d.attrs_set = true;
     return CSBWA_OK;
 }
@@ -988,11 +989,19 @@ static_assert(sizeof(csbwa_gjob) == sizeof(GlbJob), "gjob layout");
 static const int kGlbLaunches = 2;
 extern "C" int csbwa_global_launches_per_call(void) { return kGlbLaunches; }
 
+static const int kGlbBlock = 64;         // threads per block of k_glb
 static int glb_grid_warps(int n, int sms)
 {
     int warps = (n + 31) / 32;
-    const int cap = sms * 16;            // persistent: 4 blocks of 4 warps per SM
+    const int cap = sms * 8;             // persistent: up to 4 blocks of 2 warps per SM
     return warps < cap ? warps : cap;
+}
+// shared-memory columns for the H/E rows: the whole query if it fits 2 blocks per SM
+static int glb_smem_cols(int max_q_len)
+{
+    const int fit = (100 * 1024) / (kGlbBlock * (int)sizeof(GlbInt2));     // 200 columns at 64 threads
+    const int want = max_q_len + 1;
+    return want <= fit ? want : fit;
 }
 
 extern "C" int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t max_z_cells)
@@ -1003,8 +1012,9 @@ extern "C" int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len,
         if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
     } else cudaGetLastError();
     const int warps = glb_grid_warps(n_jobs > 0 ? n_jobs : 1, sms);
-    const int blocks = (warps + 3) / 4;
-    return 256 + (int64_t)blocks * 4 * (int64_t)glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
+    const int wpb = kGlbBlock / 32;
+    const int blocks = (warps + wpb - 1) / wpb;
+    return 256 + (int64_t)blocks * wpb * (int64_t)glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
 }
 
 extern "C" int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
@@ -1019,15 +1029,18 @@ extern "C" int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, con
     int rc = ensure_dev_attrs(dev);
     if (rc) return rc;
     const int warps = glb_grid_warps(n_jobs, g_dev[dev].sms);
-    const int blocks = (warps + 3) / 4;
-    const size_t need = 256 + (size_t)blocks * 4 * glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
+    const int wpb = kGlbBlock / 32;
+    const int blocks = (warps + wpb - 1) / wpb;
+    const size_t need = 256 + (size_t)blocks * wpb * glb_warp_bytes((long long)max_q_len + 1, max_z_cells);
     if ((int64_t)need > scratch_bytes) return fail(CSBWA_E_SCRATCH, "global-alignment scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     GlbHdr *hdr = (GlbHdr *)d_scratch;
+    const int smem_cols = glb_smem_cols(max_q_len);
+    const size_t smem = (size_t)smem_cols * kGlbBlock * sizeof(GlbInt2);
     k_glb_setup<<<1, 32, 0, st>>>(hdr);
-    k_glb<<<blocks, 128, 0, st>>>((const GlbJob *)d_jobs, n_jobs, (const uint8_t *)d_seqs, hdr, (char *)d_scratch + 256,
-                                  (long long)max_q_len + 1, max_z_cells, (int32_t *)d_res, (uint32_t *)d_cigars,
-                                  (unsigned long long *)d_cells);
+    k_glb<<<blocks, kGlbBlock, smem, st>>>((const GlbJob *)d_jobs, n_jobs, (const uint8_t *)d_seqs, hdr, (char *)d_scratch + 256,
+                                           (long long)max_q_len + 1, max_z_cells, smem_cols, (int32_t *)d_res,
+                                           (uint32_t *)d_cigars, (unsigned long long *)d_cells);
     CU_TRY(cudaGetLastError());
     {
         std::lock_guard<std::mutex> lk(g_stats_mu);

@@ -30,16 +30,21 @@ __global__ void k_glb_setup(GlbHdr *hdr)
     }
 }
 
+// smem_cols > 0: H/E rows of jobs with q_len + 1 <= smem_cols live in shared memory
+// (column j of thread t at smem[j * blockDim + t], 8-byte elements: conflict free for any band
+// position); longer jobs fall back to the warp's global slice.
 __global__ void __launch_bounds__(128)
 k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, GlbHdr *hdr, char *slices,
-      long long max_he_cols, long long max_z_cells, int32_t *__restrict__ res2, uint32_t *__restrict__ cigars,
-      unsigned long long *cells_acc)
+      long long max_he_cols, long long max_z_cells, int smem_cols, int32_t *__restrict__ res2,
+      uint32_t *__restrict__ cigars, unsigned long long *cells_acc)
 {
+    extern __shared__ GlbInt2 glb_smem[];
     const SwOpt &o = hdr->opt;
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     char *slice = slices + (size_t)warp_id * glb_warp_bytes(max_he_cols, max_z_cells);
-    GlbInt2 *he = (GlbInt2 *)slice + lane;
+    GlbInt2 *he_g = (GlbInt2 *)slice + lane;
+    GlbInt2 *he_s = glb_smem + threadIdx.x;
     uint8_t *z = (uint8_t *)(slice + (size_t)max_he_cols * 32 * sizeof(GlbInt2)) + lane;
     unsigned long long my_cells = 0;
     for (;;) {
@@ -58,8 +63,10 @@ k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, 
                 atomicExch(&hdr->err, -7);
                 nc = -3;
             } else {
+                const bool in_smem = glb_he_cols(jb.q_len) <= smem_cols;
                 score = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w,
-                                         he, 32, z, 32, cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
+                                         in_smem ? he_s : he_g, in_smem ? (int)blockDim.x : 32, z, 32,
+                                         cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
             }
             res2[2 * (size_t)k] = score;
             res2[2 * (size_t)k + 1] = nc;
