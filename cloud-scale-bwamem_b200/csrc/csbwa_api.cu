@@ -88,6 +88,8 @@ static int ensure_dev_attrs(int dev)
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     d.attrs_set = true;
     return CSBWA_OK;
 }
@@ -141,6 +143,16 @@ static AuxSet *aux_for_stream(int dev, cudaStream_t st)
     return a;
 }
 
+static bool ext_dual_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CSBWA_EXT_DUAL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <int SIDE>
 static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch &sc, int16_t *d_out,
                             unsigned long long *d_cells, int n, int sms, cudaStream_t st_main, AuxSet *aux)
@@ -158,6 +170,14 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
             if (grid > sms * 8) grid = sms * 8;
             k_ext_side<SIDE, false><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                               d_out, d_cells, cls);
+        } else if (ext_dual_enabled()) {
+            // two tasks per thread (s16x2 lanes): 8 bytes per column per thread, 64 KB per block
+            const int cap = ext_class_cap(cls);
+            const int bd = cls == 1 ? 32 : (cls == 2 ? 64 : 128);
+            const size_t smem = (size_t)cap * bd * 8;
+            int grid = (n + 2 * bd - 1) / (2 * bd);
+            if (grid > sms * 3) grid = sms * 3;
+            k_ext_side_dual<SIDE><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls);
         } else {
             const int cap = ext_class_cap(cls);
             const int bd = cls == 1 ? 64 : EXT_BD;

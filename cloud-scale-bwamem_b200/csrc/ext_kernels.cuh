@@ -239,6 +239,41 @@ CSW_HD void ext_run_side(const SwOpt &o, const uint32_t *words, int q_nib, int q
     out.cells = cells;
 }
 
+// One side of TWO tasks in one thread (dual s16x2 core); B may be absent (B.qlen == 0).
+// Falls back to the scalar u8 core for a query that holds an N and for the rare second band try.
+CSW_HD void ext_run_side_dual(const SwOpt &o, U2 *col, int stride, const DualTask &A, const DualTask &B,
+                              int end_bonus, int prevA, int prevB, SideRes &outA, SideRes &outB)
+{
+    uint32_t *col1 = (uint32_t *)col;            // scalar view of the same shared-memory columns
+    const int stride1 = 2 * stride;
+    const bool has_n = u8_stage_dual(col, stride, A, B);
+    if (has_n) {
+        if (A.qlen > 0) ext_run_side<true>(o, A.words, A.q_nib, A.qlen, A.t_nib, A.tlen, end_bonus, A.h0, prevA, col1, stride1, nullptr, nullptr, outA);
+        if (B.qlen > 0) ext_run_side<true>(o, B.words, B.q_nib, B.qlen, B.t_nib, B.tlen, end_bonus, B.h0, prevB, col1, stride1, nullptr, nullptr, outB);
+        return;
+    }
+    SwExtRes rA, rB;
+    sw_extend_u8_dual(o, col, stride, A, B, o.w, end_bonus, rA, rB);
+    const DualTask *T[2] = {&A, &B};
+    SwExtRes *R[2] = {&rA, &rB};
+    SideRes *O[2] = {&outA, &outB};
+    const int prev[2] = {prevA, prevB};
+    for (int x = 0; x < 2; ++x) {
+        if (T[x]->qlen <= 0) continue;
+        SwExtRes r = *R[x];
+        int aw = o.w, cells = r.cells;
+        if (!(r.score == prev[x] || r.max_off < (aw >> 1) + (aw >> 2))) {      // second band try (:810-824)
+            aw = o.w << 1;
+            u8_stage_query(col1, stride1, T[x]->words, T[x]->q_nib, T[x]->qlen);
+            sw_extend_u8(o, col1, stride1, T[x]->qlen, T[x]->words, T[x]->t_nib, T[x]->tlen, aw, end_bonus, T[x]->h0, r);
+            cells += r.cells;
+        }
+        O[x]->score = (int16_t)r.score; O[x]->qle = (int16_t)r.qle; O[x]->tle = (int16_t)r.tle;
+        O[x]->gtle = (int16_t)r.gtle; O[x]->gscore = (int16_t)r.gscore; O[x]->aw = (int16_t)aw;
+        O[x]->cells = cells;
+    }
+}
+
 // SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range; FAST = u8 core.
 template <int SIDE, bool FAST>
 __global__ void __launch_bounds__(EXT_BD)
@@ -304,6 +339,87 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
+            }
+        }
+    }
+    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
+}
+
+} // namespace csw
+
+namespace csw {
+
+// dual variant of the fast side kernel: every thread owns TWO consecutive jobs of the sorted list
+template <int SIDE>
+__global__ void __launch_bounds__(EXT_BD)
+k_ext_side_dual(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
+                SideRes *__restrict__ left, int16_t *__restrict__ out, unsigned long long *cells_acc, int cls)
+{
+    extern __shared__ U2 smem2[];
+    const SwOpt &o = hdr->opt;
+    const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
+    const int lane = threadIdx.x & 31;
+    const int stride = (int)blockDim.x;
+    U2 *col = smem2 + threadIdx.x;
+    unsigned long long my_cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&hdr->work[SIDE][cls], 64u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0) + jbeg;
+        if (chunk >= jend) break;
+        const uint32_t job0 = chunk + 2 * lane;
+        if (job0 < jend) {
+            ExtTask t[2];
+            const ExtCall *cl[2];
+            int k[2] = {-1, -1};
+            DualTask D[2];
+            SideRes L[2], R[2];
+            int prev[2] = {0, 0};
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                D[x].words = nullptr; D[x].q_nib = D[x].t_nib = 0; D[x].qlen = 0; D[x].tlen = 0; D[x].h0 = 0;
+                L[x].score = 0; L[x].qle = L[x].tle = L[x].gtle = L[x].gscore = 0; L[x].aw = (int16_t)o.w; L[x].cells = 0;
+                R[x] = L[x];
+                cl[x] = nullptr;
+                if (job0 + x >= jend) continue;
+                k[x] = (int)order[job0 + x];
+                cl[x] = &ext_call(cs, ext_locate(cs, k[x]));
+                const uint8_t *in = base + cl[x]->in_off;
+                const int n = cl[x]->n_tasks;
+                t[x] = read_task(in, k[x] - cl[x]->task_base);
+                if (!ext_task_ok(t[x], n, cl[x]->in_bytes)) { t[x].lq = t[x].lr = t[x].rq = t[x].rr = 0; t[x].pos = 8 + 8 * n; }
+                D[x].words = (const uint32_t *)in + t[x].pos;
+                if (SIDE == 0) {
+                    D[x].q_nib = seg_lq(t[x]); D[x].qlen = t[x].lq; D[x].t_nib = seg_lr(t[x]); D[x].tlen = t[x].lr;
+                    D[x].h0 = t[x].h0; prev[x] = t[x].reg_score;
+                } else {
+                    if (t[x].lq > 0) L[x] = left[k[x]];
+                    const int sc0 = t[x].lq > 0 ? (int)L[x].score : t[x].reg_score;
+                    D[x].q_nib = seg_rq(t[x]); D[x].qlen = t[x].rq; D[x].t_nib = seg_rr(t[x]); D[x].tlen = t[x].rr;
+                    D[x].h0 = sc0; prev[x] = sc0;
+                }
+            }
+            if (D[0].qlen > 0 || D[1].qlen > 0) {
+                SideRes *S = (SIDE == 0) ? L : R;
+                if (D[0].qlen > 0) ext_run_side_dual(o, col, stride, D[0], D[1], SIDE == 0 ? o.pen_clip5 : o.pen_clip3,
+                                                     prev[0], prev[1], S[0], S[1]);
+                else ext_run_side_dual(o, col, stride, D[1], D[0], SIDE == 0 ? o.pen_clip5 : o.pen_clip3,
+                                       prev[1], prev[0], S[1], S[0]);
+                my_cells += (unsigned)S[0].cells + (unsigned)S[1].cells;
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                if (k[x] < 0) continue;
+                if (SIDE == 0) {
+                    left[k[x]] = L[x];
+                } else {
+                    int16_t rec[10];
+                    ext_finalize(o, t[x], &L[x], &R[x], rec);
+                    uint32_t *dst = (uint32_t *)(out + cl[x]->out_off + (size_t)10 * (k[x] - cl[x]->task_base));
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
+                }
             }
         }
     }

@@ -77,6 +77,69 @@ CSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 
+// ---- packed 16x2 DPX wrappers (two independent 16-bit lanes per register) ---------------
+CSW_HD uint32_t pk16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+CSW_HD int lo16s(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+CSW_HD int hi16s(uint32_t v) { return (int)(int16_t)(v >> 16); }
+// per lane: max(a + b, c)              -> VIADDMNMX.S16x2
+CSW_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2(a, b, c);
+#else
+    return pk16(imax((int16_t)(lo16s(a) + lo16s(b)), lo16s(c)), imax((int16_t)(hi16s(a) + hi16s(b)), hi16s(c)));
+#endif
+}
+// per lane: max(a + b, c, 0)           -> VIADDMNMX.S16x2.RELU
+CSW_HD uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2_relu(a, b, c);
+#else
+    return pk16(imax(imax((int16_t)(lo16s(a) + lo16s(b)), lo16s(c)), 0),
+                imax(imax((int16_t)(hi16s(a) + hi16s(b)), hi16s(c)), 0));
+#endif
+}
+// per lane signed max                  -> VIMNMX.S16x2
+CSW_HD uint32_t max2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(a, b);
+#else
+    return pk16(imax(lo16s(a), lo16s(b)), imax(hi16s(a), hi16s(b)));
+#endif
+}
+// per lane unsigned max / min          -> VIMNMX.U16x2
+CSW_HD uint32_t umax2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxu2(a, b);
+#else
+    uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+    return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+#endif
+}
+CSW_HD uint32_t umin2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vminu2(a, b);
+#else
+    uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+    return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+// a * b + c on the FMA pipe (32-bit; callers guarantee no cross-lane carries when used packed)
+CSW_HD uint32_t umad(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a * b + c;
+#endif
+}
+
 // ---- scoring / options ------------------------------------------------------
 // MemOptType defaults (reference S/datatype/MemOptType.scala:28-75).  The 5x5
 // matrix is never transmitted on either seam, so it is always {a, -b, N=-1}.
