@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--reads-per-call", type=int, default=4096, help="experiments only; the headline is 4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 2 column pairs (s16x2), 0 one column per step (u8), 1 two tasks/thread; -1 library default")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -217,6 +218,9 @@ def main():
     L = pkg.lib()
     if L.csbwa_init(0) < 1:
         raise SystemExit("csbwa_init failed: " + L.csbwa_last_error().decode())
+    if args.ext_mode in (0, 1, 2):
+        L.csbwa_set_ext_mode(args.ext_mode)
+    ext_mode = L.csbwa_set_ext_mode(-1)
 
     # ---- workload (untimed) ----
     w = gen_workload(pkg, args.pairs, rank)
@@ -412,6 +416,8 @@ def main():
                     "ms_per_step": e2e_ms_max / args.steps, "caller_threads_per_gpu": nthreads,
                     "api": "csbwa_extend_batch (host buffers, pinned staging, H2D+kernels+D2H per call)"},
             "gpu_launches": int(kernels_per_step * args.steps * world),
+            "ext_core": {0: "u8, one column per step", 1: "dual s16x2 (two SWExtend sides per thread)",
+                         2: "p2 s16x2 (two adjacent query columns per DPX instruction)"}.get(ext_mode),
             "cuda_graph": graph is not None, "streams": nstreams, "calls_per_launch_sequence": gsz,
             "e2e_calls_per_device_submission": ((st_e2e1["ext_calls"] - st_e2e0["ext_calls"]) /
                                                 max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),

@@ -28,7 +28,7 @@ EXPORTS = [
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
-    "csbwa_global_batch_device", "csbwa_global_launches_per_call",
+    "csbwa_global_batch_device", "csbwa_global_launches_per_call", "csbwa_set_ext_mode",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.csbwa_global_batch_device.argtypes = [vp, i32, vp, i32, i64, vp, vp, vp, vp, i64, vp]
     L.csbwa_global_batch_device.restype = C.c_int
     L.csbwa_global_launches_per_call.restype = C.c_int
+    L.csbwa_set_ext_mode.argtypes = [C.c_int]; L.csbwa_set_ext_mode.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

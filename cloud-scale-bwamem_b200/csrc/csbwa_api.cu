@@ -85,8 +85,10 @@ static int ensure_dev_attrs(int dev)
     CU_TRY(cudaGetDeviceProperties(&p, dev));
     d.sms = p.multiProcessorCount;
     const int big = 128 * 1024;
-    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -109,10 +111,11 @@ extern "C" int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes)
 // Auxiliary streams of one submission stream: the per-class side kernels of a phase are
 // independent, so they are forked onto aux streams and joined before the next phase; their
 // tails (each is bounded by its longest job) then overlap instead of adding up.
+constexpr int kAux = 4;
 struct AuxSet {
-    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaStream_t s[kAux] = {};
     cudaEvent_t fork[2] = {nullptr, nullptr};
-    cudaEvent_t join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t join[2][kAux] = {};
     bool ok = false;
     int init()
     {
@@ -143,54 +146,86 @@ static AuxSet *aux_for_stream(int dev, cudaStream_t st)
     return a;
 }
 
-static bool ext_dual_enabled()
+// extension core selection (EXT_CORE_*): 2 = two adjacent query columns per DPX instruction
+// (default), 0 = one column per step with u8 scores, 1 = two tasks per thread in the s16x2 lanes.
+// CSBWA_EXT_CORE=0/1/2 sets the start-up default; csbwa_set_ext_mode switches at run time.
+static std::atomic<int> g_ext_mode{-1};
+static int ext_core()
 {
-    static int v = -1;
+    int v = g_ext_mode.load(std::memory_order_relaxed);
     if (v < 0) {
-        const char *e = getenv("CSBWA_EXT_DUAL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        const char *e = getenv("CSBWA_EXT_CORE");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : EXT_CORE_P2;
+        g_ext_mode.store(v, std::memory_order_relaxed);
     }
-    return v == 1;
+    return v;
+}
+extern "C" int csbwa_set_ext_mode(int mode)
+{
+    const int prev = ext_core();
+    if (mode >= 0 && mode <= 2) g_ext_mode.store(mode, std::memory_order_relaxed);
+    return prev;
+}
+
+// resident blocks per SM for a block of bd threads using smem bytes of dynamic shared memory
+static int blocks_per_sm(int bd, size_t smem, int regs_per_thread)
+{
+    int by_smem = (int)((size_t)(227 * 1024) / (smem + 1024));
+    int by_thr = 2048 / bd;
+    int by_reg = 65536 / (regs_per_thread * bd);
+    int b = by_smem < by_thr ? by_smem : by_thr;
+    if (by_reg < b) b = by_reg;
+    if (b > 32) b = 32;
+    return b < 1 ? 1 : b;
 }
 
 template <int SIDE>
 static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch &sc, int16_t *d_out,
-                            unsigned long long *d_cells, int n, int sms, cudaStream_t st_main, AuxSet *aux)
+                            unsigned long long *d_cells, int n, int sms, cudaStream_t st_main, AuxSet *aux, int core)
 {
     if (aux) {
         cudaEventRecord(aux->fork[SIDE], st_main);
-        cudaStreamWaitEvent(aux->s[0], aux->fork[SIDE], 0);
-        cudaStreamWaitEvent(aux->s[1], aux->fork[SIDE], 0);
+        for (int a = 0; a < kAux; ++a) cudaStreamWaitEvent(aux->s[a], aux->fork[SIDE], 0);
     }
     for (int cls = 0; cls < EXT_NCLS; ++cls) {
-        // classes 0 (generic) and 1 on the main stream, 2 and 3 on the aux streams
+        // classes 0 (generic) and 1 on the main stream, every other class on its own aux stream
         cudaStream_t st = (aux && cls >= 2) ? aux->s[cls - 2] : st_main;
+        const int cap = ext_class_cap(cls);
         if (cls == 0) {
             int grid = (n + EXT_BD - 1) / EXT_BD;
             if (grid > sms * 8) grid = sms * 8;
-            k_ext_side<SIDE, false><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
-                                                              d_out, d_cells, cls);
-        } else if (ext_dual_enabled()) {
-            // two tasks per thread (s16x2 lanes): 8 bytes per column per thread, 64 KB per block
-            const int cap = ext_class_cap(cls);
+            k_ext_side<SIDE, -1><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                           d_out, d_cells, cls, 0);
+        } else if (core == EXT_CORE_P2) {
+            // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
+            const int npairs = cap / 2;
+            const int bd = cls == 1 ? 64 : EXT_BD;
+            const size_t smem = (size_t)npairs * bd * 10;
+            int grid = (n + bd - 1) / bd;
+            const int cap_grid = sms * blocks_per_sm(bd, smem, 96);
+            if (grid > cap_grid) grid = cap_grid;
+            k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                                   d_out, d_cells, cls, npairs);
+        } else if (core == EXT_CORE_DUAL) {
+            // two tasks per thread (s16x2 lanes): 8 bytes per column per thread
             const int bd = cls == 1 ? 32 : (cls == 2 ? 64 : 128);
             const size_t smem = (size_t)cap * bd * 8;
             int grid = (n + 2 * bd - 1) / (2 * bd);
-            if (grid > sms * 3) grid = sms * 3;
+            const int cap_grid = sms * blocks_per_sm(bd, smem, 168);
+            if (grid > cap_grid) grid = cap_grid;
             k_ext_side_dual<SIDE><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls);
         } else {
-            const int cap = ext_class_cap(cls);
             const int bd = cls == 1 ? 64 : EXT_BD;
             const size_t smem = (size_t)cap * bd * 4;
-            const int per_sm = cls == 1 ? 3 : (cls == 2 ? 3 : 7);
             int grid = (n + bd - 1) / bd;
-            if (grid > sms * per_sm) grid = sms * per_sm;
-            k_ext_side<SIDE, true><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
-                                                            d_out, d_cells, cls);
+            const int cap_grid = sms * blocks_per_sm(bd, smem, 80);
+            if (grid > cap_grid) grid = cap_grid;
+            k_ext_side<SIDE, EXT_CORE_U8><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                                   d_out, d_cells, cls, 0);
         }
     }
     if (aux) {
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kAux; ++a) {
             cudaEventRecord(aux->join[SIDE][a], aux->s[a]);
             cudaStreamWaitEvent(st_main, aux->join[SIDE][a], 0);
         }
@@ -210,11 +245,12 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     ExtScratch sc = ext_carve(d_scratch, n);
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
     const int tb = 256, gb = (n + tb - 1) / tb;
-    k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed));
+    const int core = ext_core();
+    k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
-    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux);
-    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux);
+    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux, core);
+    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux, core);
     CU_TRY(cudaGetLastError());
     return CSBWA_OK;
 }
@@ -305,13 +341,14 @@ extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ex
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
     const int tb = 256, gb = (n_tasks + tb - 1) / tb;
     CU_TRY(cudaEventRecord(ev[0], st));
-    k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed));
+    const int core = ext_core();
+    k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
     CU_TRY(cudaEventRecord(ev[1], st));
-    launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr);
+    launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr, core);
     CU_TRY(cudaEventRecord(ev[2], st));
-    launch_ext_side<1>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr);
+    launch_ext_side<1>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr, core);
     CU_TRY(cudaEventRecord(ev[3], st));
     CU_TRY(cudaEventSynchronize(ev[3]));
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms3[i], ev[i], ev[i + 1]);

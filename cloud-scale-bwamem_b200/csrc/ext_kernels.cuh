@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ext_core.cuh"
+#include "ext_p2.cuh"
 
 namespace csw {
 
@@ -43,13 +44,19 @@ CSW_HD int ext_locate(const ExtCalls &cs, int g)
 }
 
 constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty side, 256 = generic
-constexpr int EXT_NCLS = 4;            // 0: generic, 1: cap 256, 2: cap 128, 3: cap 64
+constexpr int EXT_NCLS = 6;            // 0: generic, then fast classes by column capacity: 256, 128, 96, 64, 32
+// extension cores (csbwa_set_ext_mode): which fast core serves the eligible sides
+constexpr int EXT_CORE_U8 = 0;         // one column per step, u8 scores (ext_core.cuh sw_extend_u8)
+constexpr int EXT_CORE_DUAL = 1;       // two tasks per thread in the s16x2 lanes (sw_extend_u8_dual)
+constexpr int EXT_CORE_P2 = 2;         // two adjacent columns per step, s16 scores (ext_p2.cuh)
 constexpr int EXT_BD = 128;            // threads per block of the side kernels
 
 struct ExtHdr {
     SwOpt opt;
     int32_t n_tasks;
     int32_t err;
+    int32_t core;                      // EXT_CORE_*
+    int32_t pad_;
     uint32_t hist[2][EXT_NBIN];
     uint32_t base[2][EXT_NBIN];        // start of each bin in the descending order
     uint32_t cursor[2][EXT_NBIN];
@@ -93,12 +100,17 @@ __host__ __device__ inline ExtScratch ext_carve(void *p, int n)
 
 CSW_HD int ext_class_of_bin(int bin)
 {
-    if (bin == 256) return 0;
-    if (bin > 127) return 1;
-    if (bin > 63) return 2;
-    return 3;
+    if (bin == 256) return 0;           // a class of capacity cap holds qlen <= cap - 1 (column qlen is written)
+    if (bin >= 128) return 1;
+    if (bin >= 96) return 2;
+    if (bin >= 64) return 3;
+    if (bin >= 32) return 4;
+    return 5;
 }
-__host__ __device__ inline int ext_class_cap(int cls) { return cls == 1 ? 256 : (cls == 2 ? 128 : 64); }
+__host__ __device__ inline int ext_class_cap(int cls)
+{
+    return cls == 1 ? 256 : (cls == 2 ? 128 : (cls == 3 ? 96 : (cls == 4 ? 64 : 32)));
+}
 
 // parse the 32-byte common header into SwOpt (MemChainToAlignBatched.scala:78-85)
 CSW_HD void ext_parse_header(const uint8_t *in, SwOpt &o)
@@ -122,14 +134,15 @@ CSW_HD bool ext_task_ok(const ExtTask &t, int n, int in_bytes)
 }
 
 // bin of one side: 0 = nothing to do, 1..255 = u8 fast path by query length, 256 = generic
-CSW_HD int ext_side_bin(const SwOpt &o, int qlen, int h0)
+CSW_HD int ext_side_bin(const SwOpt &o, int qlen, int h0, int core = EXT_CORE_U8)
 {
     if (qlen <= 0) return 0;
-    return u8_eligible(o, qlen, h0) ? qlen : 256;
+    const bool ok = core == EXT_CORE_P2 ? p2_eligible(o, qlen, h0) : u8_eligible(o, qlen, h0);
+    return ok ? qlen : 256;
 }
 
 __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr,
-                           unsigned long long eh_cap)
+                           unsigned long long eh_cap, int core)
 {
     __shared__ uint32_t sh[2][EXT_NBIN];
     __shared__ SwOpt sopt;
@@ -138,7 +151,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
         const uint8_t *in0 = base + ext_call(cs, 0).in_off;
         ext_parse_header(in0, sopt);
         if (blockIdx.x == 0) {
-            hdr->opt = sopt; hdr->n_tasks = n; hdr->eh_cap = eh_cap;
+            hdr->opt = sopt; hdr->n_tasks = n; hdr->eh_cap = eh_cap; hdr->core = core;
             // coalesced calls must carry the same options (header bytes other than taskNum)
             for (int c = 1; c < cs.n_calls; ++c) {
                 const uint8_t *inc = base + ext_call(cs, c).in_off;
@@ -159,9 +172,9 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
             atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
         } else {
             // the right side's h0 is the left score, bounded by h0 + lq * max(mat)
-            bl = ext_side_bin(sopt, t.lq, t.h0);
+            bl = ext_side_bin(sopt, t.lq, t.h0, core);
             const int h0r = t.lq > 0 ? t.h0 + t.lq * sopt.max_mat : t.reg_score;
-            br = ext_side_bin(sopt, t.rq, h0r);
+            br = ext_side_bin(sopt, t.rq, h0r, core);
             if (t.lq > 0 && bl == 256 && br != 0) br = 256;   // keep score bounds trivially safe
         }
         if (bl) atomicAdd(&sh[0][bl], 1u);
@@ -204,9 +217,9 @@ __global__ void k_ext_scatter(const uint8_t *__restrict__ base, ExtCalls cs, int
     ExtTask t = read_task(base + cl.in_off, k - cl.task_base);
     int bl = 0, br = 0;
     if (ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
-        bl = ext_side_bin(o, t.lq, t.h0);
+        bl = ext_side_bin(o, t.lq, t.h0, hdr->core);
         const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
-        br = ext_side_bin(o, t.rq, h0r);
+        br = ext_side_bin(o, t.rq, h0r, hdr->core);
         if (t.lq > 0 && bl == 256 && br != 0) br = 256;
     }
     if (bl) order_l[hdr->base[0][bl] + atomicAdd(&hdr->cursor[0][bl], 1u)] = (uint32_t)k;
@@ -230,6 +243,25 @@ CSW_HD void ext_run_side(const SwOpt &o, const uint32_t *words, int q_nib, int q
         aw = o.w << i;
         if (FAST) sw_extend_u8(o, col, stride, qlen, words, t_nib, tlen, aw, end_bonus, h0, r);
         else sw_extend_generic(o, words, q_nib, qlen, t_nib, tlen, aw, end_bonus, h0, H, E, 1, r);
+        cells += r.cells;
+        if (r.score == prev || r.max_off < (aw >> 1) + (aw >> 2)) break;
+        prev = r.score;
+    }
+    out.score = (int16_t)r.score; out.qle = (int16_t)r.qle; out.tle = (int16_t)r.tle;
+    out.gtle = (int16_t)r.gtle; out.gscore = (int16_t)r.gscore; out.aw = (int16_t)aw;
+    out.cells = cells;
+}
+
+// One SWExtend side with band retries on the column-pair core (ext_p2.cuh)
+CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, int qlen, int t_nib, int tlen,
+                            int end_bonus, int h0, int prev, P2Pair *he, uint16_t *sel, int stride, SideRes &out)
+{
+    SwExtRes r;
+    int aw = o.w, cells = 0;
+    p2_stage_query(sel, stride, words, q_nib, qlen);
+    for (int i = 0; i < CSW_MAX_BAND_TRY; ++i) {
+        aw = o.w << i;
+        sw_extend_p2(o, he, sel, stride, qlen, words, t_nib, tlen, aw, end_bonus, h0, r);
         cells += r.cells;
         if (r.score == prev || r.max_off < (aw >> 1) + (aw >> 2)) break;
         prev = r.score;
@@ -274,19 +306,24 @@ CSW_HD void ext_run_side_dual(const SwOpt &o, U2 *col, int stride, const DualTas
     }
 }
 
-// SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range; FAST = u8 core.
-template <int SIDE, bool FAST>
+// SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range.
+// CORE: -1 generic (int32 rows in global scratch), EXT_CORE_U8, EXT_CORE_P2 (shared memory).
+// npairs: column pairs per thread of the P2 layout ({H2,E2} records first, then the selectors).
+template <int SIDE, int CORE>
 __global__ void __launch_bounds__(EXT_BD)
 k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
            SideRes *__restrict__ left, int *__restrict__ ehbase, int16_t *__restrict__ out,
-           unsigned long long *cells_acc, int cls)
+           unsigned long long *cells_acc, int cls, int npairs)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ uint4 smem4[];
+    constexpr bool FAST = CORE >= 0;
     const SwOpt &o = hdr->opt;
     const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;
-    uint32_t *col = smem + threadIdx.x;            // column j at col[j * stride]
+    uint32_t *col = (uint32_t *)smem4 + threadIdx.x;            // U8: column j at col[j * stride]
+    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // P2: pair p at he[p * stride]
+    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * stride) + threadIdx.x;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t chunk = 0;
@@ -314,23 +351,30 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
                     H = (int *)((char *)ehbase + off); E = H + (qm + 2);
                 }
             }
+            SideRes L, R;
+            L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
+            R = L;
             if (SIDE == 0) {
-                SideRes L;
-                L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
-                if (t.lq > 0)        // (0 only after a validation / scratch failure, already reported)
-                    ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
-                                       t.reg_score, col, stride, H, E, L);
+                if (t.lq > 0) {      // (0 only after a validation / scratch failure, already reported)
+                    if (CORE == EXT_CORE_P2)
+                        ext_run_side_p2(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
+                                        he, sel, stride, L);
+                    else
+                        ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
+                                           t.reg_score, col, stride, H, E, L);
+                }
                 left[k] = L;
                 my_cells += (unsigned)L.cells;
             } else {
-                SideRes L, R;
-                L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
-                R = L;
                 if (t.lq > 0) L = left[k];
                 if (t.rq > 0) {
                     const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
-                    ext_run_side<FAST>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0,
-                                       sc0, col, stride, H, E, R);
+                    if (CORE == EXT_CORE_P2)
+                        ext_run_side_p2(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
+                                        he, sel, stride, R);
+                    else
+                        ext_run_side<FAST>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0,
+                                           sc0, col, stride, H, E, R);
                     my_cells += (unsigned)R.cells;
                 }
                 int16_t rec[10];

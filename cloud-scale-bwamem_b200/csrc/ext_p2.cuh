@@ -1,0 +1,225 @@
+// ext_p2.cuh -- column-pair seed-extension core: one SWExtend side per thread, TWO ADJACENT QUERY
+// COLUMNS per DPX instruction (s16x2 lanes: low half = even column 2p, high half = odd column 2p+1).
+//
+// Semantics: the reference's Scala SWUtil.SWExtend (S/util/SWUtil.scala:61-230), same quirks as
+// sw_extend_u8 / sw_extend_generic in ext_core.cuh (last-j tie break :158, z-drop dangling else
+// :194-199, band shrink :201-214, gscore on the loop variable :177).
+//
+// What changes is the data flow inside one row:
+//   * H and E are kept per query column at their OWN index as 16-bit values, one 8-byte record
+//     {H2, E2} per column pair (reference eh[j].h == Hs[j-1], eh[j].e == Es[j]); the diagonal of a
+//     pair is a funnel shift of the previous and the current H2 word.
+//   * H' = max(Hdiag + S, E) and g = relu(H' - oeIns) are computed for both columns at once; only
+//     the insertion chain F(j+1) = max(F(j) - eIns, g(j)) is sequential (exact: SURVEY.md App. C),
+//     two 32-bit VIADDMNMX per pair; H = max(H', F) and the E update are packed again.
+//   * the row max / arg-max is a packed unsigned key h<<7 | p per lane (last p on ties; the two
+//     lanes are merged at the end of the row), the "last zero of the row" a second packed key
+//     (511-h)<<7 | p, so the band shrink needs a rescan only when a zero lies right of the max.
+// Per column pair: 2 PRMT/SHF + 11 DPX/ALU + 5 FMA-pipe instructions, i.e. ~8 ALU-pipe slots per
+// cell against ~16 of the one-column core.  Scores are bounded by 511 (h0 + qlen*max(mat)), so the
+// 250 bp configs stay on the fast path.  Band edges that split a pair are handled by a scalar
+// single-column step before / after the pair loop, so no lane ever computes an out-of-band cell.
+#pragma once
+#include "sw_common.cuh"
+
+namespace csw {
+
+struct P2Pair { uint32_t h2, e2; };       // {H(2p) | H(2p+1) << 16, E(2p) | E(2p+1) << 16}
+
+CSW_HD bool p2_eligible(const SwOpt &o, int qlen, int h0)
+{
+    return qlen >= 1 && qlen <= 255 && h0 >= 0 && h0 + qlen * o.max_mat <= 511 &&
+           o.e_del >= 0 && o.e_ins >= 0 && o.o_del >= 0 && o.o_ins >= 0;
+}
+// column pairs a side of qlen columns needs (column index qlen is written as eh[end].e = 0)
+CSW_HD int p2_pairs(int qlen) { return (qlen + 2) >> 1; }
+
+// sel[p]: PRMT selector giving {score(q[2p]) sign-extended to 16 bit, score(q[2p+1]) likewise}
+// from the byte tables {tlo, thi} of the current target base
+CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int q_nib, int qlen)
+{
+    NibStream qs;
+    qs.init(words, q_nib);
+    const int np = p2_pairs(qlen);
+    for (int p = 0; p < np; ++p) {
+        int q0 = 0, q1 = 0;
+        if (2 * p < qlen) { q0 = qs.next(); if (q0 > 4) q0 = 4; }
+        if (2 * p + 1 < qlen) { q1 = qs.next(); if (q1 > 4) q1 = 4; }
+        sel[(size_t)p * stride] = (uint16_t)(((uint32_t)q0 | ((uint32_t)q1 << 8)) * 0x11u + 0x8080u);
+    }
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");       // the selectors are read back through ld_u16 (inline PTX)
+#endif
+}
+
+// 16-bit load zero-extended into a 32-bit register (LDS.U16 without a masking LOP3)
+CSW_HD uint32_t ld_u16(const uint16_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
+CSW_HD uint32_t funnel16(uint32_t lo, uint32_t hi)      // (hi:lo) >> 16
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, 16);
+#else
+    return (lo >> 16) | (hi << 16);
+#endif
+}
+
+CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, int qlen,
+                         const uint32_t *words, int t_nib, int tlen,
+                         int w, int end_bonus, int h0, SwExtRes &res)
+{
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+    const int e_del = o.e_del, e_ins = o.e_ins, zdrop = o.zdrop;
+    const int ne_ins = -e_ins;
+    const uint32_t ne_del2 = pk16(-e_del, -e_del);
+    const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
+    uint16_t *h16 = (uint16_t *)he;
+    const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
+#define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
+#define P2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
+    // first row (:96-104): Hs[c] = eh[c+1].h, E = 0
+    {
+        int v = h0 > oe_ins ? h0 - oe_ins : 0;
+        const int np = p2_pairs(qlen);
+        for (int p = 0; p < np; ++p) {
+            const int lo = v; v = v > e_ins ? v - e_ins : 0;
+            const int hi = v; v = v > e_ins ? v - e_ins : 0;
+            P2Pair x; x.h2 = (uint32_t)lo | ((uint32_t)hi << 16); x.e2 = 0;
+            he[(size_t)p * stride] = x;
+        }
+    }
+    w = clamp_band(o, w, qlen, end_bonus);
+    int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+    int beg = 0, end = qlen, cells = 0;
+    int hm1 = h0;                                      // H(i-1, -1)
+    NibStream ts;
+    if (tlen > 0) ts.init(words, t_nib);
+    for (int i = 0; i < tlen; ++i) {
+        int t = ts.next(); if (t > 4) t = 4;
+        const uint32_t tlo = o.tlo[t], thi = o.thi[t];
+        const int h1i = imax(h0 - (o.o_del + e_del * (i + 1)), 0);
+        beg = imax(beg, i - w);
+        end = min3(end, i + w + 1, qlen);
+        uint32_t key2 = 0, zk2 = 0;
+        int hlast = h1i;
+        if (beg < end) {
+            int dg = beg == 0 ? hm1 : (int)P2_H(beg - 1);          // H(i-1, beg-1)
+            if (beg > 0) P2_H(beg - 1) = (uint16_t)h1i;            // H(i, beg-1) := first-column value
+            int f = 0, c = beg;
+            const int pe = end >> 1;
+            // one column, scalar (band edge inside a pair)
+#define P2_COLUMN()                                                                               \
+            {                                                                                     \
+                const int lane = c & 1, p = c >> 1;                                               \
+                const int hold = (int)P2_H(c), e = (int)P2_E(c);                                  \
+                const uint32_t sl = sel[(size_t)p * stride];                                      \
+                const int s = (int)(int16_t)((prmt(tlo, thi, sl) >> (16 * lane)) & 0xffffu);      \
+                int h = imax(imax(dg + s, e), f);                                                 \
+                P2_H(c) = (uint16_t)h;                                                            \
+                P2_E(c) = (uint16_t)imax(e - e_del, imax(h - oe_del, 0));                         \
+                f = imax(f - e_ins, imax(h - oe_ins, 0));                                         \
+                key2 = umax2(key2, (uint32_t)(h * 128 + p) << (16 * lane));                       \
+                zk2 = umax2(zk2, (uint32_t)((511 - h) * 128 + p) << (16 * lane));                 \
+                dg = hold; hlast = h; ++c;                                                        \
+            }
+            if (c & 1) P2_COLUMN()
+            int p = c >> 1;
+            if (p < pe) {
+                uint32_t hprev2 = (uint32_t)dg << 16;
+                uint32_t pp2 = (uint32_t)p * 0x00010001u;
+                uint32_t zb2 = pp2 + 511u * 128u * 0x00010001u;
+                P2Pair *ph = he + (size_t)p * stride;
+                const uint16_t *ps = sel + (size_t)p * stride;
+                uint32_t h2 = 0;
+                P2Pair cur = *ph;
+                uint32_t sl = ld_u16(ps);
+                for (; p < pe; ++p) {
+                    const P2Pair x = cur;
+                    const uint32_t sx = sl;
+                    cur = ph[stride];                              // pair p + 1 always exists (p2_pairs)
+                    sl = ld_u16(ps + stride);
+                    const uint32_t s2 = prmt(tlo, thi, sx);
+                    const uint32_t hd2 = funnel16(hprev2, x.h2);
+                    hprev2 = x.h2;
+                    const uint32_t hp2 = addmax2(hd2, s2, x.e2);
+                    const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2);     // relu(hp - oe): a negative 3rd operand
+                                                                                // avoids materialising a packed 0
+                    const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));        // F(i, 2p+1)
+                    const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));           // F(i, 2p+2)
+                    const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);
+                    h2 = max2(hp2, f2);
+                    P2Pair y;
+                    y.h2 = h2;
+                    y.e2 = addmax2(x.e2, ne_del2, addmax2_relu(h2, noe_del2, noe_del2));
+                    *ph = y;
+                    key2 = umax2(key2, umad(h2, 128u, pp2));
+                    zk2 = umax2(zk2, umad(h2, 0xffffff80u, zb2));
+                    f = fn;
+                    pp2 += 0x00010001u; zb2 += 0x00010001u;
+                    ph += stride; ps += stride;
+                }
+                dg = (int)(hprev2 >> 16);
+                hlast = (int)(h2 >> 16);
+                c = 2 * pe;
+            }
+            if (c < end) P2_COLUMN()
+#undef P2_COLUMN
+            cells += end - beg;
+            P2_E(end) = 0;                                         // eh(end) = {h1, 0}
+        }
+        hm1 = h1i;
+        const int jfin = beg < end ? end : beg;
+        if (jfin == qlen && gscore <= hlast) { best_ie = i; gscore = hlast; }
+        // row max: larger h, then larger column (last j on ties)
+        const int klo = (int)(key2 & 0xffffu), khi = (int)(key2 >> 16);
+        const int hlo = klo >> 7, hhi = khi >> 7;
+        const int jlo = 2 * (klo & 127), jhi = 2 * (khi & 127) + 1;
+        int rm, rmj;
+        if (hhi > hlo || (hhi == hlo && jhi > jlo)) { rm = hhi; rmj = jhi; } else { rm = hlo; rmj = jlo; }
+        if (rm == 0) break;
+        if (rm > best) {
+            best = rm; best_i = i; best_j = rmj;
+            int off = rmj - i; if (off < 0) off = -off;
+            max_off = imax(max_off, off);
+        } else if (zdrop > 0) {
+            const int di = i - best_i, dj = rmj - best_j;
+            if (di > dj) {
+                if (best - rm - (di - dj) * e_del > zdrop) break;
+                else if (best - rm - (dj - di) * e_ins > zdrop) break;
+            }
+        }
+        // band shrink (:201-214) in own-column terms: eh[j].h == (j == beg ? h1i : Hs[j-1])
+        const int zlo = (int)(zk2 & 0xffffu), zhi = (int)(zk2 >> 16);
+        int clast = -1;                                            // last column of the band with H == 0
+        if ((zlo >> 7) == 511) clast = 2 * (zlo & 127);
+        if ((zhi >> 7) == 511) clast = imax(clast, 2 * (zhi & 127) + 1);
+        int nbeg, nend;
+        if (clast > rmj) {                                         // a zero right of the max: rescan
+            int j = rmj;
+            while (j >= beg && (j == beg ? h1i : (int)P2_H(j - 1)) > 0) --j;
+            nbeg = j + 1;
+            j = rmj + 2;
+            while (j <= end && (int)P2_H(j - 1) > 0) ++j;
+            nend = j;
+        } else {
+            nbeg = clast >= 0 ? clast + 2 : (h1i == 0 ? beg + 1 : beg);
+            nend = end + 1;
+        }
+        beg = nbeg; end = nend;
+    }
+#undef P2_H
+#undef P2_E
+    res.score = best; res.qle = best_j + 1; res.tle = best_i + 1;
+    res.gtle = best_ie + 1; res.gscore = gscore; res.max_off = max_off; res.cells = cells;
+}
+
+} // namespace csw

@@ -84,6 +84,48 @@ extern "C" int emu_extend_wire_dual(const uint8_t *in, int in_bytes, int16_t *ou
     return 0;
 }
 
+// p2 mode: the column-pair core (csrc/ext_p2.cuh) for every side it is eligible for
+extern "C" int emu_extend_wire_p2(const uint8_t *in, int in_bytes, int16_t *out, int64_t *cells_per_task,
+                                  int32_t *fast_sides)
+{
+    SwOpt o;
+    ext_parse_header(in, o);
+    int n;
+    memcpy(&n, in + 8, 4);
+    const int stride = 3;
+    int nfast = 0;
+    for (int k = 0; k < n; ++k) {
+        ExtTask t = read_task(in, k);
+        if (!ext_task_ok(t, n, in_bytes)) return -3;
+        const uint32_t *words = (const uint32_t *)in + t.pos;
+        const int qm = t.lq > t.rq ? t.lq : t.rq;
+        std::vector<P2Pair> he((size_t)(p2_pairs(qm) + 1) * stride);
+        std::vector<uint16_t> sel((size_t)(p2_pairs(qm) + 1) * stride, 0xdead);
+        for (auto &x : he) { x.h2 = 0xdeadbeefu; x.e2 = 0xdeadbeefu; }
+        std::vector<int> HE((size_t)2 * (qm + 2), -12345);
+        int *H = HE.data(), *E = HE.data() + (qm + 2);
+        SideRes L, R;
+        memset(&L, 0, sizeof L); memset(&R, 0, sizeof R);
+        L.aw = R.aw = (int16_t)o.w;
+        int64_t cells = 0;
+        if (t.lq > 0) {
+            if (p2_eligible(o, t.lq, t.h0)) { ext_run_side_p2(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, he.data() + 1, sel.data() + 2, stride, L); ++nfast; }
+            else ext_run_side<false>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, nullptr, 1, H, E, L);
+            cells += L.cells;
+        }
+        if (t.rq > 0) {
+            const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
+            if (p2_eligible(o, t.rq, sc0)) { ext_run_side_p2(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, he.data() + 1, sel.data() + 2, stride, R); ++nfast; }
+            else ext_run_side<false>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, nullptr, 1, H, E, R);
+            cells += R.cells;
+        }
+        ext_finalize(o, t, &L, &R, out + (size_t)10 * k);
+        if (cells_per_task) cells_per_task[k] = cells;
+    }
+    if (fast_sides) *fast_sides = nfast;
+    return 0;
+}
+
 extern "C" int emu_extend_wire(const uint8_t *in, int in_bytes, int16_t *out, int64_t *cells_per_task,
                                int32_t *fast_sides, int force_generic)
 {

@@ -43,6 +43,17 @@ class Emu:
         assert rc == 0, rc
         return out, cells, nfast.value
 
+    def extend_wire_p2(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        n = int(np.frombuffer(buf[8:12].tobytes(), dtype="<i4")[0])
+        out = np.zeros(10 * n, dtype=np.int16)
+        cells = np.zeros(n, dtype=np.int64)
+        nfast = C.c_int32(0)
+        self.lib.emu_extend_wire_p2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.emu_extend_wire_p2(buf.ctypes.data, buf.size, out.ctypes.data, cells.ctypes.data, C.addressof(nfast))
+        assert rc == 0, rc
+        return out, cells, nfast.value
+
     def extend_wire_dual(self, buf):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         n = int(np.frombuffer(buf[8:12].tobytes(), dtype="<i4")[0])

@@ -27,19 +27,32 @@ def _ext_gpu(pkg, wire, device=-1):
 
 
 def _check_ext(pkg, oracle, wire):
+    """Every extension core (2 = two query columns per DPX instruction, the default; 0 = one column
+    per step; 1 = two tasks per thread) must reproduce the oracle bit for bit, including the exact
+    DP cell count."""
     ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
-    before = pkg.stats()["ext_cells"]
-    got = _ext_gpu(pkg, wire)
-    bad = np.flatnonzero((got.reshape(-1, 10) != ref.reshape(-1, 10)).any(axis=1))
-    assert len(bad) == 0, (len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
-    assert pkg.stats()["ext_cells"] - before == int(rcells.sum())      # exact DP cell count
+    L = pkg.lib()
+    prev = L.csbwa_set_ext_mode(-1)
+    try:
+        for mode in (2, 0, 1):
+            L.csbwa_set_ext_mode(mode)
+            before = pkg.stats()["ext_cells"]
+            got = _ext_gpu(pkg, wire)
+            bad = np.flatnonzero((got.reshape(-1, 10) != ref.reshape(-1, 10)).any(axis=1))
+            assert len(bad) == 0, (mode, len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
+            assert pkg.stats()["ext_cells"] - before == int(rcells.sum())      # exact DP cell count
+    finally:
+        L.csbwa_set_ext_mode(prev)
     return ref
 
 
 def test_ext_golden(pkg, oracle, gpu):
     g = np.load(os.path.join(GOLD, "ext_golden.npz"))
-    got = _ext_gpu(pkg, g["wire"])
-    assert np.array_equal(got, g["reply"])
+    L = pkg.lib()
+    for mode in (0, 1, 2):
+        L.csbwa_set_ext_mode(mode)
+        got = _ext_gpu(pkg, g["wire"])
+        assert np.array_equal(got, g["reply"]), mode
 
 
 def test_ext_random_and_adversarial(pkg, oracle, gpu):
