@@ -30,6 +30,10 @@ import time
 
 import numpy as np
 
+# more hardware queues than the default 8: the seam's submission streams and their per-class aux
+# streams are independent (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -196,7 +200,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--reads-per-call", type=int, default=4096, help="experiments only; the headline is 4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 2 column pairs (s16x2), 0 one column per step (u8), 1 two tasks/thread; -1 library default")
+    ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 1 column pairs (s16x2), 0 one column per step (u8); -1 library default")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -218,7 +222,7 @@ def main():
     L = pkg.lib()
     if L.csbwa_init(0) < 1:
         raise SystemExit("csbwa_init failed: " + L.csbwa_last_error().decode())
-    if args.ext_mode in (0, 1, 2):
+    if args.ext_mode in (0, 1):
         L.csbwa_set_ext_mode(args.ext_mode)
     ext_mode = L.csbwa_set_ext_mode(-1)
 
@@ -416,13 +420,16 @@ def main():
                     "ms_per_step": e2e_ms_max / args.steps, "caller_threads_per_gpu": nthreads,
                     "api": "csbwa_extend_batch (host buffers, pinned staging, H2D+kernels+D2H per call)"},
             "gpu_launches": int(kernels_per_step * args.steps * world),
-            "ext_core": {0: "u8, one column per step", 1: "dual s16x2 (two SWExtend sides per thread)",
-                         2: "p2 s16x2 (two adjacent query columns per DPX instruction)"}.get(ext_mode),
+            "ext_core": {0: "u8, one column per step",
+                         1: "p2 s16x2 (two adjacent query columns per DPX instruction)"}.get(ext_mode),
             "cuda_graph": graph is not None, "streams": nstreams, "calls_per_launch_sequence": gsz,
             "e2e_calls_per_device_submission": ((st_e2e1["ext_calls"] - st_e2e0["ext_calls"]) /
                                                 max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
             "e2e_ms_per_device_submission": ((st_e2e1["host_ms"] - st_e2e0["host_ms"]) /
                                              max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
+            "e2e_device_ms_per_submission": {k: (st_e2e1[k] - st_e2e0[k]) / max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])
+                                             for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+            "host_cpus": os.cpu_count(),
             "clocks": clocks,
             "roofline": {
                 "bound": "int_alu", "kernel": "k_ext_side (left + right, all size classes)",

@@ -59,8 +59,10 @@ public:
         for (auto &t : workers_) t.join();
     }
 
-    // bytes reserved at the start of the staging buffer for the call table
-    size_t table_bytes() const { return ((size_t)lim_.max_calls * sizeof(CoCall) + 255) & ~(size_t)255; }
+    // bytes reserved at the start of the staging buffer: the call table, then {n_calls, n_tasks}
+    // of the group at header_off() (so the device can size the launch sequence by itself)
+    size_t header_off() const { return (size_t)lim_.max_calls * sizeof(CoCall); }
+    size_t table_bytes() const { return (header_off() + 16 + 255) & ~(size_t)255; }
 
     // true if a call of this size can be coalesced at all
     bool fits(int in_bytes, int n_tasks) const
@@ -180,6 +182,8 @@ private:
             const int tasks = g->tasks;
             lk.unlock();
             memcpy(ex_->in_staging(g->slot), calls.data(), calls.size() * sizeof(CoCall));
+            const int32_t dyn[4] = {(int32_t)calls.size(), tasks, 0, 0};
+            memcpy(ex_->in_staging(g->slot) + header_off(), dyn, sizeof dyn);
             const int rc = ex_->run(g->slot, calls.data(), (int)calls.size(), span, tasks);
             lk.lock();
             n_groups_++;

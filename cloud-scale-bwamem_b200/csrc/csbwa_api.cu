@@ -90,8 +90,6 @@ static int ensure_dev_attrs(int dev)
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(cudaFuncSetAttribute(k_ext_side_dual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     d.attrs_set = true;
     return CSBWA_OK;
 }
@@ -146,16 +144,16 @@ static AuxSet *aux_for_stream(int dev, cudaStream_t st)
     return a;
 }
 
-// extension core selection (EXT_CORE_*): 2 = two adjacent query columns per DPX instruction
-// (default), 0 = one column per step with u8 scores, 1 = two tasks per thread in the s16x2 lanes.
-// CSBWA_EXT_CORE=0/1/2 sets the start-up default; csbwa_set_ext_mode switches at run time.
+// extension core selection (EXT_CORE_*): 1 = two adjacent query columns per DPX instruction
+// (default), 0 = one column per step with u8 scores.
+// CSBWA_EXT_CORE=0/1 sets the start-up default; csbwa_set_ext_mode switches at run time.
 static std::atomic<int> g_ext_mode{-1};
 static int ext_core()
 {
     int v = g_ext_mode.load(std::memory_order_relaxed);
     if (v < 0) {
         const char *e = getenv("CSBWA_EXT_CORE");
-        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : EXT_CORE_P2;
+        v = (e && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : EXT_CORE_P2;
         g_ext_mode.store(v, std::memory_order_relaxed);
     }
     return v;
@@ -163,7 +161,7 @@ static int ext_core()
 extern "C" int csbwa_set_ext_mode(int mode)
 {
     const int prev = ext_core();
-    if (mode >= 0 && mode <= 2) g_ext_mode.store(mode, std::memory_order_relaxed);
+    if (mode >= 0 && mode <= 1) g_ext_mode.store(mode, std::memory_order_relaxed);
     return prev;
 }
 
@@ -206,14 +204,6 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
             if (grid > cap_grid) grid = cap_grid;
             k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                                    d_out, d_cells, cls, npairs);
-        } else if (core == EXT_CORE_DUAL) {
-            // two tasks per thread (s16x2 lanes): 8 bytes per column per thread
-            const int bd = cls == 1 ? 32 : (cls == 2 ? 64 : 128);
-            const size_t smem = (size_t)cap * bd * 8;
-            int grid = (n + 2 * bd - 1) / (2 * bd);
-            const int cap_grid = sms * blocks_per_sm(bd, smem, 168);
-            if (grid > cap_grid) grid = cap_grid;
-            k_ext_side_dual<SIDE><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls);
         } else {
             const int bd = cls == 1 ? 64 : EXT_BD;
             const size_t smem = (size_t)cap * bd * 4;
@@ -244,7 +234,9 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     if (rc) return rc;
     ExtScratch sc = ext_carve(d_scratch, n);
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
-    const int tb = 256, gb = (n + tb - 1) / tb;
+    const int tb = 256;
+    int gb = (n + tb - 1) / tb;
+    if (gb > g_dev[dev].sms * 8) gb = g_dev[dev].sms * 8;     // grid-stride kernels
     const int core = ext_core();
     k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
     k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
@@ -258,7 +250,7 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
 static ExtCalls single_call(int32_t in_bytes, int32_t n_tasks)
 {
     ExtCalls cs;
-    cs.tab = nullptr; cs.n_calls = 1;
+    cs.tab = nullptr; cs.n_calls = 1; cs.dyn = nullptr;
     cs.single.in_off = 0; cs.single.in_bytes = in_bytes; cs.single.n_tasks = n_tasks;
     cs.single.out_off = 0; cs.single.task_base = 0; cs.single.pad = 0;
     return cs;
@@ -299,7 +291,7 @@ extern "C" int csbwa_extend_multi_device(const void *d_in_base, const csbwa_ext_
     }
     if (n > 0x7fffffff) return fail(CSBWA_E_BADARG, "too many tasks");
     ExtCalls cs;
-    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls;
+    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls; cs.dyn = nullptr;
     memcpy(&cs.single, &h_calls[0], sizeof(ExtCall));
     int rc = launch_extend((const uint8_t *)d_in_base, cs, (int)n, (int16_t *)d_out_base,
                            (unsigned long long *)d_cells, d_scratch, scratch_bytes, (cudaStream_t)stream, dev,
@@ -331,7 +323,7 @@ extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ex
     int rc = ensure_dev_attrs(dev);
     if (rc) return rc;
     ExtCalls cs;
-    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls;
+    cs.tab = (const ExtCall *)d_calls; cs.n_calls = n_calls; cs.dyn = nullptr;
     memcpy(&cs.single, &h_calls[0], sizeof(ExtCall));
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev[4];
@@ -459,6 +451,9 @@ extern "C" int csbwa_init(int n_gpus)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_inited) return g_ndev;
+    // submission streams + their aux streams exceed the default 8 hardware queues; ask for 32 so
+    // independent groups do not serialise behind one another (no effect once a context exists)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
@@ -566,35 +561,50 @@ static int check_ext_wire(const uint8_t *in, int32_t in_bytes, int32_t *n_out)
 // ------------------------------------------------------------------------------------
 // coalesced host path: CUDA executor for Coalescer<> (csrc/coalesce.hpp)
 // ------------------------------------------------------------------------------------
+// Per staging slot the whole launch sequence (status/accumulator reset, histogram, scan, scatter,
+// the per-class side kernels forked over the aux streams, status copy) is captured ONCE into a CUDA
+// graph: {n_calls, n_tasks} and the call table are read from the staging buffer on the device, so
+// the graph does not depend on the group.  One group = H2D + graph launch + D2H + synchronise:
+// 4 driver calls instead of ~45, which matters because the submission threads serialise on the
+// driver's context lock (measured: 2.4 ms per group with direct launches).
 struct CudaCoExec {
     struct Slot {
         cudaStream_t st = nullptr;
         uint8_t *h_in = nullptr; uint8_t *h_out = nullptr;     // pinned
         uint8_t *d_in = nullptr; uint8_t *d_out = nullptr; void *d_scratch = nullptr;
-        int32_t *h_err = nullptr;
         AuxSet aux;
+        cudaGraphExec_t graph = nullptr;
+        int graph_core = -1;
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // H2D | launch sequence | D2H
     };
+    static constexpr size_t kTrailer = 16;     // d_out / h_out: {cells : 8, status : 4, pad : 4} then the replies
     int dev = 0;
-    size_t in_cap = 0, out_cap = 0, scratch_cap = 0;
+    size_t in_cap = 0, out_cap = 0, scratch_cap = 0, hdr_off = 0;
+    int max_tasks = 0;
+    bool use_graph = true;
     std::vector<Slot> slots;
 
-    int init(int device, int n_slots, size_t max_bytes, int max_tasks)
+    int init(int device, int n_slots, size_t max_bytes, int max_tasks_, size_t header_off)
     {
         dev = device;
         in_cap = max_bytes;
-        out_cap = (size_t)max_tasks * 20 + 64;
+        max_tasks = max_tasks_;
+        hdr_off = header_off;
+        out_cap = kTrailer + (size_t)max_tasks * 20 + 64;
         scratch_cap = ext_scratch_fixed(max_tasks) + (size_t)32 * 1024 * 1024;
+        const char *e = getenv("CSBWA_CO_GRAPH");
+        use_graph = !(e && e[0] == '0');
         CU_TRY(cudaSetDevice(dev));
         slots.resize(n_slots);
         for (auto &s : slots) {
             CU_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
             CU_TRY(cudaMallocHost((void **)&s.h_in, in_cap));
             CU_TRY(cudaMallocHost((void **)&s.h_out, out_cap));
-            CU_TRY(cudaMallocHost((void **)&s.h_err, 16));
             CU_TRY(cudaMalloc((void **)&s.d_in, in_cap));
             CU_TRY(cudaMalloc((void **)&s.d_out, out_cap));
             CU_TRY(cudaMalloc(&s.d_scratch, scratch_cap));
             if (s.aux.init() != CSBWA_OK) return CSBWA_E_CUDA;
+            for (auto &e : s.ev) CU_TRY(cudaEventCreate(&e));
         }
         return CSBWA_OK;
     }
@@ -603,10 +613,11 @@ struct CudaCoExec {
         cudaSetDevice(dev);
         for (auto &s : slots) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            if (s.graph) cudaGraphExecDestroy(s.graph);
+            for (auto &e : s.ev) if (e) cudaEventDestroy(e);
             s.aux.destroy();
             if (s.h_in) cudaFreeHost(s.h_in);
             if (s.h_out) cudaFreeHost(s.h_out);
-            if (s.h_err) cudaFreeHost(s.h_err);
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
             if (s.d_scratch) cudaFree(s.d_scratch);
@@ -614,40 +625,81 @@ struct CudaCoExec {
         slots.clear();
     }
     uint8_t *in_staging(int slot) { return slots[slot].h_in; }
-    int16_t *out_staging(int slot) { return (int16_t *)slots[slot].h_out; }
+    int16_t *out_staging(int slot) { return (int16_t *)(slots[slot].h_out + kTrailer); }
 
-    // one H2D, one multi-call launch sequence, one D2H (+4 bytes of status) for the whole group
+    // the launch sequence of one slot; dyn = true: sized by the device from the staging header
+    int enqueue(Slot &s, const CoCall *calls, int n_calls, int n_tasks, bool dyn)
+    {
+        CU_TRY(cudaMemsetAsync(s.d_out, 0, kTrailer, s.st));
+        ExtCalls cs;
+        cs.tab = (const ExtCall *)s.d_in; cs.n_calls = n_calls;
+        cs.dyn = dyn ? (const int32_t *)(s.d_in + hdr_off) : nullptr;
+        if (calls) memcpy(&cs.single, &calls[0], sizeof(ExtCall)); else memset(&cs.single, 0, sizeof(ExtCall));
+        int rc = launch_extend(s.d_in, cs, dyn ? max_tasks : n_tasks, (int16_t *)(s.d_out + kTrailer),
+                               (unsigned long long *)s.d_out, s.d_scratch, (int64_t)scratch_cap, s.st, dev, &s.aux);
+        if (rc) return rc;
+        k_ext_finish<<<1, 1, 0, s.st>>>((const ExtHdr *)s.d_scratch, (int32_t *)(s.d_out + 8));
+        return CSBWA_OK;
+    }
+    int build_graph(Slot &s)
+    {
+        if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU_TRY(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue(s, nullptr, 0, 0, true);
+        cudaError_t e = cudaStreamEndCapture(s.st, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess || !g) return fail(CSBWA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&s.graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { s.graph = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+        s.graph_core = ext_core();
+        return CSBWA_OK;
+    }
+
+    // one H2D, one launch sequence (graph), one D2H (status + cells + replies) for the whole group
     int run(int slot, const CoCall *calls, int n_calls, size_t span, int n_tasks)
     {
         const double t0 = now_ms();
         Slot &s = slots[slot];
         CU_TRY(cudaSetDevice(dev));
         const size_t reply = (size_t)n_tasks * 20;
-        const size_t tail = (reply + 15) & ~(size_t)15;            // cells accumulator after the replies
+        if (use_graph && (!s.graph || s.graph_core != ext_core())) {
+            int rc = build_graph(s);
+            if (rc) return rc;
+        }
+        CU_TRY(cudaEventRecord(s.ev[0], s.st));
         CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, span, cudaMemcpyHostToDevice, s.st));
-        CU_TRY(cudaMemsetAsync(s.d_out + tail, 0, 8, s.st));
-        ExtCalls cs;
-        cs.tab = (const ExtCall *)s.d_in; cs.n_calls = n_calls;
-        memcpy(&cs.single, &calls[0], sizeof(ExtCall));
-        int rc = launch_extend(s.d_in, cs, n_tasks, (int16_t *)s.d_out, (unsigned long long *)(s.d_out + tail),
-                               s.d_scratch, (int64_t)scratch_cap, s.st, dev, &s.aux);
-        if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, tail + 8, cudaMemcpyDeviceToHost, s.st));
-        CU_TRY(cudaMemcpyAsync(s.h_err, &((ExtHdr *)s.d_scratch)->err, 4, cudaMemcpyDeviceToHost, s.st));
+        CU_TRY(cudaEventRecord(s.ev[1], s.st));
+        if (use_graph) {
+            CU_TRY(cudaGraphLaunch(s.graph, s.st));
+        } else {
+            int rc = enqueue(s, calls, n_calls, n_tasks, false);
+            if (rc) return rc;
+        }
+        CU_TRY(cudaEventRecord(s.ev[2], s.st));
+        CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, kTrailer + reply, cudaMemcpyDeviceToHost, s.st));
+        CU_TRY(cudaEventRecord(s.ev[3], s.st));
         CU_TRY(cudaStreamSynchronize(s.st));
-        const int err = *s.h_err;
+        float t_h2d = 0, t_k = 0, t_d2h = 0;
+        cudaEventElapsedTime(&t_h2d, s.ev[0], s.ev[1]);
+        cudaEventElapsedTime(&t_k, s.ev[1], s.ev[2]);
+        cudaEventElapsedTime(&t_d2h, s.ev[2], s.ev[3]);
+        int32_t err = 0;
+        memcpy(&err, s.h_out + 8, 4);
         if (err == CSBWA_E_SCRATCH) return fail(CSBWA_E_SCRATCH, "generic-row scratch exhausted");
         if (err != 0) return fail(CSBWA_E_BADWIRE, "a task record points outside its buffer, or coalesced headers differ");
         unsigned long long cells = 0;
-        memcpy(&cells, s.h_out + tail, 8);
+        memcpy(&cells, s.h_out, 8);
         size_t in_b = 0;
         for (int c = 0; c < n_calls; ++c) in_b += (size_t)calls[c].in_bytes;
         {
             std::lock_guard<std::mutex> lk(g_stats_mu);
             g_stats.ext_calls += n_calls; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)cells;
             g_stats.ext_in_bytes += (int64_t)in_b; g_stats.ext_out_bytes += (int64_t)reply;
-            g_stats.kernel_launches += kExtLaunches;
+            g_stats.kernel_launches += kExtLaunches + 1;
             g_stats.ext_groups += 1;
+            g_stats.h2d_ms += t_h2d; g_stats.kernel_ms += t_k; g_stats.d2h_ms += t_d2h;
             g_stats.host_ms += now_ms() - t0;
         }
         return CSBWA_OK;
@@ -690,7 +742,7 @@ static int get_coalescer(int dev, Coalescer<CudaCoExec> **out)
         // group buffers / submission threads per GPU (CSBWA_CO_SLOTS / CSBWA_CO_WORKERS to tune)
         const int n_slots = env_int("CSBWA_CO_SLOTS", 8, 2, 32);
         const int n_workers = env_int("CSBWA_CO_WORKERS", n_slots - 1, 1, n_slots);
-        rc = d->exec.init(dev, n_slots, kCoMaxBytes, kCoMaxTasks);
+        rc = d->exec.init(dev, n_slots, kCoMaxBytes, kCoMaxTasks, (size_t)kCoMaxCalls * sizeof(CoCall));
         if (rc) { d->exec.destroy(); delete d; return rc; }
         Coalescer<CudaCoExec>::Limits lim{kCoMaxBytes, kCoMaxTasks, kCoMaxCalls};
         d->co = new Coalescer<CudaCoExec>(&d->exec, n_slots, n_workers, lim);

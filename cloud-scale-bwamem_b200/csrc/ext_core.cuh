@@ -254,211 +254,3 @@ CSW_HD int seg_lr(const ExtTask &t) { return t.lq + t.rq; }
 CSW_HD int seg_rr(const ExtTask &t) { return t.lq + t.rq + t.lr; }
 
 } // namespace csw
-
-// =====================================================================================
-// dual core: TWO SWExtend sides per thread, one in each 16-bit lane of the DPX s16x2 forms
-// =====================================================================================
-// Both tasks advance row by row together; every recurrence instruction (VIADDMNMX.S16x2,
-// VIMNMX.S16x2/U16x2, PRMT) updates one cell of each task.  Per query column the thread keeps
-//   .x = { H_A, E_A, H_B, E_B } (bytes)     .y = PRMT selector that picks BOTH scores at once
-// The two bands are independent, so the column loop runs over the union of the two bands and a
-// lane that is outside its own band simply computes garbage: stale entries outside [beg, end] are
-// never read before they are rewritten (same invariant the reference's eh[] relies on), the
-// lane's running state is reset when its band begins and snapshotted when its band ends, and
-// nothing a lane computes can carry into the other lane.  The row max / arg-max of both tasks is
-// ONE packed key (h << 8 | j per lane, unsigned max => last j on ties); the "last zero" tracker is
-// a second packed max.  Preconditions per task: u8_eligible(), no N in the query.
-namespace csw {
-
-struct U2 { uint32_t x, y; };
-
-struct DualTask {
-    const uint32_t *words;
-    int q_nib, qlen, t_nib, tlen, h0;
-};
-
-// stage both queries; returns true if either query holds an N (caller must use the scalar core)
-CSW_HD bool u8_stage_dual(U2 *col, int stride, const DualTask &A, const DualTask &B)
-{
-    const int n = A.qlen > B.qlen ? A.qlen : B.qlen;
-    NibStream qa, qb;
-    if (A.qlen > 0) qa.init(A.words, A.q_nib);
-    if (B.qlen > 0) qb.init(B.words, B.q_nib);
-    bool has_n = false;
-    for (int j = 0; j <= n; ++j) {
-        int a = j < A.qlen ? qa.next() : 0;
-        int b = j < B.qlen ? qb.next() : 0;
-        if (a > 3 || b > 3) { has_n = true; a &= 3; b &= 3; }
-        U2 v;
-        v.x = 0;
-        // nibbles: lane A <- byte a of table A (+ sign), lane B <- byte b of table B (+ sign)
-        v.y = (uint32_t)a * 0x0011u + (uint32_t)(4 + b) * 0x1100u + 0x8080u;
-        col[(long long)j * stride] = v;
-    }
-    return has_n;
-}
-
-struct DualState {          // scalar per-task state of SWExtend
-    int best, best_i, best_j, best_ie, gscore, max_off, beg, end, cells, w;
-    bool act;
-};
-
-CSW_HD void dual_init(DualState &s, const SwOpt &o, const DualTask &t, int w_in, int end_bonus)
-{
-    s.best = t.h0; s.best_i = -1; s.best_j = -1; s.best_ie = -1; s.gscore = -1; s.max_off = 0;
-    s.beg = 0; s.end = t.qlen; s.cells = 0;
-    s.w = t.qlen > 0 ? clamp_band(o, w_in, t.qlen, end_bonus) : w_in;
-    s.act = t.qlen > 0 && t.tlen > 0;
-}
-
-// row-end logic of one task (S/util/SWUtil.scala:174-214) on its byte lane (LANE 0 = A, 1 = B)
-template <int LANE>
-CSW_HD void dual_row_end(const SwOpt &o, DualState &s, const DualTask &t, U2 *col, int stride, int i,
-                         bool empty, int h1_init, int sh1, int skey, int szk)
-{
-    const int sh = LANE ? 16 : 0;             // H byte of this lane inside .x
-    int h1 = empty ? h1_init : sh1;
-    {   // eh(end) = {h1, 0}: only this lane's two bytes
-        U2 *pe = col + (long long)s.end * stride;
-        pe->x = (pe->x & ~(0xffffu << sh)) | (((uint32_t)h1 & 0xffu) << sh);
-    }
-    const int jfin = empty ? s.beg : s.end;
-    if (jfin == t.qlen && s.gscore <= h1) { s.best_ie = i; s.gscore = h1; }
-    const int rm = empty ? 0 : (skey >> 8), rmj = skey & 0xff;
-    if (!empty) s.cells += s.end - s.beg;
-    if (rm == 0) { s.act = false; return; }
-    if (rm > s.best) {
-        s.best = rm; s.best_i = i; s.best_j = rmj;
-        int off = rmj - i; if (off < 0) off = -off;
-        s.max_off = imax(s.max_off, off);
-    } else if (o.zdrop > 0) {
-        const int di = i - s.best_i, dj = rmj - s.best_j;
-        if (di > dj) {
-            if (s.best - rm - (di - dj) * o.e_del > o.zdrop) { s.act = false; return; }
-            else if (s.best - rm - (dj - di) * o.e_ins > o.zdrop) { s.act = false; return; }
-        }
-    }
-    // band shrink (:201-214).  szk = 1 + last zero position among the stored H of the band (or beg)
-    const bool zero_right = (szk - 1 > rmj) || (h1 == 0);
-    int nbeg = szk, nend = s.end + 1;
-    if (zero_right) {
-        int j = rmj;
-        while (j >= s.beg && ((col[(long long)j * stride].x >> sh) & 0xffu) != 0) --j;
-        nbeg = j + 1;
-        j = rmj + 2;
-        while (j <= s.end && ((col[(long long)j * stride].x >> sh) & 0xffu) != 0) ++j;
-        nend = j;
-    }
-    s.beg = nbeg; s.end = nend;
-}
-
-CSW_HD void dual_result(const DualState &s, SwExtRes &r)
-{
-    r.score = s.best; r.qle = s.best_j + 1; r.tle = s.best_i + 1; r.gtle = s.best_ie + 1;
-    r.gscore = s.gscore; r.max_off = s.max_off; r.cells = s.cells;
-}
-
-CSW_HD void sw_extend_u8_dual(const SwOpt &o, U2 *col, int stride, const DualTask &A, const DualTask &B,
-                              int w_in, int end_bonus, SwExtRes &rA, SwExtRes &rB)
-{
-    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-    const uint32_t ne_del2 = pk16(-o.e_del, -o.e_del), ne_ins2 = pk16(-o.e_ins, -o.e_ins);
-    const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
-    const int BIG = 0x3fffffff;
-    // first rows (:96-104) into the byte lanes; E = 0
-    {
-        const int n = A.qlen > B.qlen ? A.qlen : B.qlen;
-        int va = A.h0 > oe_ins ? A.h0 - oe_ins : 0, vb = B.h0 > oe_ins ? B.h0 - oe_ins : 0;
-        col[0].x = ((uint32_t)A.h0 & 0xffu) | (((uint32_t)B.h0 & 0xffu) << 16);
-        for (int j = 1; j <= n; ++j) {
-            col[(long long)j * stride].x = ((uint32_t)va & 0xffu) | (((uint32_t)vb & 0xffu) << 16);
-            va = va > o.e_ins ? va - o.e_ins : 0;
-            vb = vb > o.e_ins ? vb - o.e_ins : 0;
-        }
-    }
-    DualState sa, sb;
-    dual_init(sa, o, A, w_in, end_bonus);
-    dual_init(sb, o, B, w_in, end_bonus);
-    NibStream ta, tb;
-    if (sa.act) ta.init(A.words, A.t_nib);
-    if (sb.act) tb.init(B.words, B.t_nib);
-    for (int i = 0; sa.act || sb.act; ++i) {
-        if (sa.act && i >= A.tlen) sa.act = false;
-        if (sb.act && i >= B.tlen) sb.act = false;
-        if (!sa.act && !sb.act) break;
-        uint32_t tabA = 0, tabB = 0;
-        int h1iA = 0, h1iB = 0;
-        int bA = BIG, eA = BIG, bB = BIG, eB = BIG;      // event columns of this row
-        bool emptyA = true, emptyB = true;
-        if (sa.act) {
-            int t = ta.next(); if (t > 4) t = 4;
-            tabA = o.tlo[t];
-            h1iA = imax(A.h0 - (o.o_del + o.e_del * (i + 1)), 0);
-            sa.beg = imax(sa.beg, i - sa.w);
-            sa.end = min3(sa.end, i + sa.w + 1, A.qlen);
-            emptyA = !(sa.beg < sa.end);
-            if (!emptyA) { bA = sa.beg; eA = sa.end; }
-        }
-        if (sb.act) {
-            int t = tb.next(); if (t > 4) t = 4;
-            tabB = o.tlo[t];
-            h1iB = imax(B.h0 - (o.o_del + o.e_del * (i + 1)), 0);
-            sb.beg = imax(sb.beg, i - sb.w);
-            sb.end = min3(sb.end, i + sb.w + 1, B.qlen);
-            emptyB = !(sb.beg < sb.end);
-            if (!emptyB) { bB = sb.beg; eB = sb.end; }
-        }
-        // packed running state
-        uint32_t f2 = 0, h1_2 = 0, key2 = 0, zk2 = 0;
-        int sh1A = 0, skeyA = 0, szkA = 0, sh1B = 0, skeyB = 0, szkB = 0;
-        const int lo = imin(bA, bB);
-        const int hi = (emptyA && emptyB) ? lo : imax(emptyA ? -1 : eA, emptyB ? -1 : eB);
-        int j = lo;
-        while (j < BIG) {
-            // events at column j
-            if (j == bA) { f2 &= 0xffff0000u; h1_2 = (h1_2 & 0xffff0000u) | (uint32_t)h1iA; key2 &= 0xffff0000u;
-                           zk2 = (zk2 & 0xffff0000u) | (uint32_t)bA; }
-            if (j == bB) { f2 &= 0x0000ffffu; h1_2 = (h1_2 & 0x0000ffffu) | ((uint32_t)h1iB << 16); key2 &= 0x0000ffffu;
-                           zk2 = (zk2 & 0x0000ffffu) | ((uint32_t)bB << 16); }
-            if (j == eA) { sh1A = (int)(h1_2 & 0xffffu); skeyA = (int)(key2 & 0xffffu); szkA = (int)(zk2 & 0xffffu); }
-            if (j == eB) { sh1B = (int)(h1_2 >> 16); skeyB = (int)(key2 >> 16); szkB = (int)(zk2 >> 16); }
-            if (j >= hi) break;
-            int nxt = hi;
-            if (bA > j) nxt = imin(nxt, bA);
-            if (bB > j) nxt = imin(nxt, bB);
-            if (eA > j) nxt = imin(nxt, eA);
-            if (eB > j) nxt = imin(nxt, eB);
-            // packed cell loop over [j, nxt)
-            U2 *p = col + (long long)j * stride;
-            U2 wn = *p;
-            uint32_t jj2 = (uint32_t)j * 0x00010001u;             // (j, j)
-            for (int c = j; c < nxt; ++c) {
-                const U2 wv = wn;
-                wn = p[stride];                                   // column c + 1 always exists
-                const uint32_t H2 = prmt(wv.x, 0u, 0x4240u);      // (H_A, H_B)
-                const uint32_t E2 = prmt(wv.x, 0u, 0x4341u);      // (E_A, E_B)
-                const uint32_t S2 = prmt(tabA, tabB, wv.y);       // both substitution scores, sign-extended
-                // zero tracker: stored H at column c is h1_2; candidate = c + 1 where it is 0
-                const uint32_t nz2 = umin2(h1_2, 0x00010001u);
-                const uint32_t jp2 = jj2 + 0x00010001u;
-                zk2 = umax2(zk2, umad(nz2, (uint32_t)(-(c + 1)), jp2));
-                uint32_t h2 = addmax2(H2, S2, E2);
-                h2 = max2(h2, f2);
-                key2 = umax2(key2, prmt(h2, jj2, 0x2604u));       // (h << 8 | c) per lane, low byte of h only
-                const uint32_t e2n = addmax2(E2, ne_del2, addmax2_relu(h2, noe_del2, 0u));
-                f2 = addmax2(f2, ne_ins2, addmax2_relu(h2, noe_ins2, 0u));
-                p->x = prmt(h1_2, e2n, 0x6240u);                  // { H_A, E_A, H_B, E_B }
-                h1_2 = h2;
-                jj2 = jp2;
-                p += stride;
-            }
-            j = nxt;
-        }
-        if (sa.act) dual_row_end<0>(o, sa, A, col, stride, i, emptyA, h1iA, sh1A, skeyA, szkA);
-        if (sb.act) dual_row_end<1>(o, sb, B, col, stride, i, emptyB, h1iB, sh1B, skeyB, szkB);
-    }
-    dual_result(sa, rA);
-    dual_result(sb, rB);
-}
-
-} // namespace csw

@@ -27,11 +27,20 @@ struct ExtCall {
     int pad;
 };
 struct ExtCalls {         // passed to the kernels by value
-    const ExtCall *tab;   // device table (unused when n_calls == 1)
+    const ExtCall *tab;   // device table; nullptr = one call, described by `single`
     int n_calls;
     ExtCall single;
+    // When non-null, {n_calls, n_tasks} are read from device memory instead of the by-value fields:
+    // the launch sequence then has no launch-time dependence on the batch and can be replayed as
+    // a CUDA graph (the host seam does this, one graph per staging slot).
+    const int32_t *dyn;
 };
-CSW_HD const ExtCall &ext_call(const ExtCalls &cs, int c) { return cs.n_calls == 1 ? cs.single : cs.tab[c]; }
+CSW_HD const ExtCall &ext_call(const ExtCalls &cs, int c) { return cs.tab ? cs.tab[c] : cs.single; }
+// by-value -> effective parameters (device side)
+CSW_HD void ext_resolve(ExtCalls &cs, int &n)
+{
+    if (cs.dyn) { cs.n_calls = cs.dyn[0]; n = cs.dyn[1]; }
+}
 // global task index -> call index (largest c with task_base <= g)
 CSW_HD int ext_locate(const ExtCalls &cs, int g)
 {
@@ -47,8 +56,7 @@ constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty 
 constexpr int EXT_NCLS = 6;            // 0: generic, then fast classes by column capacity: 256, 128, 96, 64, 32
 // extension cores (csbwa_set_ext_mode): which fast core serves the eligible sides
 constexpr int EXT_CORE_U8 = 0;         // one column per step, u8 scores (ext_core.cuh sw_extend_u8)
-constexpr int EXT_CORE_DUAL = 1;       // two tasks per thread in the s16x2 lanes (sw_extend_u8_dual)
-constexpr int EXT_CORE_P2 = 2;         // two adjacent columns per step, s16 scores (ext_p2.cuh)
+constexpr int EXT_CORE_P2 = 1;         // two adjacent columns per step, s16 scores (ext_p2.cuh)
 constexpr int EXT_BD = 128;            // threads per block of the side kernels
 
 struct ExtHdr {
@@ -146,6 +154,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
 {
     __shared__ uint32_t sh[2][EXT_NBIN];
     __shared__ SwOpt sopt;
+    ext_resolve(cs, n);
     for (int i = threadIdx.x; i < 2 * EXT_NBIN; i += blockDim.x) (&sh[0][0])[i] = 0;
     if (threadIdx.x == 0) {
         const uint8_t *in0 = base + ext_call(cs, 0).in_off;
@@ -162,8 +171,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
         }
     }
     __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
         const ExtCall &cl = ext_call(cs, ext_locate(cs, g));
         const uint8_t *in = base + cl.in_off;
         ExtTask t = read_task(in, g - cl.task_base);
@@ -210,21 +218,25 @@ __global__ void k_ext_scan(ExtHdr *hdr)
 __global__ void k_ext_scatter(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr,
                               uint32_t *__restrict__ order_l, uint32_t *__restrict__ order_r)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;      // global task index
-    if (k >= n) return;
+    ext_resolve(cs, n);
     const SwOpt &o = hdr->opt;
-    const ExtCall &cl = ext_call(cs, ext_locate(cs, k));
-    ExtTask t = read_task(base + cl.in_off, k - cl.task_base);
-    int bl = 0, br = 0;
-    if (ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
-        bl = ext_side_bin(o, t.lq, t.h0, hdr->core);
-        const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
-        br = ext_side_bin(o, t.rq, h0r, hdr->core);
-        if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {   // global task index
+        const ExtCall &cl = ext_call(cs, ext_locate(cs, k));
+        ExtTask t = read_task(base + cl.in_off, k - cl.task_base);
+        int bl = 0, br = 0;
+        if (ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
+            bl = ext_side_bin(o, t.lq, t.h0, hdr->core);
+            const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
+            br = ext_side_bin(o, t.rq, h0r, hdr->core);
+            if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+        }
+        if (bl) order_l[hdr->base[0][bl] + atomicAdd(&hdr->cursor[0][bl], 1u)] = (uint32_t)k;
+        order_r[hdr->base[1][br] + atomicAdd(&hdr->cursor[1][br], 1u)] = (uint32_t)k;
     }
-    if (bl) order_l[hdr->base[0][bl] + atomicAdd(&hdr->cursor[0][bl], 1u)] = (uint32_t)k;
-    order_r[hdr->base[1][br] + atomicAdd(&hdr->cursor[1][br], 1u)] = (uint32_t)k;
 }
+
+// copies the status word next to the replies so that one D2H brings both (graph path of the host seam)
+__global__ void k_ext_finish(const ExtHdr *hdr, int32_t *status_out) { *status_out = hdr->err; }
 
 // ---------------------------------------------------------------------------------
 // side kernels
@@ -271,41 +283,6 @@ CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, in
     out.cells = cells;
 }
 
-// One side of TWO tasks in one thread (dual s16x2 core); B may be absent (B.qlen == 0).
-// Falls back to the scalar u8 core for a query that holds an N and for the rare second band try.
-CSW_HD void ext_run_side_dual(const SwOpt &o, U2 *col, int stride, const DualTask &A, const DualTask &B,
-                              int end_bonus, int prevA, int prevB, SideRes &outA, SideRes &outB)
-{
-    uint32_t *col1 = (uint32_t *)col;            // scalar view of the same shared-memory columns
-    const int stride1 = 2 * stride;
-    const bool has_n = u8_stage_dual(col, stride, A, B);
-    if (has_n) {
-        if (A.qlen > 0) ext_run_side<true>(o, A.words, A.q_nib, A.qlen, A.t_nib, A.tlen, end_bonus, A.h0, prevA, col1, stride1, nullptr, nullptr, outA);
-        if (B.qlen > 0) ext_run_side<true>(o, B.words, B.q_nib, B.qlen, B.t_nib, B.tlen, end_bonus, B.h0, prevB, col1, stride1, nullptr, nullptr, outB);
-        return;
-    }
-    SwExtRes rA, rB;
-    sw_extend_u8_dual(o, col, stride, A, B, o.w, end_bonus, rA, rB);
-    const DualTask *T[2] = {&A, &B};
-    SwExtRes *R[2] = {&rA, &rB};
-    SideRes *O[2] = {&outA, &outB};
-    const int prev[2] = {prevA, prevB};
-    for (int x = 0; x < 2; ++x) {
-        if (T[x]->qlen <= 0) continue;
-        SwExtRes r = *R[x];
-        int aw = o.w, cells = r.cells;
-        if (!(r.score == prev[x] || r.max_off < (aw >> 1) + (aw >> 2))) {      // second band try (:810-824)
-            aw = o.w << 1;
-            u8_stage_query(col1, stride1, T[x]->words, T[x]->q_nib, T[x]->qlen);
-            sw_extend_u8(o, col1, stride1, T[x]->qlen, T[x]->words, T[x]->t_nib, T[x]->tlen, aw, end_bonus, T[x]->h0, r);
-            cells += r.cells;
-        }
-        O[x]->score = (int16_t)r.score; O[x]->qle = (int16_t)r.qle; O[x]->tle = (int16_t)r.tle;
-        O[x]->gtle = (int16_t)r.gtle; O[x]->gscore = (int16_t)r.gscore; O[x]->aw = (int16_t)aw;
-        O[x]->cells = cells;
-    }
-}
-
 // SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range.
 // CORE: -1 generic (int32 rows in global scratch), EXT_CORE_U8, EXT_CORE_P2 (shared memory).
 // npairs: column pairs per thread of the P2 layout ({H2,E2} records first, then the selectors).
@@ -317,6 +294,7 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
 {
     extern __shared__ uint4 smem4[];
     constexpr bool FAST = CORE >= 0;
+    { int n_unused = 0; ext_resolve(cs, n_unused); }
     const SwOpt &o = hdr->opt;
     const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
     const int lane = threadIdx.x & 31;
@@ -383,87 +361,6 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
-            }
-        }
-    }
-    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
-}
-
-} // namespace csw
-
-namespace csw {
-
-// dual variant of the fast side kernel: every thread owns TWO consecutive jobs of the sorted list
-template <int SIDE>
-__global__ void __launch_bounds__(EXT_BD)
-k_ext_side_dual(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
-                SideRes *__restrict__ left, int16_t *__restrict__ out, unsigned long long *cells_acc, int cls)
-{
-    extern __shared__ U2 smem2[];
-    const SwOpt &o = hdr->opt;
-    const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
-    const int lane = threadIdx.x & 31;
-    const int stride = (int)blockDim.x;
-    U2 *col = smem2 + threadIdx.x;
-    unsigned long long my_cells = 0;
-    for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&hdr->work[SIDE][cls], 64u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0) + jbeg;
-        if (chunk >= jend) break;
-        const uint32_t job0 = chunk + 2 * lane;
-        if (job0 < jend) {
-            ExtTask t[2];
-            const ExtCall *cl[2];
-            int k[2] = {-1, -1};
-            DualTask D[2];
-            SideRes L[2], R[2];
-            int prev[2] = {0, 0};
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                D[x].words = nullptr; D[x].q_nib = D[x].t_nib = 0; D[x].qlen = 0; D[x].tlen = 0; D[x].h0 = 0;
-                L[x].score = 0; L[x].qle = L[x].tle = L[x].gtle = L[x].gscore = 0; L[x].aw = (int16_t)o.w; L[x].cells = 0;
-                R[x] = L[x];
-                cl[x] = nullptr;
-                if (job0 + x >= jend) continue;
-                k[x] = (int)order[job0 + x];
-                cl[x] = &ext_call(cs, ext_locate(cs, k[x]));
-                const uint8_t *in = base + cl[x]->in_off;
-                const int n = cl[x]->n_tasks;
-                t[x] = read_task(in, k[x] - cl[x]->task_base);
-                if (!ext_task_ok(t[x], n, cl[x]->in_bytes)) { t[x].lq = t[x].lr = t[x].rq = t[x].rr = 0; t[x].pos = 8 + 8 * n; }
-                D[x].words = (const uint32_t *)in + t[x].pos;
-                if (SIDE == 0) {
-                    D[x].q_nib = seg_lq(t[x]); D[x].qlen = t[x].lq; D[x].t_nib = seg_lr(t[x]); D[x].tlen = t[x].lr;
-                    D[x].h0 = t[x].h0; prev[x] = t[x].reg_score;
-                } else {
-                    if (t[x].lq > 0) L[x] = left[k[x]];
-                    const int sc0 = t[x].lq > 0 ? (int)L[x].score : t[x].reg_score;
-                    D[x].q_nib = seg_rq(t[x]); D[x].qlen = t[x].rq; D[x].t_nib = seg_rr(t[x]); D[x].tlen = t[x].rr;
-                    D[x].h0 = sc0; prev[x] = sc0;
-                }
-            }
-            if (D[0].qlen > 0 || D[1].qlen > 0) {
-                SideRes *S = (SIDE == 0) ? L : R;
-                if (D[0].qlen > 0) ext_run_side_dual(o, col, stride, D[0], D[1], SIDE == 0 ? o.pen_clip5 : o.pen_clip3,
-                                                     prev[0], prev[1], S[0], S[1]);
-                else ext_run_side_dual(o, col, stride, D[1], D[0], SIDE == 0 ? o.pen_clip5 : o.pen_clip3,
-                                       prev[1], prev[0], S[1], S[0]);
-                my_cells += (unsigned)S[0].cells + (unsigned)S[1].cells;
-            }
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                if (k[x] < 0) continue;
-                if (SIDE == 0) {
-                    left[k[x]] = L[x];
-                } else {
-                    int16_t rec[10];
-                    ext_finalize(o, t[x], &L[x], &R[x], rec);
-                    uint32_t *dst = (uint32_t *)(out + cl[x]->out_off + (size_t)10 * (k[x] - cl[x]->task_base));
-#pragma unroll
-                    for (int q = 0; q < 5; ++q)
-                        dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
-                }
             }
         }
     }

@@ -190,9 +190,8 @@ int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_
 
 /* number of kernels one *_batch_device call enqueues (for launch accounting) */
 int csbwa_extend_launches_per_call(void);
-/* extension core: 2 = two adjacent query columns per DPX s16x2 instruction (default), 0 = one
- * column per step with u8 scores, 1 = two SWExtend sides per thread in the s16x2 lanes.
- * Returns the previous mode; any other argument only queries. */
+/* extension core: 1 = two adjacent query columns per DPX s16x2 instruction (default), 0 = one
+ * column per step with u8 scores.  Returns the previous mode; any other argument only queries. */
 int csbwa_set_ext_mode(int mode);
 int csbwa_align2_launches_per_call(void);
 

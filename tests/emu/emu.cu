@@ -13,77 +13,6 @@
 
 using namespace csw;
 
-// dual mode: the two-tasks-per-thread s16x2 core, pairing consecutive fast jobs of each side the
-// way k_ext_side_dual pairs consecutive entries of the sorted job list
-extern "C" int emu_extend_wire_dual(const uint8_t *in, int in_bytes, int16_t *out, int64_t *cells_per_task,
-                                    int32_t *dual_pairs)
-{
-    SwOpt o;
-    ext_parse_header(in, o);
-    int n;
-    memcpy(&n, in + 8, 4);
-    std::vector<ExtTask> T(n);
-    std::vector<SideRes> L(n), R(n);
-    std::vector<int64_t> cells(n, 0);
-    std::vector<int> fastL, fastR, slowL, slowR;
-    for (int k = 0; k < n; ++k) {
-        T[k] = read_task(in, k);
-        if (!ext_task_ok(T[k], n, in_bytes)) return -3;
-        memset(&L[k], 0, sizeof(SideRes)); memset(&R[k], 0, sizeof(SideRes));
-        L[k].aw = R[k].aw = (int16_t)o.w;
-        int bl = ext_side_bin(o, T[k].lq, T[k].h0);
-        const int h0r = T[k].lq > 0 ? T[k].h0 + T[k].lq * o.max_mat : T[k].reg_score;
-        int br = ext_side_bin(o, T[k].rq, h0r);
-        if (T[k].lq > 0 && bl == 256 && br != 0) br = 256;
-        if (bl) (bl == 256 ? slowL : fastL).push_back(k);
-        if (br) (br == 256 ? slowR : fastR).push_back(k);
-    }
-    const int stride = 3;
-    int npairs = 0;
-    for (int side = 0; side < 2; ++side) {
-        std::vector<int> &fast = side ? fastR : fastL, &slow = side ? slowR : slowL;
-        std::vector<SideRes> &S = side ? R : L;
-        for (int k : slow) {
-            const ExtTask &t = T[k];
-            const uint32_t *words = (const uint32_t *)in + t.pos;
-            const int qm = t.lq > t.rq ? t.lq : t.rq;
-            std::vector<int> HE((size_t)2 * (qm + 2));
-            if (side == 0) ext_run_side<false>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, nullptr, 1, HE.data(), HE.data() + qm + 2, S[k]);
-            else { const int sc0 = t.lq > 0 ? (int)L[k].score : t.reg_score;
-                   ext_run_side<false>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, nullptr, 1, HE.data(), HE.data() + qm + 2, S[k]); }
-            cells[k] += S[k].cells;
-        }
-        for (size_t x = 0; x < fast.size(); x += 2) {
-            DualTask D[2];
-            int prev[2] = {0, 0}, kk[2] = {fast[x], x + 1 < fast.size() ? fast[x + 1] : -1};
-            int qm = 1;
-            for (int y = 0; y < 2; ++y) {
-                D[y].words = nullptr; D[y].q_nib = D[y].t_nib = D[y].qlen = D[y].tlen = D[y].h0 = 0;
-                if (kk[y] < 0) continue;
-                const ExtTask &t = T[kk[y]];
-                D[y].words = (const uint32_t *)in + t.pos;
-                if (side == 0) { D[y].q_nib = seg_lq(t); D[y].qlen = t.lq; D[y].t_nib = seg_lr(t); D[y].tlen = t.lr; D[y].h0 = t.h0; prev[y] = t.reg_score; }
-                else { const int sc0 = t.lq > 0 ? (int)L[kk[y]].score : t.reg_score;
-                       D[y].q_nib = seg_rq(t); D[y].qlen = t.rq; D[y].t_nib = seg_rr(t); D[y].tlen = t.rr; D[y].h0 = sc0; prev[y] = sc0; }
-                if (D[y].qlen > qm) qm = D[y].qlen;
-            }
-            std::vector<U2> col((size_t)(qm + 2) * stride);
-            for (auto &c : col) { c.x = 0xdeadbeefu; c.y = 0xdeadbeefu; }
-            SideRes dummy;
-            ext_run_side_dual(o, col.data(), stride, D[0], D[1], side == 0 ? o.pen_clip5 : o.pen_clip3, prev[0], prev[1],
-                              S[kk[0]], kk[1] >= 0 ? S[kk[1]] : dummy);
-            cells[kk[0]] += S[kk[0]].cells;
-            if (kk[1] >= 0) { cells[kk[1]] += S[kk[1]].cells; ++npairs; }
-        }
-    }
-    for (int k = 0; k < n; ++k) {
-        ext_finalize(o, T[k], &L[k], &R[k], out + (size_t)10 * k);
-        if (cells_per_task) cells_per_task[k] = cells[k];
-    }
-    if (dual_pairs) *dual_pairs = npairs;
-    return 0;
-}
-
 // p2 mode: the column-pair core (csrc/ext_p2.cuh) for every side it is eligible for
 extern "C" int emu_extend_wire_p2(const uint8_t *in, int in_bytes, int16_t *out, int64_t *cells_per_task,
                                   int32_t *fast_sides)

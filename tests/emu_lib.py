@@ -54,17 +54,6 @@ class Emu:
         assert rc == 0, rc
         return out, cells, nfast.value
 
-    def extend_wire_dual(self, buf):
-        buf = np.ascontiguousarray(buf, dtype=np.uint8)
-        n = int(np.frombuffer(buf[8:12].tobytes(), dtype="<i4")[0])
-        out = np.zeros(10 * n, dtype=np.int16)
-        cells = np.zeros(n, dtype=np.int64)
-        npairs = C.c_int32(0)
-        self.lib.emu_extend_wire_dual.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        rc = self.lib.emu_extend_wire_dual(buf.ctypes.data, buf.size, out.ctypes.data, cells.ctypes.data, C.addressof(npairs))
-        assert rc == 0, rc
-        return out, cells, npairs.value
-
     def align2_batch(self, jobs, seqs, force_generic=False):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)

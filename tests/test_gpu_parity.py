@@ -27,14 +27,13 @@ def _ext_gpu(pkg, wire, device=-1):
 
 
 def _check_ext(pkg, oracle, wire):
-    """Every extension core (2 = two query columns per DPX instruction, the default; 0 = one column
-    per step; 1 = two tasks per thread) must reproduce the oracle bit for bit, including the exact
-    DP cell count."""
+    """Both extension cores (1 = two query columns per DPX instruction, the default; 0 = one column
+    per step) must reproduce the oracle bit for bit, including the exact DP cell count."""
     ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
     L = pkg.lib()
     prev = L.csbwa_set_ext_mode(-1)
     try:
-        for mode in (2, 0, 1):
+        for mode in (1, 0):
             L.csbwa_set_ext_mode(mode)
             before = pkg.stats()["ext_cells"]
             got = _ext_gpu(pkg, wire)
@@ -49,7 +48,7 @@ def _check_ext(pkg, oracle, wire):
 def test_ext_golden(pkg, oracle, gpu):
     g = np.load(os.path.join(GOLD, "ext_golden.npz"))
     L = pkg.lib()
-    for mode in (0, 1, 2):
+    for mode in (0, 1):
         L.csbwa_set_ext_mode(mode)
         got = _ext_gpu(pkg, g["wire"])
         assert np.array_equal(got, g["reply"]), mode
