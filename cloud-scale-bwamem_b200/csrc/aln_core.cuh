@@ -9,12 +9,13 @@
 //
 // Two cores, both host+device:
 //   * sw_align2_generic : one thread per job, rows in caller memory.  Any size.
-//   * AlnLane<C> + AlnBook : the fast path.  One warp per job as a 32-stage systolic array:
-//     lane l owns query columns [l*C, (l+1)*C) in registers and processes target row (s - l)
-//     at step s; H of its last column, the running F, the running row-max key and the
-//     target base flow to lane l+1 by one shuffle step.  SWAlign has no band and no
-//     row-to-row control except "stop at score X", so the skew is exact: the lane that owns
-//     the last column sees complete rows in order and does the sequential bookkeeping.
+//   * AlnLaneP<P> + AlnBook : the fast path.  16 lanes per job as a 16-stage systolic array:
+//     lane l owns query columns [l*2P, (l+1)*2P) in registers, two adjacent columns per s16x2
+//     register, and processes target row (s - l) at step s; H of its last column, the running F,
+//     the running row-max keys and the target base flow to lane l+1 by one shuffle step.
+//     SWAlign has no band and no row-to-row control except "stop at score X", so the skew is
+//     exact: the lane that owns the last column sees complete rows in order and does the
+//     sequential bookkeeping.
 #pragma once
 #include "sw_common.cuh"
 
@@ -133,82 +134,98 @@ CSW_HD long long sw_align2_generic(const SwOpt &o, const uint8_t *q, int qlen, c
 }
 
 // ---------------------------------------------------------------------------------
-// systolic lane
+// packed systolic lane: P column PAIRS per lane (low half = even column), s16x2 DPX
 // ---------------------------------------------------------------------------------
-struct AlnMsg {
-    int h;      // H(i, last column of the sender)
-    int ft;     // F(i, first column of the receiver) | target base << 16
-    int key;    // running row max: h << 16 | (0xffff - j)  (largest h, smallest j)
+// Same skewed wavefront as AlnLane, 16 lanes per job (two jobs per warp) and two adjacent query
+// columns per instruction like the extension's p2 core: H' = max(Hd + S, E) and g = relu(H' - oeIns)
+// for both columns at once, the insertion chain F(j+1) = max(F(j) - eIns, g(j)) as two 32-bit
+// VIADDMNMX, then H = max(H', F) and the E update packed again.  The running row max is a packed
+// unsigned key h << 8 | (255 - j) per half (largest h, first j; merged by the last lane): valid
+// rows have h <= 251 because the pass stops at 255 - |b| (S/util/SWUtil.scala:537), and rows
+// computed past the stop (the skew runs ahead by at most 15 rows) are never consumed.
+struct AlnMsgP {
+    uint32_t h;      // H(i, last column of the sender)
+    uint32_t ft;     // F(i, first column of the receiver) | target base << 16
+    uint32_t key2;   // running packed row-max keys
 };
 
-template <int C>
-struct AlnLane {
-    int H[C], E[C];
-    uint32_t prof[C];     // byte t = score(target base t, this column's query base), t = 0..3
-    int kc[C];            // 0xffff - column index
-    int ncols;            // valid columns in this lane
-    int diag;             // H(i-1, first column - 1)
-    uint32_t nfill;       // byte 0 = score against target N
+constexpr int ALN_G = 16;      // lanes per job
+
+template <int P>
+struct AlnLaneP {
+    uint32_t H2[P], E2[P];
+    uint32_t pa[P], pb[P];     // byte t = score(target base t, even / odd column's query base), t = 0..3
+    uint32_t kc2[P];           // (255 - j) per column
+    uint32_t mk2[P];           // 0xffff per valid column (j < qn)
+    uint32_t dprev;            // H(i-1, first column - 1) << 16
 
     CSW_HD void setup(const SwOpt &o, const uint8_t *q, int qn, bool rev, int qe, int lane)
     {
-        ncols = qn - lane * C;
-        if (ncols > C) ncols = C;
-        if (ncols < 0) ncols = 0;
-        nfill = o.thi[0];
-        diag = 0;
+        dprev = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = lane * C + c;
-            H[c] = 0; E[c] = 0; kc[c] = 0xffff - j;
-            int qb = 4;
-            if (c < ncols) { qb = q[aln_qidx(rev, qe, j)]; if (qb > 4) qb = 4; }
-            prof[c] = o.tlo[qb];   // mat is symmetric: mat[t][q] == mat[q][t]
+        for (int p = 0; p < P; ++p) {
+            const int j0 = lane * 2 * P + 2 * p, j1 = j0 + 1;
+            int q0 = 4, q1 = 4;
+            if (j0 < qn) { q0 = q[aln_qidx(rev, qe, j0)]; if (q0 > 4) q0 = 4; }
+            if (j1 < qn) { q1 = q[aln_qidx(rev, qe, j1)]; if (q1 > 4) q1 = 4; }
+            H2[p] = 0; E2[p] = 0;
+            pa[p] = o.tlo[q0]; pb[p] = o.tlo[q1];          // mat is symmetric: mat[t][q] == mat[q][t]
+            kc2[p] = ((uint32_t)(255 - j0) & 0xffu) | (((uint32_t)(255 - j1) & 0xffu) << 16);
+            mk2[p] = (j0 < qn ? 0xffffu : 0u) | (j1 < qn ? 0xffff0000u : 0u);
         }
     }
 
-    // process one target row.  in: message of the left neighbour for THIS row.
-    CSW_HD void step(const SwOpt &o, const AlnMsg &in, AlnMsg &out)
+    // one target row.  TN: the target base is N (every score is mat[4][*] = thi[0])
+    template <bool TN>
+    CSW_HD void step(const SwOpt &o, const AlnMsgP &in, AlnMsgP &out)
     {
-        const int ne_del = -o.e_del, ne_ins = -o.e_ins;
-        const int noe_del = -(o.o_del + o.e_del), noe_ins = -(o.o_ins + o.e_ins);
-        const int t = in.ft >> 16;
-        const uint32_t sel = (uint32_t)t * 0x1111u + 0x8880u;
-        int f = in.ft & 0xffff;
-        int key = in.key;
-        int hd = diag;
-        diag = in.h;
-        int hl = in.h;
+        const int ne_ins = -o.e_ins;
+        const uint32_t ne_del2 = pk16(-o.e_del, -o.e_del);
+        const uint32_t noe_del2 = pk16(-(o.o_del + o.e_del), -(o.o_del + o.e_del));
+        const uint32_t noe_ins2 = pk16(-(o.o_ins + o.e_ins), -(o.o_ins + o.e_ins));
+        const uint32_t t = in.ft >> 16;
+        const uint32_t sel = t * 0x1111u + 0xc480u;        // {a[t], sign, b[t], sign}
+        const uint32_t sn = (uint32_t)(int)(int8_t)(o.thi[0] & 0xffu) & 0xffffu;
+        const uint32_t sn2 = sn | (sn << 16);
+        int f = (int)(in.ft & 0xffffu);
+        uint32_t key2 = in.key2;
+        uint32_t hprev2 = dprev;
+        dprev = in.h << 16;
+        uint32_t h2 = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            if (c < ncols) {
-                const int s = (int)prmt(prof[c], nfill, sel);
-                int h = addmax(hd, s, E[c]);
-                h = imax(h, f);
-                key = imax(key, (h << 16) + kc[c]);
-                E[c] = addmax(E[c], ne_del, addmax_relu(h, noe_del, 0));
-                f = addmax(f, ne_ins, addmax_relu(h, noe_ins, 0));
-                hd = H[c];
-                H[c] = h;
-                hl = h;
-            }
+        for (int p = 0; p < P; ++p) {
+            const uint32_t s2 = TN ? sn2 : prmt(pa[p], pb[p], sel);
+            const uint32_t hd2 = funnel16(hprev2, H2[p]);
+            hprev2 = H2[p];
+            const uint32_t hp2 = addmax2(hd2, s2, E2[p]);
+            const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2);
+            const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));
+            const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));
+            const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);
+            h2 = max2(hp2, f2);
+            E2[p] = addmax2(E2[p], ne_del2, addmax2_relu(h2, noe_del2, noe_del2));
+            key2 = umax2(key2, umad(h2 & mk2[p], 256u, kc2[p]));
+            H2[p] = h2;
+            f = fn;
         }
-        out.h = hl;
-        out.ft = f | (t << 16);
-        out.key = key;
+        out.h = h2 >> 16;
+        out.ft = (uint32_t)f | (t << 16);
+        out.key2 = key2;
     }
 };
 
-CSW_HD void aln_decode_key(int key, int &m, int &mj)
+CSW_HD void aln_decode_key2(uint32_t key2, int &m, int &mj)
 {
-    m = key >> 16;
-    mj = m > 0 ? 0xffff - (key & 0xffff) : -1;
+    const uint32_t lo = key2 & 0xffffu, hi = key2 >> 16;
+    const uint32_t k = lo > hi ? lo : hi;
+    m = (int)(k >> 8);
+    mj = m > 0 ? 255 - (int)(k & 0xffu) : -1;
 }
 
-// limits of the systolic path: scores are < 32768 (key packing) and F fits 16 bits
-CSW_HD bool aln_fast_eligible(const SwOpt &o, int qlen, int tlen, int cmax)
+// limits of the packed path: 16 lanes x 2P columns, column index and valid scores fit 8 bits
+CSW_HD bool aln_packed_eligible(const SwOpt &o, int qlen, int tlen, int pmax)
 {
-    return qlen >= 1 && qlen <= 32 * cmax && tlen >= 1 && qlen * o.max_mat < 30000 &&
+    return qlen >= 1 && qlen <= ALN_G * 2 * pmax && qlen <= 256 && tlen >= 1 && o.a == 1 && o.b >= 0 && o.b <= 100 &&
            o.e_del >= 0 && o.e_ins >= 0 && o.o_del >= 0 && o.o_ins >= 0;
 }
 

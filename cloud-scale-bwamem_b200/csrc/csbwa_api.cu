@@ -372,15 +372,16 @@ static int launch_align2(const AlnJob *d_jobs, int n, const uint8_t *d_seqs, int
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(AlnHdr), st));
     const int tb = 256, gb = (n + tb - 1) / tb;
     k_aln_classify<<<gb, tb, 0, st>>>(d_jobs, n, sc, (unsigned long long)(scratch_bytes - fixed));
-    int gw = (n + 3) / 4;
+    int gw = (n + 7) / 8;                       // 4 warps per block, 2 jobs per warp
     if (gw > sms * 8) gw = sms * 8;
+    if (gw < 1) gw = 1;
     int gg = (n + 127) / 128;
     if (gg > sms * 8) gg = sms * 8;
     k_aln_generic<<<gg, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells);
-    k_aln_warp<8><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 1);
-    k_aln_warp<5><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 2);
-    k_aln_warp<4><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 3);
-    k_aln_warp<2><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 4);
+    k_aln_half<8><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 1);
+    k_aln_half<5><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 2);
+    k_aln_half<4><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 3);
+    k_aln_half<2><<<gw, 128, 0, st>>>(d_jobs, d_seqs, sc, d_out, d_cells, 4);
     CU_TRY(cudaGetLastError());
     return CSBWA_OK;
 }

@@ -64,15 +64,6 @@ CSW_HD uint32_t ld_u16(const uint16_t *p)
 #endif
 }
 
-CSW_HD uint32_t funnel16(uint32_t lo, uint32_t hi)      // (hi:lo) >> 16
-{
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, 16);
-#else
-    return (lo >> 16) | (hi << 16);
-#endif
-}
-
 CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, int qlen,
                          const uint32_t *words, int t_nib, int tlen,
                          int w, int end_bonus, int h0, SwExtRes &res)

@@ -140,6 +140,16 @@ CSW_HD uint32_t umad(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// (hi:lo) >> 16: the diagonal of a column pair from the previous and the current H2 word -> SHF.R.W
+CSW_HD uint32_t funnel16(uint32_t lo, uint32_t hi)      // (hi:lo) >> 16
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, 16);
+#else
+    return (lo >> 16) | (hi << 16);
+#endif
+}
+
 // ---- scoring / options ------------------------------------------------------
 // MemOptType defaults (reference S/datatype/MemOptType.scala:28-75).  The 5x5
 // matrix is never transmitted on either seam, so it is always {a, -b, N=-1}.

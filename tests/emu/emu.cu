@@ -101,32 +101,34 @@ extern "C" int emu_extend_wire(const uint8_t *in, int in_bytes, int16_t *out, in
     return 0;
 }
 
-template <int C>
-static void emu_warp_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, int qn, int tlen, bool rev,
+// one pass of the packed 16-lane systolic array (k_aln_half's schedule restated as loops over lanes)
+template <int P>
+static void emu_half_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, int qn, int tlen, bool rev,
                           int qe, int te, int xtra, int *bsc, int *bte, AlnBook &bk, int &rows_done)
 {
-    AlnLane<C> L[32];
-    for (int l = 0; l < 32; ++l) L[l].setup(o, q, qn, rev, qe, l);
+    AlnLaneP<P> L[ALN_G];
+    for (int l = 0; l < ALN_G; ++l) L[l].setup(o, q, qn, rev, qe, l);
     bk.init(o, xtra);
-    AlnMsg out[32], nout[32];
+    AlnMsgP out[ALN_G], nout[ALN_G];
     memset(out, 0, sizeof out);
-    const int LQ = (qn - 1) / C;
+    const int LQ = (qn - 1) / (2 * P);
     rows_done = 0;
     for (int s = 0; s < tlen + LQ; ++s) {
-        for (int l = 0; l < 32; ++l) {
-            AlnMsg in;
+        for (int l = 0; l < ALN_G; ++l) {
+            AlnMsgP in;
             if (l == 0) {
                 int t0 = s < tlen ? t[aln_tidx(rev, te, s)] : 0;
                 if (t0 > 4) t0 = 4;
-                in.h = 0; in.ft = t0 << 16; in.key = 0;
+                in.h = 0; in.ft = (uint32_t)t0 << 16; in.key2 = 0;
             } else in = out[l - 1];
             nout[l] = out[l];
             const int row = s - l;
             if (row >= 0 && row < tlen && l <= LQ) {
-                L[l].step(o, in, nout[l]);
+                if ((in.ft >> 16) > 3) L[l].template step<true>(o, in, nout[l]);
+                else L[l].template step<false>(o, in, nout[l]);
                 if (l == LQ) {
                     int m, mj;
-                    aln_decode_key(nout[l].key, m, mj);
+                    aln_decode_key2(nout[l].key2, m, mj);
                     bk.row(row, m, mj, bsc, bte);
                     rows_done = row + 1;
                 }
@@ -137,14 +139,14 @@ static void emu_warp_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, in
     }
 }
 
-template <int C>
-static long long emu_align2_warp(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int xtra, AlnRes &r)
+template <int P>
+static long long emu_align2_half(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int xtra, AlnRes &r)
 {
     std::vector<int> b((size_t)2 * (tlen / 2 + 2));
     int *bsc = b.data(), *bte = b.data() + (tlen / 2 + 2);
     AlnBook bk;
     int rows = 0;
-    emu_warp_pass<C>(o, q, t, qlen, tlen, false, 0, 0, xtra, bsc, bte, bk, rows);
+    emu_half_pass<P>(o, q, t, qlen, tlen, false, 0, 0, xtra, bsc, bte, bk, rows);
     aln_finish_head(bk, r);
     aln_second_best_serial(o, bk, bsc, bte, r);
     long long cells = (long long)qlen * rows;
@@ -154,7 +156,7 @@ static long long emu_align2_warp(const SwOpt &o, const uint8_t *q, int qlen, con
         if (qn2 >= 1) {
             AlnBook bk2;
             int rows2 = 0;
-            emu_warp_pass<C>(o, q, t, qn2, tlen, true, r.qe, r.te, XSTOP | r.score, bsc, bte, bk2, rows2);
+            emu_half_pass<P>(o, q, t, qn2, tlen, true, r.qe, r.te, XSTOP | r.score, bsc, bte, bk2, rows2);
             aln_finish_head(bk2, rr);
             cells += (long long)qn2 * rows2;
         } else {
@@ -189,10 +191,10 @@ extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, 
             c = sw_align2_generic(o, q, qn, t, tn, jb.xtra, H, E, bsc, bte, r);
         } else {
             ++nf;
-            if (cls == 1) c = emu_align2_warp<8>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
-            else if (cls == 2) c = emu_align2_warp<5>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
-            else if (cls == 3) c = emu_align2_warp<4>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
-            else c = emu_align2_warp<2>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            if (cls == 1) c = emu_align2_half<8>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else if (cls == 2) c = emu_align2_half<5>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else if (cls == 3) c = emu_align2_half<4>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
+            else c = emu_align2_half<2>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);
         }
         int32_t *o7 = out7 + (size_t)7 * k;
         o7[0] = r.score; o7[1] = r.te; o7[2] = r.qe; o7[3] = r.score2; o7[4] = r.te2; o7[5] = r.tb; o7[6] = r.qb;
