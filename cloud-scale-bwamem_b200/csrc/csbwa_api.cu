@@ -23,6 +23,7 @@
 #include "aln_kernels.cuh"
 #include "glb_kernels.cuh"
 #include "peak_kernels.cuh"
+#include "coords_kernels.cuh"
 #include "coalesce.hpp"
 
 using namespace csw;
@@ -1089,6 +1090,163 @@ extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *rea
     }
     return need;
 }
+// ------------------------------------------------------------------------------------
+// coordinate-only extension tasks against a device-resident reference
+// ------------------------------------------------------------------------------------
+static_assert(sizeof(csbwa_seed_task) == sizeof(SeedTask), "seed task layout");
+struct DevRef { uint8_t *d_pac = nullptr; int64_t l_pac = 0; };
+static DevRef g_ref[64];
+static std::mutex g_ref_mu;
+
+extern "C" int csbwa_ref_release(int device)
+{
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    for (int d = 0; d < 64; ++d) {
+        if (device >= 0 && d != device) continue;
+        if (g_ref[d].d_pac) { cudaSetDevice(d); cudaFree(g_ref[d].d_pac); g_ref[d].d_pac = nullptr; g_ref[d].l_pac = 0; }
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_ref_upload(const uint8_t *pac, int64_t l_pac, int device)
+{
+    if (!pac || l_pac <= 0) return fail(CSBWA_E_BADARG, "null pac or non-positive length");
+    if (!g_inited) {
+        int rc = csbwa_init(0);
+        if (rc < 0) return rc;
+    }
+    if (device >= g_ndev) return fail(CSBWA_E_BADARG, "device index out of range");
+    const size_t bytes = (size_t)((l_pac + 3) / 4);
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    for (int d = 0; d < g_ndev; ++d) {                 // replicated: every GPU in use holds its own copy
+        if (device >= 0 && d != device) continue;
+        CU_TRY(cudaSetDevice(d));
+        if (g_ref[d].d_pac) { cudaFree(g_ref[d].d_pac); g_ref[d].d_pac = nullptr; g_ref[d].l_pac = 0; }
+        if (cudaMalloc((void **)&g_ref[d].d_pac, bytes + 16) != cudaSuccess) return fail(CSBWA_E_NOMEM, "cudaMalloc of the reference failed");
+        CU_TRY(cudaMemcpy(g_ref[d].d_pac, pac, bytes, cudaMemcpyHostToDevice));
+        g_ref[d].l_pac = l_pac;
+    }
+    return CSBWA_OK;
+}
+
+// shared body: expand on the device, optionally copy the expanded wire back (wire_out), optionally run
+static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, const csbwa_seed_task *tasks,
+                      int32_t n_tasks, const int32_t *opt7, int16_t *out, uint8_t *wire_out, int64_t wire_cap,
+                      int64_t *wire_bytes, int device)
+{
+    const double t0 = now_ms();
+    if (n_tasks < 0 || n_reads < 0 || read_len <= 0 || read_len > 32000 || !opt7 || (n_tasks > 0 && (!reads || !tasks)))
+        return fail(CSBWA_E_BADARG, "bad argument");
+    Ctx *c = nullptr;
+    int rc = acquire_ctx(device, &c);
+    if (rc) return rc;
+    CtxGuard guard{c};
+    DevRef ref;
+    {
+        std::lock_guard<std::mutex> lk(g_ref_mu);
+        ref = g_ref[c->dev];
+    }
+    if (!ref.d_pac) return fail(CSBWA_E_BADARG, "no reference uploaded on this device (csbwa_ref_upload)");
+    // host: validate, size the blocks (prefix of the per-task word counts)
+    const size_t tb = (size_t)n_tasks * sizeof(SeedTask), pb = ((size_t)n_tasks + 1) * 4;
+    const size_t off_pos = (tb + 255) & ~(size_t)255, off_reads = (off_pos + pb + 255) & ~(size_t)255;
+    const size_t in_bytes = off_reads + (size_t)n_reads * read_len;
+    if ((rc = grow_pinned(c->h_in, in_bytes + 16))) return rc;
+    uint8_t *h = (uint8_t *)c->h_in.p;
+    int32_t *pos = (int32_t *)(h + off_pos);
+    int64_t words = 8 + 8 * (int64_t)n_tasks;
+    for (int32_t k = 0; k < n_tasks; ++k) {
+        SeedTask t;
+        memcpy(&t, &tasks[k], sizeof t);
+        if (!seed_task_ok(t, n_reads, read_len, ref.l_pac)) return fail(CSBWA_E_BADARG, "a task's coordinates leave the read / reference or bridge the strands");
+        pos[k] = (int32_t)words;
+        words += seed_task_words(t, read_len);
+        if (words > 0x7fffffff / 4) return fail(CSBWA_E_BADARG, "call too large");
+    }
+    pos[n_tasks] = (int32_t)words;
+    const int64_t wire_b = words * 4;
+    if (wire_bytes) *wire_bytes = wire_b;
+    if (wire_out && wire_cap < wire_b) return fail(CSBWA_E_SHORTOUT, "wire buffer too small");
+    if (n_tasks == 0 && !wire_out) return CSBWA_OK;
+    memcpy(h, tasks, tb);
+    memcpy(h + off_reads, reads, (size_t)n_reads * read_len);
+    const size_t out_bytes = (size_t)n_tasks * CSBWA_EXT_RET_SHORTS * 2;
+    const size_t scr = ext_scratch_bytes(n_tasks, wire_b);
+    if ((rc = grow_dev(c->d_in, in_bytes + 16)) || (rc = grow_dev(c->d_aux, (size_t)wire_b + 256)) ||
+        (rc = grow_pinned(c->h_out, out_bytes + (wire_out ? (size_t)wire_b : 0) + 64)) || (rc = grow_dev(c->d_out, out_bytes + 64)) ||
+        (rc = grow_dev(c->d_scratch, scr)))
+        return rc;
+    CoordsOpt co;
+    for (int i = 0; i < 7; ++i) co.v[i] = opt7[i];
+    CU_TRY(cudaEventRecord(c->ev[0], c->st));
+    CU_TRY(cudaMemcpyAsync(c->d_in.p, h, in_bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
+    CU_TRY(cudaMemsetAsync((char *)c->d_scratch.p + offsetof(ExtHdr, err), 0, 4, c->st));
+    CU_TRY(cudaEventRecord(c->ev[1], c->st));
+    const uint8_t *d = (const uint8_t *)c->d_in.p;
+    int grid = (int)((words + 255) / 256);
+    if (grid > g_dev[c->dev].sms * 16) grid = g_dev[c->dev].sms * 16;
+    if (grid < 1) grid = 1;
+    int32_t *d_err = (int32_t *)((char *)c->d_out.p + out_bytes + 16);
+    CU_TRY(cudaMemsetAsync(d_err, 0, 4, c->st));
+    k_coords_expand<<<grid, 256, 0, c->st>>>((const SeedTask *)d, (const int32_t *)(d + off_pos), n_tasks, d + off_reads, n_reads,
+                                             read_len, ref.d_pac, ref.l_pac, co, (uint32_t *)c->d_aux.p, d_err);
+    if (out && n_tasks > 0) {
+        rc = launch_extend((const uint8_t *)c->d_aux.p, single_call((int32_t)wire_b, n_tasks), n_tasks, (int16_t *)c->d_out.p,
+                           c->d_cells, c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev, &c->aux);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaEventRecord(c->ev[2], c->st));
+    uint8_t *ho = (uint8_t *)c->h_out.p;
+    if (out && n_tasks > 0) CU_TRY(cudaMemcpyAsync(ho, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
+    if (wire_out) CU_TRY(cudaMemcpyAsync(ho + out_bytes + 64 - 64 % 16, c->d_aux.p, (size_t)wire_b, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_cells, c->d_cells, 8, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaMemcpyAsync(c->h_err, d_err, 4, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaEventRecord(c->ev[3], c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    if (*c->h_err != 0) return fail(CSBWA_E_BADARG, "a task failed validation on the device");
+    if (out && n_tasks > 0) {
+        int32_t herr = 0;
+        CU_TRY(cudaMemcpy(&herr, (char *)c->d_scratch.p + offsetof(ExtHdr, err), 4, cudaMemcpyDeviceToHost));
+        if (herr == CSBWA_E_SCRATCH) return fail(CSBWA_E_SCRATCH, "generic-row scratch exhausted");
+        if (herr != 0) return fail(CSBWA_E_BADWIRE, "expanded wire failed validation");
+        memcpy(out, ho, out_bytes);
+    }
+    if (wire_out) memcpy(wire_out, ho + out_bytes + 64 - 64 % 16, (size_t)wire_b);
+    float a = 0, b = 0, dd = 0;
+    cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&dd, c->ev[2], c->ev[3]);
+    {
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        if (out && n_tasks > 0) {
+            g_stats.ext_calls++; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)*c->h_cells;
+            g_stats.ext_in_bytes += (int64_t)in_bytes; g_stats.ext_out_bytes += (int64_t)out_bytes;
+            g_stats.kernel_launches += kExtLaunches + 1;
+        }
+        g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += dd;
+        g_stats.host_ms += now_ms() - t0;
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_extend_coords_batch(const uint8_t *reads, int32_t n_reads, int32_t read_len,
+                                         const csbwa_seed_task *tasks, int32_t n_tasks, const int32_t *opt7,
+                                         int16_t *out, int32_t out_shorts, int device)
+{
+    if (!out || out_shorts < CSBWA_EXT_RET_SHORTS * (int64_t)n_tasks) return fail(CSBWA_E_SHORTOUT, "reply array too small");
+    return coords_run(reads, n_reads, read_len, tasks, n_tasks, opt7, out, nullptr, 0, nullptr, device);
+}
+
+extern "C" int64_t csbwa_expand_coords(const uint8_t *reads, int32_t n_reads, int32_t read_len,
+                                       const csbwa_seed_task *tasks, int32_t n_tasks, const int32_t *opt7,
+                                       uint8_t *wire_out, int64_t cap, int device)
+{
+    int64_t nb = 0;
+    int rc = coords_run(reads, n_reads, read_len, tasks, n_tasks, opt7, nullptr, wire_out, cap, &nb, device);
+    return rc < 0 ? rc : nb;
+}
+
 #include "matesw_group.inc"
 
 // ------------------------------------------------------------------------------------

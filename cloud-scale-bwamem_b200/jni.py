@@ -257,3 +257,58 @@ def SWGlobal(query, target, w, cap=512, device=-1):
     res, cig = swGlobalBatch(jobs, seqs, device)
     nc = int(res[0, 1])
     return int(res[0, 0]), [(int(c & 0xf), int(c >> 4)) for c in cig[:max(nc, 0)]]
+
+
+# ---- coordinate-only extension tasks against a device-resident reference ----
+def packPac(ref):
+    """Forward reference (1 base per byte, 0-3) -> bwa .pac bytes: 4 bases per byte, base k at bits
+    ((~k)&3)<<1 (reference S/util/BNTSeqUtil.scala:60: `pac(k>>>2) >>> (((~k)&3)<<1) & 3`)."""
+    ref = np.ascontiguousarray(ref, dtype=np.uint8)
+    n = len(ref)
+    pad = np.zeros(((n + 3) // 4) * 4, dtype=np.uint8)
+    pad[:n] = ref & 3
+    q = pad.reshape(-1, 4)
+    return (q[:, 0] << 6 | q[:, 1] << 4 | q[:, 2] << 2 | q[:, 3]).astype(np.uint8)
+
+
+def refUpload(pac, pacLen, device=-1):
+    pac = np.ascontiguousarray(pac, dtype=np.uint8)
+    _lib.check(_lib.lib().csbwa_ref_upload(pac.ctypes.data, int(pacLen), device))
+
+
+def seedTasks(seed6, idx=None):
+    """int64[n,6] rows {read index, qBeg, len, rBeg, rmax0, rmax1} (what calPreResultsOfSW and the
+    seed hold, S/worker1/MemChainToAlignBatched.scala:348-378) -> csbwa_seed_task records."""
+    s = np.asarray(seed6, dtype=np.int64)
+    t = np.zeros(len(s), dtype=_lib.SEEDTASK_DTYPE)
+    t["r_beg"] = s[:, 3]; t["read_idx"] = s[:, 0]; t["q_beg"] = s[:, 1]; t["seed_len"] = s[:, 2]
+    t["left_ref"] = s[:, 3] - s[:, 4]; t["right_ref"] = s[:, 5] - (s[:, 3] + s[:, 2])
+    t["idx"] = np.arange(len(s)) if idx is None else idx
+    return t
+
+
+def extendCoords(reads, tasks, opt=None, device=-1):
+    """Replies of seam (1) (10 shorts per task) for coordinate-only tasks."""
+    opt = opt or MemOptType()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    tasks = np.ascontiguousarray(tasks, dtype=_lib.SEEDTASK_DTYPE)
+    o7 = opt.opt7()
+    out = np.zeros(10 * len(tasks), dtype=np.int16)
+    _lib.check(_lib.lib().csbwa_extend_coords_batch(reads.ctypes.data, reads.shape[0], reads.shape[1], tasks.ctypes.data,
+                                                    len(tasks), o7.ctypes.data, out.ctypes.data, out.size, device))
+    return out
+
+
+def expandCoords(reads, tasks, opt=None, device=-1):
+    """The wire buffer the device builds from the coordinates (diagnostic / parity tests)."""
+    opt = opt or MemOptType()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    tasks = np.ascontiguousarray(tasks, dtype=_lib.SEEDTASK_DTYPE)
+    o7 = opt.opt7()
+    L = _lib.lib()
+    nb = _lib.check(L.csbwa_expand_coords(reads.ctypes.data, reads.shape[0], reads.shape[1], tasks.ctypes.data, len(tasks),
+                                          o7.ctypes.data, None, 0, device))
+    wire = np.zeros(nb, dtype=np.uint8)
+    _lib.check(L.csbwa_expand_coords(reads.ctypes.data, reads.shape[0], reads.shape[1], tasks.ctypes.data, len(tasks),
+                                     o7.ctypes.data, wire.ctypes.data, wire.size, device))
+    return wire

@@ -218,6 +218,32 @@ int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *reads, int32_t
                                   const int32_t *opt7, uint8_t *out, int64_t cap);
 
 
+/* ---- next row: coordinate-only tasks against a device-resident reference ----
+ * csbwa_ref_upload replicates the 2-bit .pac (S/datatype/BWAIdxType.scala:72-89; 4 bases per byte,
+ * base k at bits ((~k)&3)<<1) on one GPU (device >= 0) or on every GPU in use (device = -1).
+ * A task then carries coordinates only; the device fetches the windows the way bnsGetSeq does
+ * (S/util/BNTSeqUtil.scala:37-83, both strands addressed as [0, 2*l_pac)), reverses the left
+ * segments like the caller (S/worker1/MemChainToAlignBatched.scala:505-541) and builds the very
+ * wire buffer of seam (1) in device memory.  reads: n_reads x read_len, one base per byte (0-4).
+ * Replies: the 10 shorts per task of seam (1).  A task whose window leaves [0, 2*l_pac) or bridges
+ * the strand boundary is refused (CSBWA_E_BADARG), as the reference asserts (:363). */
+typedef struct {
+    int64_t r_beg;                 /* seed start on the doubled reference */
+    int32_t read_idx;
+    int16_t q_beg, seed_len;
+    int16_t left_ref, right_ref;   /* rBeg - rmax0 and rmax1 - (rBeg + len) of the chain window */
+    int32_t idx;                   /* echoed in the reply (shorts 0-1) */
+} csbwa_seed_task;
+int csbwa_ref_upload(const uint8_t *pac, int64_t l_pac, int device);
+int csbwa_ref_release(int device);
+int csbwa_extend_coords_batch(const uint8_t *reads, int32_t n_reads, int32_t read_len,
+                              const csbwa_seed_task *tasks, int32_t n_tasks, const int32_t *opt7,
+                              int16_t *out, int32_t out_shorts, int device);
+/* test/diagnostic: only expand, and return the wire buffer the device built (bytes, or < 0) */
+int64_t csbwa_expand_coords(const uint8_t *reads, int32_t n_reads, int32_t read_len,
+                            const csbwa_seed_task *tasks, int32_t n_tasks, const int32_t *opt7,
+                            uint8_t *wire_out, int64_t cap, int device);
+
 /* ---- next row of the path: SWGlobal (banded global alignment + backtrace -> CIGAR) ---------
  * Reference: S/util/SWUtil.scala:233-397 (port of ksw_global2, N/ksw.c:501-584), called once per
  * emitted alignment by bwaGenCigar2 (S/worker2/MemRegToADAMSAM.scala:738-893), which also chooses

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Coordinate-only seam (device-resident 2-bit reference) next to the wire seam, same tasks.
+
+For every seam call of `--reads-per-call` reads both seams are driven through their host C ABI
+(host buffers, H2D / kernels / D2H inside the timed region, `--threads` caller threads) and must
+return identical replies.  Prints one JSON line: host bytes per task, wall time and GCUPS of both.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=262144)
+    ap.add_argument("--reads-per-call", type=int, default=32768)
+    ap.add_argument("--threads", type=int, default=8)
+    ap.add_argument("--ref-bp", type=int, default=20_000_000)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    pkg = importlib.import_module("cloud-scale-bwamem_b200")
+    W, J = pkg.workload, pkg.jni
+    L = pkg.lib()
+    assert L.csbwa_init(1) >= 1
+    os.environ["CSBWA_COALESCE"] = os.environ.get("CSBWA_COALESCE", "1")
+    opt = J.MemOptType()
+    rng = np.random.default_rng(20260110)
+    ref = W.make_reference(args.ref_bp, 77)
+    J.refUpload(J.packPac(ref), len(ref), device=0)
+    calls = []          # (wire, reads of the call, tasks)
+    done = 0
+    while done < args.pairs:
+        m = min(65536, args.pairs - done)
+        rb = W.ReadBatch(ref, m, 151, 0.01, 400, 50, rng)
+        valid, seed6 = W.longest_seeds(rb, opt)
+        s6 = seed6[valid].copy()
+        s6[:, 4] = np.clip(s6[:, 4], 0, len(ref)); s6[:, 5] = np.clip(s6[:, 5], 0, len(ref))
+        cid = s6[:, 0] // args.reads_per_call
+        for c in np.unique(cid):
+            part = np.ascontiguousarray(s6[cid == c])
+            wire = W.pack_ext_calls(ref, rb, part, args.reads_per_call, opt)[0]
+            r0 = int(c) * args.reads_per_call
+            reads = np.ascontiguousarray(rb.reads[r0:r0 + args.reads_per_call])
+            loc = part.copy(); loc[:, 0] -= r0
+            calls.append((wire, reads, J.seedTasks(loc)))
+        done += m
+    n_tasks = sum(len(t) for _, _, t in calls)
+
+    def run_wire(c):
+        w = c[0]
+        return J.SWExtendFPGAJNI(0).swExtendFPGAJNI(10 * len(c[2]), w)
+
+    def run_coords(c):
+        return J.extendCoords(c[1], c[2], opt, device=0)
+
+    out = {}
+    with ThreadPoolExecutor(args.threads) as ex:
+        a = list(ex.map(run_wire, calls)); b = list(ex.map(run_coords, calls))      # warm-up + parity
+        same = all(np.array_equal(x, y) for x, y in zip(a, b))
+        for name, fn in (("wire", run_wire), ("coords", run_coords)):
+            c0 = pkg.stats()["ext_cells"]
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                list(ex.map(fn, calls))
+            dt = (time.perf_counter() - t0) / args.steps
+            cells = (pkg.stats()["ext_cells"] - c0) / args.steps
+            out[name] = {"ms_per_step": 1e3 * dt, "gcups": cells / dt / 1e9}
+    out["wire"]["host_bytes_per_task"] = sum(c[0].size for c in calls) / n_tasks
+    out["coords"]["host_bytes_per_task"] = sum(c[1].size + c[2].nbytes for c in calls) / n_tasks
+    print(json.dumps({"workload": "C2 tasks, %d pairs, %d reads per call, %d caller threads" % (args.pairs, args.reads_per_call, args.threads),
+                      "tasks": n_tasks, "replies_identical": bool(same), **out}))
+
+
+if __name__ == "__main__":
+    main()
