@@ -295,7 +295,12 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     extern __shared__ uint4 smem4[];
     constexpr bool FAST = CORE >= 0;
     { int n_unused = 0; ext_resolve(cs, n_unused); }
-    const SwOpt &o = hdr->opt;
+    // block-shared copy of the options: the per-row score-table lookups (o.tlo[t], o.thi[t]) become
+    // shared-memory loads instead of dependent global loads at the head of every row
+    __shared__ SwOpt s_opt;
+    if (threadIdx.x == 0) s_opt = hdr->opt;
+    __syncthreads();
+    const SwOpt &o = s_opt;
     const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;

@@ -170,12 +170,10 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
         hm1 = h1i;
         const int jfin = beg < end ? end : beg;
         if (jfin == qlen && gscore <= hlast) { best_ie = i; gscore = hlast; }
-        // row max: larger h, then larger column (last j on ties)
-        const int klo = (int)(key2 & 0xffffu), khi = (int)(key2 >> 16);
-        const int hlo = klo >> 7, hhi = khi >> 7;
-        const int jlo = 2 * (klo & 127), jhi = 2 * (khi & 127) + 1;
-        int rm, rmj;
-        if (hhi > hlo || (hhi == hlo && jhi > jlo)) { rm = hhi; rmj = jhi; } else { rm = hlo; rmj = jlo; }
+        // row max: larger h, then larger column (last j on ties).  Lane keys are h << 7 | pair:
+        // doubling them (+1 for the odd lane) turns them into h << 8 | column, one max merges them.
+        const int kk = imax((int)((key2 & 0xffffu) << 1), (int)((key2 >> 16) << 1) | 1);
+        const int rm = kk >> 8, rmj = kk & 255;
         if (rm == 0) break;
         if (rm > best) {
             best = rm; best_i = i; best_j = rmj;
@@ -189,10 +187,8 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
             }
         }
         // band shrink (:201-214) in own-column terms: eh[j].h == (j == beg ? h1i : Hs[j-1])
-        const int zlo = (int)(zk2 & 0xffffu), zhi = (int)(zk2 >> 16);
-        int clast = -1;                                            // last column of the band with H == 0
-        if ((zlo >> 7) == 511) clast = 2 * (zlo & 127);
-        if ((zhi >> 7) == 511) clast = imax(clast, 2 * (zhi & 127) + 1);
+        const int zz = imax((int)((zk2 & 0xffffu) << 1), (int)((zk2 >> 16) << 1) | 1);     // (511 - h) << 8 | column
+        const int clast = (zz >> 8) == 511 ? (zz & 255) : -1;         // last column of the band with H == 0
         int nbeg, nend;
         if (clast > rmj) {                                         // a zero right of the max: rescan
             int j = rmj;
