@@ -1257,6 +1257,8 @@ static_assert(sizeof(csbwa_gjob) == sizeof(GlbJob), "gjob layout");
 static const int kGlbLaunches = 2;
 extern "C" int csbwa_global_launches_per_call(void) { return kGlbLaunches; }
 
+extern "C" int64_t csbwa_global_z_cells(int32_t q_len, int32_t t_len, int32_t w) { return (int64_t)glb_z_cells(q_len, t_len, w); }
+
 static const int kGlbBlock = 64;         // threads per block of k_glb
 static int glb_grid_warps(int n, int sms)
 {
@@ -1264,12 +1266,11 @@ static int glb_grid_warps(int n, int sms)
     const int cap = sms * 8;             // persistent: up to 4 blocks of 2 warps per SM
     return warps < cap ? warps : cap;
 }
-// shared-memory columns for the H/E rows: the whole query if it fits 2 blocks per SM
-static int glb_smem_cols(int max_q_len)
+// shared-memory column pairs of the p2 core ({H2,E2} + selector = 10 bytes per pair per thread)
+static int glb_smem_pairs(int max_q_len)
 {
-    const int fit = (100 * 1024) / (kGlbBlock * (int)sizeof(GlbInt2));     // 200 columns at 64 threads
-    const int want = max_q_len + 1;
-    return want <= fit ? want : fit;
+    const int q = max_q_len < 254 ? max_q_len : 254;
+    return glb_p2_pairs(q > 1 ? q : 1);
 }
 
 extern "C" int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t max_z_cells)
@@ -1303,8 +1304,8 @@ extern "C" int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, con
     if ((int64_t)need > scratch_bytes) return fail(CSBWA_E_SCRATCH, "global-alignment scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     GlbHdr *hdr = (GlbHdr *)d_scratch;
-    const int smem_cols = glb_smem_cols(max_q_len);
-    const size_t smem = (size_t)smem_cols * kGlbBlock * sizeof(GlbInt2);
+    const int smem_cols = glb_smem_pairs(max_q_len);
+    const size_t smem = (size_t)smem_cols * kGlbBlock * 10;
     k_glb_setup<<<1, 32, 0, st>>>(hdr);
     k_glb<<<blocks, kGlbBlock, smem, st>>>((const GlbJob *)d_jobs, n_jobs, (const uint8_t *)d_seqs, hdr, (char *)d_scratch + 256,
                                            (long long)max_q_len + 1, max_z_cells, smem_cols, (int32_t *)d_res,

@@ -52,18 +52,6 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 #endif
 }
 
-// 16-bit load zero-extended into a 32-bit register (LDS.U16 without a masking LOP3)
-CSW_HD uint32_t ld_u16(const uint16_t *p)
-{
-#if defined(__CUDA_ARCH__)
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    return v;
-#else
-    return *p;
-#endif
-}
-
 CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, int qlen,
                          const uint32_t *words, int t_nib, int tlen,
                          int w, int end_bonus, int h0, SwExtRes &res)

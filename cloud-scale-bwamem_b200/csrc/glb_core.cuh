@@ -119,10 +119,12 @@ CSW_HD int sw_global_thread(const SwOpt &o, const uint8_t *q, int qlen, const ui
 
 // per-job storage need, in units of one lane
 CSW_HD long long glb_he_cols(int qlen) { return (long long)(qlen > 0 ? qlen : 0) + 1; }
+// direction-matrix bytes of one job: covers both layouts (1 byte per band cell here, 2 bytes per
+// column pair of the row's band in glb_p2.cuh: 2 * (n_col / 2 + 2) <= n_col + 4)
 CSW_HD long long glb_z_cells(int qlen, int tlen, int w)
 {
     const long long n_col = qlen < 2 * w + 1 ? qlen : 2 * (long long)w + 1;
-    return (n_col > 0 ? n_col : 0) * (long long)(tlen > 0 ? tlen : 0);
+    return ((n_col > 0 ? n_col : 0) + 4) * (long long)(tlen > 0 ? tlen : 0);
 }
 
 } // namespace csw

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "glb_core.cuh"
+#include "glb_p2.cuh"
 
 namespace csw {
 
@@ -30,22 +31,27 @@ __global__ void k_glb_setup(GlbHdr *hdr)
     }
 }
 
-// smem_cols > 0: H/E rows of jobs with q_len + 1 <= smem_cols live in shared memory
-// (column j of thread t at smem[j * blockDim + t], 8-byte elements: conflict free for any band
-// position); longer jobs fall back to the warp's global slice.
-__global__ void __launch_bounds__(128)
+// smem_pairs: column pairs of the p2 core's shared-memory rows ({H2,E2} records first, then the
+// selectors; pair p of thread t at [p * blockDim + t]: conflict free for any band position).
+// Jobs the p2 core is eligible for (glb_p2.cuh) and that fit use it; the rest run the scalar int32
+// core on the warp's global slice.
+__global__ void __launch_bounds__(64)
 k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, GlbHdr *hdr, char *slices,
-      long long max_he_cols, long long max_z_cells, int smem_cols, int32_t *__restrict__ res2,
+      long long max_he_cols, long long max_z_cells, int smem_pairs, int32_t *__restrict__ res2,
       uint32_t *__restrict__ cigars, unsigned long long *cells_acc)
 {
-    extern __shared__ GlbInt2 glb_smem[];
-    const SwOpt &o = hdr->opt;
+    extern __shared__ uint4 glb_smem4[];
+    __shared__ SwOpt s_opt;
+    if (threadIdx.x == 0) s_opt = hdr->opt;
+    __syncthreads();
+    const SwOpt &o = s_opt;
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     char *slice = slices + (size_t)warp_id * glb_warp_bytes(max_he_cols, max_z_cells);
     GlbInt2 *he_g = (GlbInt2 *)slice + lane;
-    GlbInt2 *he_s = glb_smem + threadIdx.x;
-    uint8_t *z = (uint8_t *)(slice + (size_t)max_he_cols * 32 * sizeof(GlbInt2)) + lane;
+    GP2Pair *he_s = (GP2Pair *)glb_smem4 + threadIdx.x;
+    uint16_t *sel_s = (uint16_t *)((GP2Pair *)glb_smem4 + (size_t)smem_pairs * blockDim.x) + threadIdx.x;
+    char *zbase = slice + (size_t)max_he_cols * 32 * sizeof(GlbInt2);
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t chunk = 0;
@@ -62,10 +68,12 @@ k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, 
                 glb_z_cells(jb.q_len, jb.t_len, jb.w) > max_z_cells) {
                 atomicExch(&hdr->err, -7);
                 nc = -3;
+            } else if (glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w) && glb_p2_pairs(jb.q_len) <= smem_pairs) {
+                score = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he_s, sel_s,
+                                     (int)blockDim.x, (uint16_t *)zbase + lane, 32, cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
             } else {
-                const bool in_smem = glb_he_cols(jb.q_len) <= smem_cols;
                 score = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w,
-                                         in_smem ? he_s : he_g, in_smem ? (int)blockDim.x : 32, z, 32,
+                                         he_g, 32, (uint8_t *)zbase + lane, 32,
                                          cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
             }
             res2[2 * (size_t)k] = score;

@@ -140,6 +140,18 @@ CSW_HD uint32_t umad(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// 16-bit load zero-extended into a 32-bit register (LDS.U16 without a masking LOP3)
+CSW_HD uint32_t ld_u16(const uint16_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 // (hi:lo) >> 16: the diagonal of a column pair from the previous and the current H2 word -> SHF.R.W
 CSW_HD uint32_t funnel16(uint32_t lo, uint32_t hi)      // (hi:lo) >> 16
 {

@@ -262,7 +262,9 @@ typedef struct {
 typedef struct { int32_t score, n_cigar; } csbwa_gres;
 int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes,
                        csbwa_gres *res, uint32_t *cigars, int64_t cigar_words, int device);
-/* device-resident: max_q_len = max q_len, max_z_cells = max over jobs of min(q_len, 2w+1) * t_len */
+/* device-resident: max_q_len = max q_len, max_z_cells = max over jobs of csbwa_global_z_cells()
+ * (direction-matrix bytes of one job: (min(q_len, 2w+1) + 4) * t_len) */
+int64_t csbwa_global_z_cells(int32_t q_len, int32_t t_len, int32_t w);
 int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t max_z_cells);
 int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
                               int64_t max_z_cells, void *d_res, void *d_cigars, void *d_cells,

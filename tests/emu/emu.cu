@@ -270,21 +270,34 @@ extern "C" void emu_co_destroy(void *h)
 // SWGlobal core on the CPU (same function the k_glb kernel calls, stride 1)
 // ---------------------------------------------------------------------------------------------
 #include "../../cloud-scale-bwamem_b200/csrc/glb_kernels.cuh"
-extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, int32_t *res2, uint32_t *cigars, int64_t *cells)
+extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, int32_t *res2, uint32_t *cigars, int64_t *cells,
+                                int force_scalar, int32_t *n_p2)
 {
+    int np2 = 0;
     SwOpt o;
     fill_default_opt(o);
     finish_opt(o);
     for (int k = 0; k < n; ++k) {
         const GlbJob &jb = jobs[k];
         std::vector<GlbInt2> he((size_t)glb_he_cols(jb.q_len) + 1);
-        std::vector<uint8_t> z((size_t)glb_z_cells(jb.q_len, jb.t_len, jb.w) + 1);
+        std::vector<uint8_t> z((size_t)glb_z_cells(jb.q_len, jb.t_len, jb.w) * 3 + 16, 0xa5);
         int nc = 0;
         long long c = 0;
-        int sc = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he.data(), 1, z.data(), 1,
+        int sc;
+        if (!force_scalar && glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w)) {
+            const int stride = 3, np = glb_p2_pairs(jb.q_len);
+            std::vector<GP2Pair> hp((size_t)(np + 1) * stride);
+            for (auto &x : hp) { x.h2 = 0xdeadbeefu; x.e2 = 0xdeadbeefu; }
+            std::vector<uint16_t> sl((size_t)(np + 1) * stride, 0xdead);
+            sc = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, hp.data() + 1, sl.data() + 2, stride,
+                              (uint16_t *)z.data() + 1, 3, cigars + jb.cigar_off, jb.cigar_cap, nc, c);
+            ++np2;
+        } else
+        sc = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he.data(), 1, z.data(), 1,
                                   cigars + jb.cigar_off, jb.cigar_cap, nc, c);
         res2[2 * k] = sc; res2[2 * k + 1] = nc;
         if (cells) cells[k] = c;
     }
+    if (n_p2) *n_p2 = np2;
     return 0;
 }

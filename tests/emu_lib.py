@@ -118,7 +118,7 @@ GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t
                        ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
 
 
-def emu_global_batch(emu, jobs, seqs):
+def emu_global_batch(emu, jobs, seqs, force_scalar=False, want_count=False):
     jobs = np.ascontiguousarray(jobs, dtype=GJOB_DTYPE)
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     n = len(jobs)
@@ -126,7 +126,11 @@ def emu_global_batch(emu, jobs, seqs):
     res = np.zeros((n, 2), dtype=np.int32)
     cig = np.zeros(max(1, total), dtype=np.uint32)
     cells = np.zeros(n, dtype=np.int64)
-    emu.lib.emu_global_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    rc = emu.lib.emu_global_batch(jobs.ctypes.data, n, seqs.ctypes.data, res.ctypes.data, cig.ctypes.data, cells.ctypes.data)
+    emu.lib.emu_global_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    np2 = C.c_int32(0)
+    rc = emu.lib.emu_global_batch(jobs.ctypes.data, n, seqs.ctypes.data, res.ctypes.data, cig.ctypes.data, cells.ctypes.data,
+                                  int(force_scalar), C.addressof(np2))
     assert rc == 0
+    if want_count:
+        return res, cig, cells, np2.value
     return res, cig, cells

@@ -56,10 +56,27 @@ def test_emu_vs_oracle(pkg, oracle, emu):
     rng = np.random.default_rng(92)
     triples = [rand_global_job(rng, pkg) for _ in range(300)]
     triples += [(np.zeros(1, np.uint8), np.zeros(1, np.uint8), 3), (rng.integers(0, 4, 50).astype(np.uint8), rng.integers(0, 4, 2).astype(np.uint8), 51)]
+    r = lambda n: rng.integers(0, 4, n).astype(np.uint8)
+    # band 0, a query of 254 columns (largest the p2 core takes) and 255 (scalar core), band wider than the query
+    triples += [(r(30), r(30), 0), (r(254), r(260), 30), (r(255), r(250), 30), (r(151), r(151), 200)]
     jobs, seqs = build_gjobs(triples, oracle.GJOB_DTYPE)
     ref, rcig, rcells = oracle.global_batch(jobs, seqs)
-    got, gcig, gcells = emu_lib.emu_global_batch(emu, jobs, seqs)
+    got, gcig, gcells, np2 = emu_lib.emu_global_batch(emu, jobs, seqs, want_count=True)     # p2 core where eligible
+    bad = np.flatnonzero((got != ref).any(axis=1))
+    assert len(bad) == 0, (bad[:5], got[bad[:3]], ref[bad[:3]], [(len(triples[b][0]), len(triples[b][1]), triples[b][2]) for b in bad[:3]])
+    assert np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
+    assert np2 >= 250
+    got, gcig, gcells = emu_lib.emu_global_batch(emu, jobs, seqs, force_scalar=True)          # scalar int32 core
     assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
+    # outside the caller's contract (bwaGenCigar2 always passes w >= |tlen - qlen|): the last cell lies outside
+    # the band, some rows have an empty band.  The reference then backtracks through never-written direction
+    # bytes; both product cores agree with each other and report it (n_cigar = -2), with the reference's score.
+    deg = [(r(20), r(60), 5), (r(60), r(20), 5), (r(10), r(100), 2)]
+    dj, ds = build_gjobs(deg, oracle.GJOB_DTYPE)
+    a = emu_lib.emu_global_batch(emu, dj, ds)
+    b = emu_lib.emu_global_batch(emu, dj, ds, force_scalar=True)
+    assert np.array_equal(a[0], b[0]) and (a[0][:, 1] == -2).sum() >= 2
+    assert np.array_equal(a[0][:, 0], oracle.global_batch(dj, ds)[0][:, 0])
     small, _ = build_gjobs(triples[:50], oracle.GJOB_DTYPE, cap=2)   # CIGAR does not fit -> n_cigar = -1 on both
     r2, _, _ = oracle.global_batch(small, seqs)
     g2, _, _ = emu_lib.emu_global_batch(emu, small, seqs)

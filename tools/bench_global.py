@@ -48,7 +48,9 @@ def main():
     seqs = np.concatenate([rb.reads.reshape(-1), ref[idx]])
     max_q = args.L
     ncol = np.minimum(jobs["q_len"], 2 * jobs["w"] + 1).astype(np.int64)
-    max_z = int((ncol * jobs["t_len"]).max())
+    max_z = int(((ncol + 4) * jobs["t_len"]).max())            # == max csbwa_global_z_cells(q_len, t_len, w)
+    kmax = int(np.argmax((ncol + 4) * jobs["t_len"]))
+    assert max_z == L.csbwa_global_z_cells(int(jobs["q_len"][kmax]), int(jobs["t_len"][kmax]), int(jobs["w"][kmax]))
     d_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(dev)
     d_seqs = torch.from_numpy(seqs).to(dev)
     d_res = torch.zeros(2 * n, dtype=torch.int32, device=dev)
@@ -75,6 +77,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     cells = int(d_cells.item())
+    assert int((d_res.cpu().numpy().reshape(-1, 2)[:, 1] < 0).sum()) == 0      # every job produced a CIGAR
+    pkg.jni.swGlobalBatch(jobs, seqs, device=0)                                 # first call sizes the context's buffers
     t0 = time.perf_counter()
     res, cig = pkg.jni.swGlobalBatch(jobs, seqs, device=0)
     host_s = time.perf_counter() - t0
