@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--reads-per-call", type=int, default=4096, help="experiments only; the headline is 4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matesw", action="store_true", help="skip the short mate-SW (C3 shape) leg reported under 'matesw'")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs under ncu only)")
     ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 1 column pairs (s16x2), 0 one column per step (u8); -1 library default")
     args = ap.parse_args()
@@ -456,6 +457,15 @@ def main():
             },
             "int_peaks_ginstr_per_s": peaks,
         }
+        if world == 1 and not args.no_matesw:
+            # the other half of the north-star path (pair-end mate rescue, SWAlign2), C3 window shape, short run
+            try:
+                from tools import bench_matesw
+                m = bench_matesw.run_config(pkg, "C3", 8192, pairs_per_call=4096, steps=3, cpu_sample_jobs=256, peaks=peaks, device=local)
+                line["matesw"] = {k: m[k] for k in ("workload", "jobs", "kernel_gcups", "roofline_frac_alu", "host_abi_gcups",
+                                                    "cpu_oracle_gcups", "parity_sample_ok")}
+            except Exception as e:       # never lose the headline line over the extra leg
+                line["matesw"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
