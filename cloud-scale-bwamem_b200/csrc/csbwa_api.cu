@@ -88,8 +88,9 @@ static int ensure_dev_attrs(int dev)
     const int big = 128 * 1024;
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    const int big_p2 = 128 * EXT_BD * 10;            // the 256-column class: 128 pairs x 10 bytes per thread
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
     CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     d.attrs_set = true;
     return CSBWA_OK;
@@ -198,7 +199,7 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
         } else if (core == EXT_CORE_P2) {
             // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
             const int npairs = cap / 2;
-            const int bd = cls == 1 ? 64 : EXT_BD;
+            const int bd = EXT_BD;                          // the core is compiled for this stride
             const size_t smem = (size_t)npairs * bd * 10;
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 96);

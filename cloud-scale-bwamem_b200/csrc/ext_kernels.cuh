@@ -265,6 +265,7 @@ CSW_HD void ext_run_side(const SwOpt &o, const uint32_t *words, int q_nib, int q
 }
 
 // One SWExtend side with band retries on the column-pair core (ext_p2.cuh)
+template <int STRIDE>
 CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, int qlen, int t_nib, int tlen,
                             int end_bonus, int h0, int prev, P2Pair *he, uint16_t *sel, int stride, SideRes &out)
 {
@@ -273,7 +274,7 @@ CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, in
     p2_stage_query(sel, stride, words, q_nib, qlen);
     for (int i = 0; i < CSW_MAX_BAND_TRY; ++i) {
         aw = o.w << i;
-        sw_extend_p2(o, he, sel, stride, qlen, words, t_nib, tlen, aw, end_bonus, h0, r);
+        sw_extend_p2<STRIDE>(o, he, sel, stride, qlen, words, t_nib, tlen, aw, end_bonus, h0, r);
         cells += r.cells;
         if (r.score == prev || r.max_off < (aw >> 1) + (aw >> 2)) break;
         prev = r.score;
@@ -305,8 +306,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;
     uint32_t *col = (uint32_t *)smem4 + threadIdx.x;            // U8: column j at col[j * stride]
-    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // P2: pair p at he[p * stride]
-    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * stride) + threadIdx.x;
+    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // P2: pair p at he[p * EXT_BD] (blocks of EXT_BD threads)
+    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * EXT_BD) + threadIdx.x;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t chunk = 0;
@@ -340,8 +341,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
             if (SIDE == 0) {
                 if (t.lq > 0) {      // (0 only after a validation / scratch failure, already reported)
                     if (CORE == EXT_CORE_P2)
-                        ext_run_side_p2(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
-                                        he, sel, stride, L);
+                        ext_run_side_p2<EXT_BD>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
+                                                he, sel, EXT_BD, L);
                     else
                         ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
                                            t.reg_score, col, stride, H, E, L);
@@ -353,8 +354,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
                 if (t.rq > 0) {
                     const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
                     if (CORE == EXT_CORE_P2)
-                        ext_run_side_p2(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
-                                        he, sel, stride, R);
+                        ext_run_side_p2<EXT_BD>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
+                                                he, sel, EXT_BD, R);
                     else
                         ext_run_side<FAST>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0,
                                            sc0, col, stride, H, E, R);

@@ -13,8 +13,9 @@
 //     the insertion chain F(j+1) = max(F(j) - eIns, g(j)) is sequential (exact: SURVEY.md App. C),
 //     two 32-bit VIADDMNMX per pair; H = max(H', F) and the E update are packed again.
 //   * the row max / arg-max is a packed unsigned key h<<7 | p per lane (last p on ties; the two
-//     lanes are merged at the end of the row), the "last zero of the row" a second packed key
-//     (511-h)<<7 | p, so the band shrink needs a rescan only when a zero lies right of the max.
+//     lanes are merged at the end of the row), the "last zero of the row" the packed MINIMUM of the
+//     same key with its pair bits inverted (smallest h, then last p), so the band shrink needs a
+//     rescan only when a zero lies right of the max.
 // Per column pair: 2 PRMT/SHF + 11 DPX/ALU + 5 FMA-pipe instructions, i.e. ~8 ALU-pipe slots per
 // cell against ~16 of the one-column core.  Scores are bounded by 511 (h0 + qlen*max(mat)), so the
 // 250 bp configs stay on the fast path.  Band edges that split a pair are handled by a scalar
@@ -52,10 +53,14 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 #endif
 }
 
-CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, int qlen,
+// STRIDE: compile-time element stride between consecutive pairs (threads per block on the device, so
+// the unrolled pair loop addresses shared memory with immediate offsets); 0 = use stride_rt
+template <int STRIDE>
+CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_rt, int qlen,
                          const uint32_t *words, int t_nib, int tlen,
                          int w, int end_bonus, int h0, SwExtRes &res)
 {
+    const int stride = STRIDE ? STRIDE : stride_rt;
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
     const int e_del = o.e_del, e_ins = o.e_ins, zdrop = o.zdrop;
     const int ne_ins = -e_ins;
@@ -88,7 +93,7 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
         const int h1i = imax(h0 - (o.o_del + e_del * (i + 1)), 0);
         beg = imax(beg, i - w);
         end = min3(end, i + w + 1, qlen);
-        uint32_t key2 = 0, zk2 = 0;
+        uint32_t key2 = 0, zk2 = 0xffffffffu;          // zk2: packed MIN of (h << 7 | pair) ^ 127: smallest h, then last pair
         int hlast = h1i;
         if (beg < end) {
             int dg = beg == 0 ? hm1 : (int)P2_H(beg - 1);          // H(i-1, beg-1)
@@ -107,7 +112,7 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
                 P2_E(c) = (uint16_t)imax(e - e_del, imax(h - oe_del, 0));                         \
                 f = imax(f - e_ins, imax(h - oe_ins, 0));                                         \
                 key2 = umax2(key2, (uint32_t)(h * 128 + p) << (16 * lane));                       \
-                zk2 = umax2(zk2, (uint32_t)((511 - h) * 128 + p) << (16 * lane));                 \
+                zk2 = umin2(zk2, ((uint32_t)((h * 128 + p) ^ 127) << (16 * lane)) | (0xffff0000u >> (16 * lane))); \
                 dg = hold; hlast = h; ++c;                                                        \
             }
             if (c & 1) P2_COLUMN()
@@ -115,7 +120,6 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
             if (p < pe) {
                 uint32_t hprev2 = (uint32_t)dg << 16;
                 uint32_t pp2 = (uint32_t)p * 0x00010001u;
-                uint32_t zb2 = pp2 + 511u * 128u * 0x00010001u;
                 P2Pair *ph = he + (size_t)p * stride;
                 const uint16_t *ps = sel + (size_t)p * stride;
                 uint32_t h2 = 0;
@@ -140,10 +144,11 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
                     y.h2 = h2;
                     y.e2 = addmax2(x.e2, ne_del2, addmax2_relu(h2, noe_del2, noe_del2));
                     *ph = y;
-                    key2 = umax2(key2, umad(h2, 128u, pp2));
-                    zk2 = umax2(zk2, umad(h2, 0xffffff80u, zb2));
+                    const uint32_t kp2 = umad(h2, 128u, pp2);                  // h << 7 | pair, both lanes
+                    key2 = umax2(key2, kp2);
+                    zk2 = umin2(zk2, kp2 ^ 0x007f007fu);
                     f = fn;
-                    pp2 += 0x00010001u; zb2 += 0x00010001u;
+                    pp2 += 0x00010001u;
                     ph += stride; ps += stride;
                 }
                 dg = (int)(hprev2 >> 16);
@@ -175,8 +180,9 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride, 
             }
         }
         // band shrink (:201-214) in own-column terms: eh[j].h == (j == beg ? h1i : Hs[j-1])
-        const int zz = imax((int)((zk2 & 0xffffu) << 1), (int)((zk2 >> 16) << 1) | 1);     // (511 - h) << 8 | column
-        const int clast = (zz >> 8) == 511 ? (zz & 255) : -1;         // last column of the band with H == 0
+        // last column of the band with H == 0: a lane holds a zero iff its key is < 128, the pair is 127 - key
+        const int zlo = (int)(zk2 & 0xffffu), zhi = (int)(zk2 >> 16);
+        const int clast = imax(zlo < 128 ? 2 * (127 - zlo) : -1, zhi < 128 ? 2 * (127 - zhi) + 1 : -1);
         int nbeg, nend;
         if (clast > rmj) {                                         // a zero right of the max: rescan
             int j = rmj;

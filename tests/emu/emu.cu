@@ -38,13 +38,13 @@ extern "C" int emu_extend_wire_p2(const uint8_t *in, int in_bytes, int16_t *out,
         L.aw = R.aw = (int16_t)o.w;
         int64_t cells = 0;
         if (t.lq > 0) {
-            if (p2_eligible(o, t.lq, t.h0)) { ext_run_side_p2(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, he.data() + 1, sel.data() + 2, stride, L); ++nfast; }
+            if (p2_eligible(o, t.lq, t.h0)) { ext_run_side_p2<0>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, he.data() + 1, sel.data() + 2, stride, L); ++nfast; }
             else ext_run_side<false>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, nullptr, 1, H, E, L);
             cells += L.cells;
         }
         if (t.rq > 0) {
             const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
-            if (p2_eligible(o, t.rq, sc0)) { ext_run_side_p2(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, he.data() + 1, sel.data() + 2, stride, R); ++nfast; }
+            if (p2_eligible(o, t.rq, sc0)) { ext_run_side_p2<0>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, he.data() + 1, sel.data() + 2, stride, R); ++nfast; }
             else ext_run_side<false>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, nullptr, 1, H, E, R);
             cells += R.cells;
         }
