@@ -33,9 +33,16 @@ import numpy as np
 # more hardware queues than the default 8: the seam's submission streams and their per-class aux
 # streams are independent (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# rank 0 prints ONE JSON line: keep NCCL's version banner off stdout
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints ONE JSON line on stdout: everything else that writes to file descriptor 1 (NCCL's
+# version banner, library chatter) is sent to stderr, and the result line goes to the saved descriptor
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -175,7 +182,7 @@ def run_reference_arm(args, pkg):
         "read_pairs_per_s": (n_calls * READS_PER_CALL / 2) / (t_total / args.steps),
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_block(args, n_pairs):
@@ -490,7 +497,7 @@ def main():
             line["cpu_baseline"] = {"value": ccells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
                                     "sample": "first %d seam calls (%d tasks) of the same workload x %d passes, %.1f s" %
                                               (n_calls, sum(ntasks[:n_calls]), passes, dt)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
