@@ -21,6 +21,8 @@ GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t
                        ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
 SEEDTASK_DTYPE = np.dtype([("r_beg", "<i8"), ("read_idx", "<i4"), ("q_beg", "<i2"), ("seed_len", "<i2"),
                            ("left_ref", "<i2"), ("right_ref", "<i2"), ("idx", "<i4")])
+SEED_DTYPE = np.dtype([("r_beg", "<i8"), ("q_beg", "<i4"), ("len", "<i4")])
+CHAIN_DTYPE = np.dtype([("seed_off", "<i4"), ("n_seeds", "<i4")])
 CALL_DTYPE = np.dtype([("in_off", "<i8"), ("in_bytes", "<i4"), ("n_tasks", "<i4"), ("out_off", "<i8"),
                        ("task_base", "<i4"), ("pad", "<i4")])
 
@@ -30,7 +32,7 @@ EXPORTS = [
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
-    "csbwa_global_batch_device", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords",
+    "csbwa_global_batch_device", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat",
 ]
 
 
@@ -97,6 +99,8 @@ def lib():
     L.csbwa_extend_coords_batch.argtypes = [vp, i32, i32, vp, i32, vp, vp, i32, C.c_int]
     L.csbwa_extend_coords_batch.restype = C.c_int
     L.csbwa_expand_coords.argtypes = [vp, i32, i32, vp, i32, vp, vp, i64, C.c_int]; L.csbwa_expand_coords.restype = i64
+    L.csbwa_chain2aln_flat.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, C.c_int]
+    L.csbwa_chain2aln_flat.restype = C.c_int
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -1248,6 +1249,7 @@ extern "C" int64_t csbwa_expand_coords(const uint8_t *reads, int32_t n_reads, in
     return rc < 0 ? rc : nb;
 }
 
+#include "chain2aln.inc"
 #include "matesw_group.inc"
 
 // ------------------------------------------------------------------------------------

@@ -312,3 +312,23 @@ def expandCoords(reads, tasks, opt=None, device=-1):
     _lib.check(L.csbwa_expand_coords(reads.ctypes.data, reads.shape[0], reads.shape[1], tasks.ctypes.data, len(tasks),
                                      o7.ctypes.data, wire.ctypes.data, wire.size, device))
     return wire
+
+
+def memChainToAlnBatched(reads, read_chain_off, chains, seeds, opt=None, device=-1, cap=None):
+    """Round-flattened mirror of memChainToAlnBatched (S/worker1/MemChainToAlignBatched.scala:380-615)
+    against the resident reference: returns (regs ALNREG_DTYPE[], out_off int32[n+1], n_spec, n_used)."""
+    import ctypes as C
+    opt = opt or MemOptType()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    read_chain_off = np.ascontiguousarray(read_chain_off, dtype=np.int32)
+    chains = np.ascontiguousarray(chains, dtype=_lib.CHAIN_DTYPE)
+    seeds = np.ascontiguousarray(seeds, dtype=_lib.SEED_DTYPE)
+    o7 = opt.opt7()
+    cap = int(cap if cap is not None else len(seeds) + 1)
+    regs = np.zeros(cap, dtype=_lib.ALNREG_DTYPE)
+    out_off = np.zeros(reads.shape[0] + 1, dtype=np.int32)
+    n_spec, n_used = C.c_int64(0), C.c_int64(0)
+    n = _lib.check(_lib.lib().csbwa_chain2aln_flat(reads.ctypes.data, reads.shape[0], reads.shape[1], read_chain_off.ctypes.data,
+                                                   chains.ctypes.data, seeds.ctypes.data, o7.ctypes.data, regs.ctypes.data, cap,
+                                                   out_off.ctypes.data, C.addressof(n_spec), C.addressof(n_used), device))
+    return regs[:n], out_off, n_spec.value, n_used.value

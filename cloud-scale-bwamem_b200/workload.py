@@ -252,3 +252,28 @@ def matesw_workload(n_pairs, L, ref_bp, eps, mu, sigma, rescue_frac, seed, pairs
             n_jobs += len(jobs)
         done += m
     return dict(calls=calls, n_jobs=n_jobs, n_pairs=n_pairs, L=L, low=low, high=high, ref=ref)
+
+
+def all_seeds(rb, opt):
+    """Every seed of every read (maximal exact runs >= minSeedLen), one chain per read, seeds in
+    query order (the seedsRefArray order of a chain).  Returns (read_chain_off int32[n+1],
+    chains CHAIN_DTYPE[], seeds SEED_DTYPE[])."""
+    n, L = rb.n, rb.L
+    j = np.arange(L, dtype=np.int64)[None, :]
+    start = np.maximum.accumulate(np.where(rb.err, j + 1, np.where(rb.cut, j, 0)), axis=1)
+    run = np.where(rb.err, 0, j + 1 - start)
+    nxt_break = np.ones((n, L), dtype=bool)
+    nxt_break[:, :-1] = rb.err[:, 1:] | rb.cut[:, 1:]
+    is_end = (run >= opt.minSeedLen) & nxt_break
+    rr, ee = np.nonzero(is_end)                                  # row-major: query order inside a read
+    slen = run[rr, ee]
+    qbeg = ee - slen + 1
+    seeds = np.zeros(len(rr), dtype=_lib.SEED_DTYPE)
+    seeds["r_beg"] = rb.ref_idx[rr, qbeg]; seeds["q_beg"] = qbeg; seeds["len"] = slen
+    cnt = np.bincount(rr, minlength=n)
+    has = cnt > 0
+    chains = np.zeros(int(has.sum()), dtype=_lib.CHAIN_DTYPE)
+    off = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    chains["seed_off"] = off[has]; chains["n_seeds"] = cnt[has]
+    read_chain_off = np.concatenate([[0], np.cumsum(has.astype(np.int64))]).astype(np.int32)
+    return read_chain_off, chains, seeds

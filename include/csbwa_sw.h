@@ -244,6 +244,23 @@ int64_t csbwa_expand_coords(const uint8_t *reads, int32_t n_reads, int32_t read_
                             const csbwa_seed_task *tasks, int32_t n_tasks, const int32_t *opt7,
                             uint8_t *wire_out, int64_t cap, int device);
 
+/* ---- next row: round-flattened chain -> alignment driver -------------------
+ * memChainToAlnBatched (S/worker1/MemChainToAlignBatched.scala:380-615) extends one seed per read
+ * per round because testExtension / checkOverlapping (:688-787) look at the regions of earlier
+ * rounds.  Here every seed that does not span its read is extended speculatively in ONE launch
+ * sequence (coordinate tasks against the resident reference), and the order-dependent logic --
+ * calPreResultsOfSW's window and visiting order (:348-378, 653-678), the skip decisions, MARKED
+ * bookkeeping, region construction (:590-601), computeSeedCoverage (:892-908) -- is replayed per
+ * read on the host.  seeds: seedsRefArray order inside each chain; read_chain_off: CSR of chains
+ * per read.  out_regs / out_off: the regArrays (MemAlnRegType), CSR per read.  n_spec / n_used
+ * (nullable): extensions computed / consumed.  Returns regions written or a negative code. */
+typedef struct { int64_t r_beg; int32_t q_beg, len; } csbwa_seed;       /* MemSeedType */
+typedef struct { int32_t seed_off, n_seeds; } csbwa_chain;              /* MemChainType: a slice of seeds[] */
+int csbwa_chain2aln_flat(const uint8_t *reads, int32_t n_reads, int32_t read_len,
+                         const int32_t *read_chain_off, const csbwa_chain *chains, const csbwa_seed *seeds,
+                         const int32_t *opt7, csbwa_alnreg *out_regs, int32_t out_cap, int32_t *out_off,
+                         int64_t *n_spec, int64_t *n_used, int device);
+
 /* ---- next row of the path: SWGlobal (banded global alignment + backtrace -> CIGAR) ---------
  * Reference: S/util/SWUtil.scala:233-397 (port of ksw_global2, N/ksw.c:501-584), called once per
  * emitted alignment by bwaGenCigar2 (S/worker2/MemRegToADAMSAM.scala:738-893), which also chooses

@@ -791,3 +791,186 @@ int orc_global_batch(const orc_gjob_t *jobs, int32_t n, const uint8_t *seqs, int
     orc_parallel_for(n, n_threads, 16, orc_gl_body, &c);
     return 0;
 }
+
+/* =====================================================================================
+ * chain -> alignment driver (worker1 round loop), S/worker1/MemChainToAlignBatched.scala
+ * ===================================================================================== */
+/* calMaxGap (:625-641) */
+static int orc_cal_max_gap(const orc_opt_t *o, int qlen)
+{
+    int len_del = (int)((double)(qlen * o->a - o->o_del) / (double)o->e_del + 1.0);
+    int len_ins = (int)((double)(qlen * o->a - o->o_ins) / (double)o->e_ins + 1.0);
+    int len = len_del > len_ins ? len_del : len_ins;
+    if (len <= 1) len = 1;
+    const int tmp = o->w << 1;
+    return len < tmp ? len : tmp;
+}
+
+/* bnsGetSeq (S/util/BNTSeqUtil.scala:37-83); returns rlen, seq must hold |end - beg| bytes */
+static int64_t orc_bns_get_seq(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, uint8_t *seq)
+{
+    if (end < beg) { int64_t t = beg; beg = end; end = t; }
+    if (end > (l_pac << 1)) end = l_pac << 1;
+    if (beg < 0) beg = 0;
+    int64_t rlen = end - beg;
+    if (beg >= l_pac || end <= l_pac) {
+        int64_t l = 0;
+        if (beg >= l_pac) {                                   /* reverse strand */
+            const int64_t beg_f = (l_pac << 1) - 1 - end, end_f = (l_pac << 1) - 1 - beg;
+            for (int64_t k = end_f; k >= beg_f + 1; --k)
+                seq[l++] = (uint8_t)((3 - (pac[k >> 2] >> ((~k & 3) << 1))) & 3);
+        } else {
+            for (int64_t k = beg; k < end; ++k)
+                seq[l++] = (uint8_t)((pac[k >> 2] >> ((~k & 3) << 1)) & 3);
+        }
+    } else rlen = 0;                                          /* bridging the strands: nothing */
+    return rlen;
+}
+
+#define ORC_MARKED (-2)
+
+/* testExtension (:688-747): index of the first region the seed is "around", else cur_len */
+static int orc_test_extension(const orc_opt_t *o, const orc_seed_t *sd, const orc_alnreg_t *regs, int cur_len)
+{
+    for (int i = 0; i < cur_len; ++i) {
+        const orc_alnreg_t *r = &regs[i];
+        if (sd->r_beg >= r->rb && sd->r_beg + sd->len <= r->re && sd->q_beg >= r->qb && sd->q_beg + sd->len <= r->qe) {
+            int q_dist = sd->q_beg - r->qb;
+            int64_t r_dist = sd->r_beg - r->rb;
+            int min_dist = q_dist < r_dist ? q_dist : (int)r_dist;
+            int max_gap = orc_cal_max_gap(o, min_dist);
+            int w = max_gap < o->w ? max_gap : o->w;
+            if (q_dist - r_dist < w && r_dist - q_dist < w) return i;
+            q_dist = r->qe - (sd->q_beg + sd->len);
+            r_dist = r->re - (sd->r_beg + sd->len);
+            min_dist = q_dist < r_dist ? q_dist : (int)r_dist;
+            max_gap = orc_cal_max_gap(o, min_dist);
+            w = max_gap < o->w ? max_gap : o->w;
+            if (q_dist - r_dist < w && r_dist - q_dist < w) return i;
+        }
+    }
+    return cur_len;
+}
+
+/* checkOverlapping (:758-787): srt_index[] holds seedsRefArray indices or ORC_MARKED */
+static int orc_check_overlapping(int start, const orc_seed_t *sd, const orc_seed_t *chain_seeds, int n_seeds,
+                                 const int *srt_index)
+{
+    for (int i = start; i < n_seeds; ++i) {
+        if (srt_index[i] == ORC_MARKED) continue;
+        const orc_seed_t *t = &chain_seeds[srt_index[i]];
+        if ((double)t->len >= (double)sd->len * 0.95) {
+            if (sd->q_beg <= t->q_beg && (sd->q_beg + sd->len - t->q_beg) >= (sd->len >> 2) &&
+                (int64_t)(t->q_beg - sd->q_beg) != (t->r_beg - sd->r_beg)) return i;
+            if (t->q_beg <= sd->q_beg && (t->q_beg + t->len - sd->q_beg) >= (sd->len >> 2) &&
+                (int64_t)(sd->q_beg - t->q_beg) != (sd->r_beg - t->r_beg)) return i;
+        }
+    }
+    return n_seeds;
+}
+
+typedef struct { int len, index; } orc_srt_t;
+static int orc_srt_cmp(const void *a, const void *b)
+{
+    const orc_srt_t *x = (const orc_srt_t *)a, *y = (const orc_srt_t *)b;
+    if (x->len != y->len) return x->len < y->len ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0);
+}
+
+int orc_chain2aln(const uint8_t *reads, int32_t n_reads, int32_t read_len, const int32_t *read_chain_off,
+                  const orc_chain_t *chains, const orc_seed_t *seeds, const uint8_t *pac, int64_t l_pac,
+                  const orc_opt_t *opt, orc_alnreg_t *out, int32_t cap, int32_t *out_off,
+                  int64_t *cells_out, int64_t *n_ext_out)
+{
+    int64_t cells = 0, n_ext = 0;
+    int32_t n_out = 0;
+    const int L = read_len;
+    uint8_t *lq = (uint8_t *)malloc((size_t)L + 1);
+    for (int32_t r = 0; r < n_reads; ++r) {
+        out_off[r] = n_out;
+        const uint8_t *query = reads + (size_t)r * L;
+        orc_alnreg_t *regs = out + n_out;                     /* this read's growing region list */
+        int cur = 0;
+        for (int32_t c = read_chain_off[r]; c < read_chain_off[r + 1]; ++c) {
+            const orc_seed_t *cs = seeds + chains[c].seed_off;
+            const int ns = chains[c].n_seeds;
+            if (ns <= 0) continue;
+            /* getMaxSpan (:653-678) */
+            int64_t rmax0 = l_pac << 1, rmax1 = 0;
+            for (int k = 0; k < ns; ++k) {
+                const int64_t b = cs[k].r_beg - (cs[k].q_beg + orc_cal_max_gap(opt, cs[k].q_beg));
+                const int rest = L - cs[k].q_beg - cs[k].len;
+                const int64_t e = cs[k].r_beg + cs[k].len + rest + orc_cal_max_gap(opt, rest);
+                if (rmax0 > b) rmax0 = b;
+                if (rmax1 < e) rmax1 = e;
+            }
+            if (rmax0 <= 0) rmax0 = 0;
+            if (rmax1 >= (l_pac << 1)) rmax1 = l_pac << 1;
+            if (rmax0 < l_pac && l_pac < rmax1) {
+                if (cs[0].r_beg < l_pac) rmax1 = l_pac; else rmax0 = l_pac;
+            }
+            uint8_t *rseq = (uint8_t *)malloc((size_t)(rmax1 - rmax0) + 1);
+            const int64_t rlen = orc_bns_get_seq(l_pac, pac, rmax0, rmax1, rseq);
+            if (rlen != rmax1 - rmax0) { free(rseq); free(lq); return -3; }        /* the reference asserts (:363) */
+            orc_srt_t *srt = (orc_srt_t *)malloc(sizeof(orc_srt_t) * (size_t)ns);
+            int *sidx = (int *)malloc(sizeof(int) * (size_t)ns);
+            for (int k = 0; k < ns; ++k) { srt[k].len = cs[k].len; srt[k].index = k; }
+            qsort(srt, (size_t)ns, sizeof(orc_srt_t), orc_srt_cmp);
+            for (int k = 0; k < ns; ++k) sidx[k] = srt[k].index;
+            uint8_t *lr = (uint8_t *)malloc((size_t)(rmax1 - rmax0) + 1);
+            for (int y = ns - 1; y >= 0; --y) {                /* longest seed first (:408, 439-451) */
+                const orc_seed_t *sd = &cs[sidx[y]];
+                const int ext = orc_test_extension(opt, sd, regs, cur);
+                int ovl = -1;
+                if (ext < cur) ovl = orc_check_overlapping(y + 1, sd, cs, ns, sidx);
+                if (ext < cur && ovl == ns) { sidx[y] = ORC_MARKED; continue; }
+                if (n_out + cur >= cap) { free(lr); free(srt); free(sidx); free(rseq); free(lq); return -4; }
+                orc_alnreg_t reg;
+                memset(&reg, 0, sizeof reg);
+                reg.w = opt->w;
+                reg.score = sd->len * opt->a; reg.truesc = sd->len * opt->a;
+                reg.qb = 0; reg.rb = sd->r_beg; reg.qe = L; reg.re = sd->r_beg + sd->len;
+                if (sd->q_beg > 0 || sd->q_beg + sd->len != L) {
+                    orc_task_t t;
+                    memset(&t, 0, sizeof t);
+                    t.left_qlen = sd->q_beg;
+                    if (t.left_qlen > 0) {
+                        for (int ii = 0; ii < t.left_qlen; ++ii) lq[ii] = query[t.left_qlen - 1 - ii];
+                        t.left_rlen = (int)(sd->r_beg - rmax0);
+                        for (int ii = 0; ii < t.left_rlen; ++ii) lr[ii] = rseq[t.left_rlen - 1 - ii];
+                        t.left_q = lq; t.left_r = lr;
+                    }
+                    const int qe = sd->q_beg + sd->len;
+                    t.right_qlen = L - qe;
+                    if (t.right_qlen > 0) {
+                        const int64_t re = sd->r_beg + sd->len - rmax0;
+                        t.right_rlen = (int)(rmax1 - rmax0 - re);
+                        t.right_q = query + qe; t.right_r = rseq + re;
+                    }
+                    t.h0 = sd->len * opt->a; t.reg_score = reg.score; t.q_beg = sd->q_beg; t.idx = r;
+                    orc_extret_t er;
+                    orc_extension(&t, opt, &er);
+                    cells += er.cells; ++n_ext;
+                    reg.qb = er.q_beg;
+                    reg.rb = er.r_beg + sd->r_beg;
+                    reg.qe = er.q_end + sd->q_beg + sd->len;
+                    reg.re = er.r_end + sd->r_beg + sd->len;
+                    reg.score = er.score; reg.truesc = er.true_score; reg.w = er.width;
+                }
+                int cov = 0;                                   /* computeSeedCoverage (:892-908) */
+                for (int k = 0; k < ns; ++k)
+                    if (cs[k].q_beg >= reg.qb && cs[k].q_beg + cs[k].len <= reg.qe &&
+                        cs[k].r_beg >= reg.rb && cs[k].r_beg + cs[k].len <= reg.re) cov += cs[k].len;
+                reg.seedcov = cov;
+                regs[cur++] = reg;
+            }
+            free(lr); free(srt); free(sidx); free(rseq);
+        }
+        n_out += cur;
+    }
+    out_off[n_reads] = n_out;
+    free(lq);
+    if (cells_out) *cells_out = cells;
+    if (n_ext_out) *n_ext_out = n_ext;
+    return n_out;
+}

@@ -154,6 +154,21 @@ typedef struct {
 int orc_global_batch(const orc_gjob_t *jobs, int32_t n, const uint8_t *seqs, int32_t *res2,
                      uint32_t *cigars, int64_t *cells_per_job, int n_threads);
 
+/* ---- chain -> alignment driver of worker1 (the round loop around the extension seam) ------------
+ * calPreResultsOfSW (getMaxSpan + bnsGetSeq + srt sort, S/worker1/MemChainToAlignBatched.scala:348-378,
+ * 653-678; S/util/BNTSeqUtil.scala:37-83) and memChainToAlnBatched (:380-615) with testExtension
+ * (:688-747), checkOverlapping (:758-787) and computeSeedCoverage (:892-908), one read at a time
+ * (reads never interact; the rounds of the reference only decide what is batched together).
+ * seeds are in seedsRefArray order inside each chain; read_chain_off is the CSR of chains per read
+ * (a read without chains has an empty range).  pac: bwa 2-bit reference.  Extensions run on demand,
+ * exactly when the reference would run them; n_ext counts them.  Returns regions written or < 0. */
+typedef struct { int64_t r_beg; int32_t q_beg, len; } orc_seed_t;
+typedef struct { int32_t seed_off, n_seeds; } orc_chain_t;
+int orc_chain2aln(const uint8_t *reads, int32_t n_reads, int32_t read_len, const int32_t *read_chain_off,
+                  const orc_chain_t *chains, const orc_seed_t *seeds, const uint8_t *pac, int64_t l_pac,
+                  const orc_opt_t *opt, orc_alnreg_t *out, int32_t cap, int32_t *out_off,
+                  int64_t *cells, int64_t *n_ext);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -336,3 +336,32 @@ def ref_ksw_global2(query, target, w, opt=None):
     if nc.value:
         C.CDLL(None).free(cg)
     return sc, out
+
+
+SEED_DTYPE = np.dtype([("r_beg", "<i8"), ("q_beg", "<i4"), ("len", "<i4")])
+CHAIN_DTYPE = np.dtype([("seed_off", "<i4"), ("n_seeds", "<i4")])
+
+
+def chain2aln(reads, read_chain_off, chains, seeds, pac, l_pac, opt=None, cap=None):
+    """memChainToAlnBatched, read by read, extensions on demand (the reference's own order of work).
+    Returns (regs ALNREG_DTYPE[], out_off int32[n+1], cells, n_ext)."""
+    L = lib()
+    o = opt or default_opt()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    read_chain_off = np.ascontiguousarray(read_chain_off, dtype=np.int32)
+    chains = np.ascontiguousarray(chains, dtype=CHAIN_DTYPE)
+    seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+    pac = np.ascontiguousarray(pac, dtype=np.uint8)
+    cap = int(cap if cap is not None else len(seeds) + 1)
+    out = np.zeros(cap, dtype=ALNREG_DTYPE)
+    out_off = np.zeros(reads.shape[0] + 1, dtype=np.int32)
+    cells, n_ext = C.c_int64(0), C.c_int64(0)
+    L.orc_chain2aln.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.POINTER(Opt), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_chain2aln.restype = C.c_int
+    n = L.orc_chain2aln(reads.ctypes.data, reads.shape[0], reads.shape[1], read_chain_off.ctypes.data, chains.ctypes.data,
+                        seeds.ctypes.data, pac.ctypes.data, int(l_pac), C.byref(o), out.ctypes.data, cap, out_off.ctypes.data,
+                        C.addressof(cells), C.addressof(n_ext))
+    if n < 0:
+        raise RuntimeError("orc_chain2aln failed: %d" % n)
+    return out[:n], out_off, cells.value, n_ext.value

@@ -1,0 +1,87 @@
+"""Round-flattened chain -> alignment driver: every seed extended speculatively in
+one GPU launch sequence + host replay of testExtension / checkOverlapping / MARKED / seed coverage must give
+the region lists of the reference's round loop (oracle: extensions on demand, in the reference's order)."""
+import numpy as np
+import pytest
+
+
+def _workload_chains(pkg, seed=11, n_pairs=600, L=151, G=400000, eps=0.03):
+    W = pkg.workload
+    opt = pkg.jni.MemOptType()
+    rng = np.random.default_rng(seed)
+    ref = W.make_reference(G, seed)
+    rb = W.ReadBatch(ref, n_pairs, L, eps, 400, 50, rng, indel_frac=0.5)
+    rco, chains, seeds = W.all_seeds(rb, opt)
+    return opt, ref, rb.reads, rco, chains, seeds
+
+
+def _crafted_chains(pkg, rng, ref, L=101, n_reads=400):
+    """Adversarial chain sets: several chains per read, seeds overlapping on different diagonals, duplicates,
+    seeds spanning the read, reads without chains, reverse-strand chains (coordinates >= l_pac)."""
+    G = len(ref)
+    comp = pkg.workload.COMP
+    reads = np.zeros((n_reads, L), dtype=np.uint8)
+    rco, chains, seeds = [0], [], []
+    for r in range(n_reads):
+        pos = int(rng.integers(2000, G - 2000))
+        rev = rng.random() < 0.3
+        frag = ref[pos:pos + L].copy()
+        k = int(rng.integers(0, 4))
+        for _ in range(k):                                        # substitutions
+            frag[int(rng.integers(0, L))] = rng.integers(0, 4)
+        read = comp[frag[::-1]] if rev else frag
+        reads[r] = read
+        base = (2 * G - (pos + L)) if rev else pos               # doubled coordinate of read base 0
+        n_ch = int(rng.choice([0, 1, 1, 1, 2, 3]))
+        for _c in range(n_ch):
+            ns = int(rng.choice([1, 1, 2, 3, 5, 8]))
+            first = len(seeds)
+            qs = sorted(int(x) for x in rng.integers(0, L - 19, ns))
+            for q in qs:
+                ln = int(min(L - q, rng.choice([19, 20, 25, 40, 60, L])))
+                dg = int(rng.choice([0, 0, 0, 1, -1, 3, -7, 20]))        # diagonal shift: overlapping seeds off the main diagonal
+                seeds.append((base + q + dg, q, ln))
+            chains.append((first, ns))
+        rco.append(len(chains))
+    return (reads, np.array(rco, dtype=np.int32), np.array(chains, dtype=pkg._lib.CHAIN_DTYPE).reshape(-1),
+            np.array(seeds, dtype=pkg._lib.SEED_DTYPE).reshape(-1))
+
+
+def test_oracle_round_loop_sanity(pkg, oracle):
+    """CPU only: the restated round loop on workload chains -- one region per read for clean reads, the extra
+    seeds of a read skipped (MARKED) once the first extension covers them."""
+    opt, ref, reads, rco, chains, seeds = _workload_chains(pkg, n_pairs=150, eps=0.02)
+    pac = pkg.jni.packPac(ref)
+    regs, off, cells, n_ext = oracle.chain2aln(reads, rco, chains, seeds, pac, len(ref))
+    assert off[-1] == len(regs) and len(regs) >= int((np.diff(rco) > 0).sum())
+    assert n_ext <= len(seeds) and n_ext >= len(regs) * 0.5 and cells > 0
+    per_read = np.diff(off)
+    assert (per_read[np.diff(rco) > 0] >= 1).all() and per_read.mean() < 1.6
+    assert (regs["seedcov"] >= 19).all() and (regs["qe"] > regs["qb"]).all()
+
+
+@pytest.mark.gpu
+def test_chain2aln_flat_parity(pkg, oracle):
+    L_ = pkg.lib()
+    assert L_.csbwa_init(0) >= 1
+    # (1) workload chains (indel-rich so that seeds sit on different diagonals)
+    opt, ref, reads, rco, chains, seeds = _workload_chains(pkg)
+    pac = pkg.jni.packPac(ref)
+    pkg.jni.refUpload(pac, len(ref))
+    want, woff, cells, n_ext = oracle.chain2aln(reads, rco, chains, seeds, pac, len(ref))
+    before = pkg.stats()["ext_cells"]
+    got, goff, n_spec, n_used = pkg.jni.memChainToAlnBatched(reads, rco, chains, seeds, opt, device=0)
+    assert np.array_equal(goff, woff)
+    assert got.tobytes() == want.tobytes()
+    assert n_used == n_ext and n_spec >= n_used                    # consumed == what the reference would run
+    assert pkg.stats()["ext_cells"] - before >= cells              # speculation only ever adds work
+    # (2) crafted adversarial chains, both strands
+    rng = np.random.default_rng(12)
+    creads, crco, cchains, cseeds = _crafted_chains(pkg, rng, ref)
+    want, woff, _, n_ext = oracle.chain2aln(creads, crco, cchains, cseeds, pac, len(ref))
+    got, goff, n_spec, n_used = pkg.jni.memChainToAlnBatched(creads, crco, cchains, cseeds, opt, device=0)
+    assert np.array_equal(goff, woff) and got.tobytes() == want.tobytes()
+    assert n_used == n_ext and n_spec > n_used                      # some seeds really are skipped
+    assert (np.diff(crco) == 0).any() and (np.diff(crco) >= 2).any()
+    assert (cseeds["r_beg"] >= len(ref)).any()
+    L_.csbwa_ref_release(-1)
