@@ -50,7 +50,12 @@ if ROOT not in sys.path:
 
 OPS_PER_CELL = 13          # BASELINE.md section 2 / SURVEY.md 8(d)
 READS_PER_CALL = 4096
-CFG = dict(L=151, ref_bp=100_000_000, eps=0.01, mu=400, sigma=50, seed=20260103)
+CFGS = {   # BASELINE.md section 3; the headline (and the default) is C2
+    "C1": dict(name="C1", L=101, ref_bp=5_000_000, eps=0.01, mu=300, sigma=30, seed=20260102),
+    "C2": dict(name="C2", L=151, ref_bp=100_000_000, eps=0.01, mu=400, sigma=50, seed=20260103),
+    "C5": dict(name="C5", L=250, ref_bp=100_000_000, eps=0.05, mu=600, sigma=60, seed=20260106),
+}
+CFG = CFGS["C2"]
 
 
 def env_int(name, default):
@@ -186,8 +191,8 @@ def run_reference_arm(args, pkg):
 
 
 def config_block(args, n_pairs):
-    return {"workload": "C2: pair-end %dx2 %d bp reads vs %d Mbp synthetic reference, eps=%.2f, seed extension, "
-                        "%d reads per seam call" % (n_pairs, CFG["L"], CFG["ref_bp"] // 1000000, CFG["eps"], READS_PER_CALL),
+    return {"workload": "%s: pair-end %dx2 %d bp reads vs %d Mbp synthetic reference, eps=%.2f, seed extension, "
+                        "%d reads per seam call" % (CFG["name"], n_pairs, CFG["L"], CFG["ref_bp"] // 1000000, CFG["eps"], READS_PER_CALL),
             "pairs_per_gpu": n_pairs, "reads_per_call": READS_PER_CALL,
             "l2_policy": "inputs larger than L2 (all seam-call buffers of the shard stay resident, > 126 MB)",
             "parallelism": "reads sharded per GPU, no collective"}
@@ -210,6 +215,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--reads-per-call", type=int, default=4096, help="experiments only; the headline is 4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C2", choices=sorted(CFGS), help="BASELINE config (the headline is C2)")
     ap.add_argument("--no-matesw", action="store_true", help="skip the short mate-SW (C3 shape) leg reported under 'matesw'")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs under ncu only)")
     ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 1 column pairs (s16x2), 0 one column per step (u8); -1 library default")
@@ -217,6 +223,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     globals()["READS_PER_CALL"] = args.reads_per_call
+    globals()["CFG"] = CFGS[args.workload]
     pkg = importlib.import_module("cloud-scale-bwamem_b200")
     if args.impl == "reference":
         run_reference_arm(args, pkg)
@@ -347,7 +354,9 @@ def main():
     result_dev = d_out.cpu().numpy()
 
     # ---- e2e through the C ABI with host buffers ----
-    nthreads = args.threads or max(4, min(32, 2 * (os.cpu_count() or 4) // max(1, world)))
+    # concurrent seam callers: Spark task threads block inside the JNI call, so executors oversubscribe the
+    # cores (4 task threads per core here, at most 64 per GPU); reported as e2e.caller_threads_per_gpu
+    nthreads = args.threads or max(4, min(64, 4 * (os.cpu_count() or 4) // max(1, world)))
     outs = [np.zeros(10 * n, dtype=np.int16) for n in ntasks]
     in_ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
     out_ptrs = (C.c_void_p * len(bufs))(*[o.ctypes.data for o in outs])
