@@ -98,12 +98,12 @@ def longest_seeds(rb, opt):
     best_end = np.argmax(np.where(is_end, run, 0), axis=1)             # first longest
     r = np.arange(n)
     slen = run[r, best_end]
-    qbeg = best_end - slen + 1
+    qbeg = np.minimum(best_end - slen + 1, L - 1)
     rbeg = rb.ref_idx[r, qbeg]
     # chain-wide span: min/max over ALL seeds of the read (getMaxSpan :653-678)
     first_end = np.argmax(is_end, axis=1)
     last_end = L - 1 - np.argmax(is_end[:, ::-1], axis=1)
-    last_qbeg = last_end - run[r, last_end] + 1
+    last_qbeg = np.minimum(last_end - run[r, last_end] + 1, L - 1)      # (reads without any seed are dropped by `valid`)
     first_qend = first_end + 1
     diag_last = rb.ref_idx[r, last_qbeg] - last_qbeg
     rmax0 = diag_last - cal_max_gap(last_qbeg, opt)
