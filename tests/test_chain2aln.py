@@ -85,3 +85,45 @@ def test_chain2aln_flat_parity(pkg, oracle):
     assert (np.diff(crco) == 0).any() and (np.diff(crco) >= 2).any()
     assert (cseeds["r_beg"] >= len(ref)).any()
     L_.csbwa_ref_release(-1)
+
+
+@pytest.mark.gpu
+def test_human_sized_reference_coordinates(pkg, oracle):
+    """BASELINE config 4 shape: a 3.1 Gbp reference (775 MB of .pac, replicated per GPU), seeds whose
+    doubled coordinates exceed 2^32 on both strands; coordinate tasks and the flattened driver must
+    still agree with the oracle (64-bit addressing of the resident reference)."""
+    L_ = pkg.lib()
+    assert L_.csbwa_init(0) >= 1
+    rng = np.random.default_rng(13)
+    l_pac = 3_100_000_000
+    pac = rng.integers(0, 256, size=(l_pac + 3) // 4, dtype=np.uint8)
+    comp = pkg.workload.COMP
+    Lr, n = 151, 256
+    reads = np.zeros((n, Lr), dtype=np.uint8)
+    seeds = np.zeros(n, dtype=pkg._lib.SEED_DTYPE)
+    for r in range(n):
+        # positions spread over the whole forward strand, every other read from the reverse strand
+        pos = int(rng.integers(1000, l_pac - 1000)) if r % 4 else l_pac - 2000 - r      # also right below the strand boundary
+        k = np.arange(pos, pos + Lr, dtype=np.int64)
+        frag = ((pac[k >> 2] >> ((~k & 3) << 1)) & 3).astype(np.uint8)
+        q = int(rng.integers(0, 60)); ln = int(rng.integers(19, 70))
+        for _ in range(2):
+            frag_m = frag
+            j = int(rng.integers(0, Lr))
+            if not (q <= j < q + ln):
+                frag_m = frag.copy(); frag_m[j] = (frag[j] + 1) & 3; frag = frag_m
+        rev = r % 2 == 1
+        reads[r] = comp[frag[::-1]] if rev else frag
+        base = (2 * l_pac - (pos + Lr)) if rev else pos
+        qq = (Lr - q - ln) if rev else q
+        seeds[r] = (base + qq, qq, ln)
+    chains = np.zeros(n, dtype=pkg._lib.CHAIN_DTYPE)
+    chains["seed_off"] = np.arange(n); chains["n_seeds"] = 1
+    rco = np.arange(n + 1, dtype=np.int32)
+    assert (seeds["r_beg"] > 2 ** 32).any() and (seeds["r_beg"] < l_pac).any()
+    want, woff, _, n_ext = oracle.chain2aln(reads, rco, chains, seeds, pac, l_pac)
+    pkg.jni.refUpload(pac, l_pac, device=0)
+    got, goff, n_spec, n_used = pkg.jni.memChainToAlnBatched(reads, rco, chains, seeds, device=0)
+    assert np.array_equal(goff, woff) and got.tobytes() == want.tobytes()
+    assert n_used == n_ext == n and (got["score"] > 100).mean() > 0.9          # the reads really align at those coordinates
+    L_.csbwa_ref_release(-1)
