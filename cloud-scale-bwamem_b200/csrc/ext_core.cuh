@@ -5,10 +5,11 @@
 // including its quirks (last-j tie break :158, z-drop dangling else :194-199, band
 // shrink :201-214, gscore test on the loop variable :177).
 //
-// Two cores, both CSW_HD so tests/emu can run them on the CPU:
+// Two cores here (the default fast core, two query columns per instruction, is in ext_p2.cuh),
+// both CSW_HD so tests/emu can run them on the CPU:
 //   * sw_extend_generic : any size, int32 H/E rows in caller-provided memory (global
 //     scratch on the device).  The correctness anchor and the fallback for outliers.
-//   * sw_extend_u8      : the fast path.  Scores bounded by 255 (h0 + qlen*max(mat) <= 255,
+//   * sw_extend_u8      : the one-column fast core (csbwa_set_ext_mode(0)).  Scores bounded by 255 (h0 + qlen*max(mat) <= 255,
 //     always true for reads <= 255 bp with a = 1), qlen <= 255.  One 32-bit word per query
 //     column {PRMT selector for the base : 16, H : 8, E : 8} in thread-strided shared
 //     memory (bank == lane, conflict free for any band position), DPX add-max for the

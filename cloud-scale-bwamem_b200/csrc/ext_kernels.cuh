@@ -4,11 +4,15 @@
 //   k_ext_hist     : parse + validate the 32-B task records, histogram both sides by query length
 //   k_ext_scan     : descending prefix over the 257 bins, class boundaries
 //   k_ext_scatter  : counting-sort scatter -> per-side job lists ordered longest-first
-//   k_ext_side<L>  : one thread per LEFT job, one launch per size class (shared-memory budget)
-//   k_ext_side<R>  : one thread per task; RIGHT SWExtend seeded with the left score, then the
+//   k_ext_side<0, core> : one thread per LEFT job, one launch per size class (shared-memory budget:
+//                    generic + capacities 256/128/96/64/32 columns), each class on its own stream
+//   k_ext_side<1, core> : one thread per task; RIGHT SWExtend seeded with the left score, then the
 //                    ExtRet record is finalised and written (10 shorts)
-// Jobs are length-binned so the 32 lanes of a warp run bands of (nearly) equal width; warps
-// pull 32-job chunks from a per-class atomic cursor (longest first).
+// core = the column-pair s16x2 core of ext_p2.cuh (default) or the one-column u8 core of
+// ext_core.cuh.  Jobs are length-binned so the 32 lanes of a warp run bands of (nearly) equal width;
+// warps pull 32-job chunks from a per-class atomic cursor (longest first).  All kernels are
+// grid-stride or cursor-driven and can take {n_calls, n_tasks} from device memory (ExtCalls::dyn),
+// so the whole sequence replays as one CUDA graph whatever the batch.
 #pragma once
 #include <cuda_runtime.h>
 #include "ext_core.cuh"
