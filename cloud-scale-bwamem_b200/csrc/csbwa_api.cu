@@ -83,6 +83,9 @@ static int ensure_dev_attrs(int dev)
     std::lock_guard<std::mutex> lk(g_dev_mu);
     DevInfo &d = g_dev[dev];
     if (d.attrs_set) return CSBWA_OK;
+    // function attributes are per device: make `dev` current for the calls below (and leave it current --
+    // every caller works on `dev` next)
+    CU_TRY(cudaSetDevice(dev));
     cudaDeviceProp p;
     CU_TRY(cudaGetDeviceProperties(&p, dev));
     d.sms = p.multiProcessorCount;
@@ -786,6 +789,8 @@ extern "C" int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes, int16_t *
         if (rc) return rc;
         if (co->fits(in_bytes, n)) {
             rc = co->submit(in, in_bytes, out, n);
+            // (the detail string of a failed group lives in the submission thread; say what is known here)
+            if (rc < 0 && rc != CSBWA_E_SCRATCH) return fail(rc, "coalesced device submission failed: %s", csbwa_strerror(rc));
             if (rc != CSBWA_E_SCRATCH) return rc;      // outlier-heavy call: redo alone with the safe scratch size
         }
         device = dev;
