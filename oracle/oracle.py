@@ -19,6 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libcsbwa_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libksw_ref.so")
+_REF_MEM = os.path.join(_HERE, "_ref", "libbwamem_ref.so")
 
 XBYTE, XSTOP, XSUBO, XSTART = 0x10000, 0x20000, 0x40000, 0x80000
 
@@ -28,7 +29,7 @@ def build(force=False):
     if force or not os.path.exists(_LIB) or \
             os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "csbwa_oracle.c")):
         subprocess.check_call(["make", "-C", _HERE, "libcsbwa_oracle.so"], stdout=subprocess.DEVNULL)
-    if (force or not os.path.exists(_REF)) and os.path.exists("/root/reference/src/main/native/ksw.c"):
+    if (force or not os.path.exists(_REF) or not os.path.exists(_REF_MEM)) and os.path.exists("/root/reference/src/main/native/ksw.c"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -365,3 +366,71 @@ def chain2aln(reads, read_chain_off, chains, seeds, pac, l_pac, opt=None, cap=No
     if n < 0:
         raise RuntimeError("orc_chain2aln failed: %d" % n)
     return out[:n], out_off, cells.value, n_ext.value
+
+
+# ---- the reference's own bwa-0.7.8 mem_chain2aln (oracle/_ref/libbwamem_ref.so), for pinning orc_chain2aln ----
+class _MemOpt(C.Structure):                      # N/bwamem.h:21-47
+    _fields_ = [(n, C.c_int) for n in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "pen_unpaired", "pen_clip5", "pen_clip3",
+                                       "w", "zdrop", "T", "flag", "min_seed_len")] + \
+               [("split_factor", C.c_float), ("split_width", C.c_int), ("max_occ", C.c_int), ("max_chain_gap", C.c_int),
+                ("n_threads", C.c_int), ("chunk_size", C.c_int), ("mask_level", C.c_float), ("chain_drop_ratio", C.c_float),
+                ("mask_level_redun", C.c_float), ("mapQ_coef_len", C.c_float), ("mapQ_coef_fac", C.c_int), ("max_ins", C.c_int),
+                ("max_matesw", C.c_int), ("mat", C.c_int8 * 25)]
+
+
+class _MemSeed(C.Structure):                     # N/bwamem.c:167-170
+    _fields_ = [("rbeg", C.c_int64), ("qbeg", C.c_int32), ("len", C.c_int32)]
+
+
+class _MemChain(C.Structure):                    # N/bwamem.c:172-176
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("pos", C.c_int64), ("seeds", C.POINTER(_MemSeed))]
+
+
+class _MemAlnRegV(C.Structure):                  # N/bwamem.h:63
+    _fields_ = [("n", C.c_size_t), ("m", C.c_size_t), ("a", C.c_void_p)]
+
+
+_ref_mem = None
+
+
+def ref_mem_available():
+    return os.path.exists(_REF_MEM)
+
+
+def ref_mem_chain2aln(reads, read_chain_off, chains, seeds, pac, l_pac, zdrop=None):
+    """Region lists from the reference's C mem_chain2aln (N/bwamem.c:552-700), chain after chain per
+    read.  Returns (regs ALNREG_DTYPE[], out_off int32[n+1])."""
+    global _ref_mem
+    if _ref_mem is None:
+        build()
+        _ref_mem = C.CDLL(_REF_MEM)
+        _ref_mem.mem_opt_init.restype = C.POINTER(_MemOpt)
+        _ref_mem.mem_chain2aln.argtypes = [C.POINTER(_MemOpt), C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.POINTER(_MemChain), C.POINTER(_MemAlnRegV)]
+        _ref_mem.mem_chain2aln.restype = None
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    opt = _ref_mem.mem_opt_init()
+    if zdrop is not None:
+        opt.contents.zdrop = int(zdrop)
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    pac = np.ascontiguousarray(pac, dtype=np.uint8)
+    seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+    out, off = [], [0]
+    for r in range(reads.shape[0]):
+        av = _MemAlnRegV(0, 0, None)
+        for c in range(int(read_chain_off[r]), int(read_chain_off[r + 1])):
+            so, ns = int(chains["seed_off"][c]), int(chains["n_seeds"][c])
+            arr = (_MemSeed * max(ns, 1))()
+            for k in range(ns):
+                arr[k] = _MemSeed(int(seeds["r_beg"][so + k]), int(seeds["q_beg"][so + k]), int(seeds["len"][so + k]))
+            ch = _MemChain(ns, ns, 0, C.cast(arr, C.POINTER(_MemSeed)))
+            _ref_mem.mem_chain2aln(opt, int(l_pac), pac.ctypes.data, reads.shape[1], reads[r].ctypes.data, C.byref(ch), C.byref(av))
+        if av.n:
+            out.append(np.frombuffer(C.string_at(av.a, av.n * ALNREG_DTYPE.itemsize), dtype=ALNREG_DTYPE).copy())
+        if av.a:
+            libc.free(av.a)
+        off.append(off[-1] + int(av.n))
+    libc.free(C.cast(opt, C.c_void_p))
+    regs = np.concatenate(out) if out else np.zeros(0, dtype=ALNREG_DTYPE)
+    return regs, np.array(off, dtype=np.int32)

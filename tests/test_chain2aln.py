@@ -60,6 +60,28 @@ def test_oracle_round_loop_sanity(pkg, oracle):
     assert (regs["seedcov"] >= 19).all() and (regs["qe"] > regs["qb"]).all()
 
 
+def test_oracle_pinned_vs_reference_c(pkg, oracle):
+    """orc_chain2aln (restatement of the Scala round loop) against the reference's own bwa-0.7.8
+    mem_chain2aln compiled from /root/reference (oracle/_ref/libbwamem_ref.so): identical region
+    lists with zdrop = 0, where the Scala and the C z-drop rules coincide, on workload
+    chains and on crafted adversarial chain sets, both strands; with the default zdrop the two may
+    differ only through that documented quirk."""
+    if not oracle.ref_mem_available():
+        pytest.skip("oracle/_ref/libbwamem_ref.so not built")
+    opt, ref, reads, rco, chains, seeds = _workload_chains(pkg, n_pairs=200, eps=0.03)
+    pac = pkg.jni.packPac(ref)
+    o0 = oracle.default_opt(); o0.zdrop = 0
+    for (rd, rc_, ch, sd) in ((reads, rco, chains, seeds), _crafted_chains(pkg, np.random.default_rng(14), ref, n_reads=300)):
+        want, woff = oracle.ref_mem_chain2aln(rd, rc_, ch, sd, pac, len(ref), zdrop=0)
+        got, goff, _, _ = oracle.chain2aln(rd, rc_, ch, sd, pac, len(ref), opt=o0)
+        assert np.array_equal(goff, woff)
+        assert got.tobytes() == want.tobytes()
+        want, woff = oracle.ref_mem_chain2aln(rd, rc_, ch, sd, pac, len(ref))                # default zdrop = 100
+        got, goff, _, _ = oracle.chain2aln(rd, rc_, ch, sd, pac, len(ref))
+        same = np.array_equal(goff, woff) and got.tobytes() == want.tobytes()
+        assert same or (np.array_equal(goff, woff) and (got != want).mean() < 0.02)
+
+
 @pytest.mark.gpu
 def test_chain2aln_flat_parity(pkg, oracle):
     L_ = pkg.lib()
