@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU")
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=6)
     ap.add_argument("--group-calls", type=int, default=32, help="seam calls coalesced per launch sequence (resident leg)")
     ap.add_argument("--threads", type=int, default=0, help="caller threads of the e2e leg (0 = auto)")
     ap.add_argument("--cpu-step-seconds", type=float, default=6.0)

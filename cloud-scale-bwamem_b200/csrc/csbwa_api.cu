@@ -92,9 +92,12 @@ static int ensure_dev_attrs(int dev)
     const int big = 128 * 1024;
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    const int big_p2 = 128 * EXT_BD * 10;            // the 256-column class: 128 pairs x 10 bytes per thread
+    const int big_p2 = 64 * EXT_BD * 10;             // the 128-column class: 64 pairs x 10 bytes per thread
     CU_TRY(cudaFuncSetAttribute(k_ext_side<0, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
     CU_TRY(cudaFuncSetAttribute(k_ext_side<1, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
+    const int big_p2l = 128 * EXT_BD_LONG * 10;      // the 256-column class at one warp per block
+    CU_TRY(cudaFuncSetAttribute((k_ext_side<0, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side<1, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     CU_TRY(cudaFuncSetAttribute(k_glb, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     d.attrs_set = true;
     return CSBWA_OK;
@@ -115,7 +118,7 @@ extern "C" int64_t csbwa_extend_scratch_bytes(int32_t n_tasks, int64_t in_bytes)
 // Auxiliary streams of one submission stream: the per-class side kernels of a phase are
 // independent, so they are forked onto aux streams and joined before the next phase; their
 // tails (each is bounded by its longest job) then overlap instead of adding up.
-constexpr int kAux = 4;
+constexpr int kAux = 5;      // one aux stream per class 2..6
 struct AuxSet {
     cudaStream_t s[kAux] = {};
     cudaEvent_t fork[2] = {nullptr, nullptr};
@@ -203,15 +206,20 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
         } else if (core == EXT_CORE_P2) {
             // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
             const int npairs = cap / 2;
-            const int bd = EXT_BD;                          // the core is compiled for this stride
+            const bool lng = cls <= 2;                      // 256 / 192 columns: one warp per block
+            const int bd = lng ? EXT_BD_LONG : EXT_BD;      // the core is compiled for these strides
             const size_t smem = (size_t)npairs * bd * 10;
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 96);
             if (grid > cap_grid) grid = cap_grid;
-            k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
-                                                                   d_out, d_cells, cls, npairs);
+            if (lng)
+                k_ext_side<SIDE, EXT_CORE_P2, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                                                    d_out, d_cells, cls, npairs);
+            else
+                k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                                                                       d_out, d_cells, cls, npairs);
         } else {
-            const int bd = cls == 1 ? 64 : EXT_BD;
+            const int bd = cls <= 2 ? 64 : EXT_BD;
             const size_t smem = (size_t)cap * bd * 4;
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 80);

@@ -57,11 +57,13 @@ CSW_HD int ext_locate(const ExtCalls &cs, int g)
 }
 
 constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty side, 256 = generic
-constexpr int EXT_NCLS = 6;            // 0: generic, then fast classes by column capacity: 256, 128, 96, 64, 32
+constexpr int EXT_NCLS = 7;            // 0: generic, then fast classes by column capacity: 256, 192, 128, 96, 64, 32
 // extension cores (csbwa_set_ext_mode): which fast core serves the eligible sides
 constexpr int EXT_CORE_U8 = 0;         // one column per step, u8 scores (ext_core.cuh sw_extend_u8)
 constexpr int EXT_CORE_P2 = 1;         // two adjacent columns per step, s16 scores (ext_p2.cuh)
-constexpr int EXT_BD = 128;            // threads per block of the side kernels
+constexpr int EXT_BD = 128;            // threads per block of the side kernels ...
+constexpr int EXT_BD_LONG = 32;        // ... except the two long p2 classes (256 / 192 columns): one warp per block, so that
+                                       // 5 / 7 warps fit the shared memory of an SM instead of 4
 
 struct ExtHdr {
     SwOpt opt;
@@ -113,15 +115,16 @@ __host__ __device__ inline ExtScratch ext_carve(void *p, int n)
 CSW_HD int ext_class_of_bin(int bin)
 {
     if (bin == 256) return 0;           // a class of capacity cap holds qlen <= cap - 1 (column qlen is written)
-    if (bin >= 128) return 1;
-    if (bin >= 96) return 2;
-    if (bin >= 64) return 3;
-    if (bin >= 32) return 4;
-    return 5;
+    if (bin >= 192) return 1;
+    if (bin >= 128) return 2;
+    if (bin >= 96) return 3;
+    if (bin >= 64) return 4;
+    if (bin >= 32) return 5;
+    return 6;
 }
 __host__ __device__ inline int ext_class_cap(int cls)
 {
-    return cls == 1 ? 256 : (cls == 2 ? 128 : (cls == 3 ? 96 : (cls == 4 ? 64 : 32)));
+    return cls == 1 ? 256 : (cls == 2 ? 192 : (cls == 3 ? 128 : (cls == 4 ? 96 : (cls == 5 ? 64 : 32))));
 }
 
 // parse the 32-byte common header into SwOpt (MemChainToAlignBatched.scala:78-85)
@@ -291,8 +294,9 @@ CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, in
 // SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range.
 // CORE: -1 generic (int32 rows in global scratch), EXT_CORE_U8, EXT_CORE_P2 (shared memory).
 // npairs: column pairs per thread of the P2 layout ({H2,E2} records first, then the selectors).
-template <int SIDE, int CORE>
-__global__ void __launch_bounds__(EXT_BD)
+// BD: threads per block == element stride of the shared-memory rows (compile time for the p2 core).
+template <int SIDE, int CORE, int BD = EXT_BD>
+__global__ void __launch_bounds__(BD)
 k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
            SideRes *__restrict__ left, int *__restrict__ ehbase, int16_t *__restrict__ out,
            unsigned long long *cells_acc, int cls, int npairs)
@@ -310,8 +314,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;
     uint32_t *col = (uint32_t *)smem4 + threadIdx.x;            // U8: column j at col[j * stride]
-    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // P2: pair p at he[p * EXT_BD] (blocks of EXT_BD threads)
-    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * EXT_BD) + threadIdx.x;
+    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // P2: pair p at he[p * BD] (blocks of BD threads)
+    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * BD) + threadIdx.x;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t chunk = 0;
@@ -345,8 +349,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
             if (SIDE == 0) {
                 if (t.lq > 0) {      // (0 only after a validation / scratch failure, already reported)
                     if (CORE == EXT_CORE_P2)
-                        ext_run_side_p2<EXT_BD>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
-                                                he, sel, EXT_BD, L);
+                        ext_run_side_p2<BD>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
+                                            he, sel, BD, L);
                     else
                         ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
                                            t.reg_score, col, stride, H, E, L);
@@ -358,8 +362,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
                 if (t.rq > 0) {
                     const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
                     if (CORE == EXT_CORE_P2)
-                        ext_run_side_p2<EXT_BD>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
-                                                he, sel, EXT_BD, R);
+                        ext_run_side_p2<BD>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
+                                            he, sel, BD, R);
                     else
                         ext_run_side<FAST>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0,
                                            sc0, col, stride, H, E, R);

@@ -23,7 +23,7 @@ def test_exports_match_header(pkg):
         assert hasattr(L, name), name
     assert declared == set(pkg._lib.EXPORTS)
     assert L.csbwa_version().decode().startswith("csbwa-sw-b200")
-    assert L.csbwa_extend_launches_per_call() == 15 and L.csbwa_align2_launches_per_call() == 6
+    assert L.csbwa_extend_launches_per_call() == 17 and L.csbwa_align2_launches_per_call() == 6
 
 
 def test_no_cpu_fallback(pkg):
