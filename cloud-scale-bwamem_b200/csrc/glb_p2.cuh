@@ -91,8 +91,10 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
     const int rp = glb_p2_row_pairs(qlen, w);
     int hm1 = GP2_BIAS;                                 // H(i-1, -1): 0 before the first row
     long long ncell = 0;
+    int tb_next = tlen > 0 ? t[0] : 0;                  // target base of the next row, loaded one row ahead
     for (int i = 0; i < tlen; ++i) {
-        int tb = t[i]; if (tb > 4) tb = 4;
+        int tb = tb_next; if (tb > 4) tb = 4;
+        if (i + 1 < tlen) tb_next = t[i + 1];
         const uint32_t tlo = o.tlo[tb], thi = o.thi[tb];
         int beg = 0, end = qlen;
         if (i > w) beg = i - w;
