@@ -32,7 +32,7 @@ EXPORTS = [
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
-    "csbwa_global_batch_device", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat",
+    "csbwa_global_batch_device", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat", "csbwa_h2d_probe",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.csbwa_expand_coords.argtypes = [vp, i32, i32, vp, i32, vp, vp, i64, C.c_int]; L.csbwa_expand_coords.restype = i64
     L.csbwa_chain2aln_flat.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, C.c_int]
     L.csbwa_chain2aln_flat.restype = C.c_int
+    L.csbwa_h2d_probe.argtypes = [i64, C.c_int, C.c_int, C.c_int, C.c_int]; L.csbwa_h2d_probe.restype = C.c_double
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     _lib = L
     return L

@@ -1106,6 +1106,41 @@ extern "C" int64_t csbwa_pack_ext_from_seeds(int32_t n_tasks, const uint8_t *rea
     return need;
 }
 // ------------------------------------------------------------------------------------
+// host -> device staging: copy engine vs a pull kernel over mapped pinned memory (diagnostic)
+// ------------------------------------------------------------------------------------
+__global__ void k_pull(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// mode 0: cudaMemcpyAsync, 1: pull kernel.  n_streams copies of `bytes` in flight, `reps` rounds.  Returns GB/s.
+extern "C" double csbwa_h2d_probe(int64_t bytes, int reps, int mode, int n_streams, int grid)
+{
+    if (bytes < 16 || reps < 1 || n_streams < 1 || n_streams > 32) return -1.0;
+    std::vector<cudaStream_t> st((size_t)n_streams);
+    std::vector<void *> h((size_t)n_streams), d((size_t)n_streams);
+    for (int i = 0; i < n_streams; ++i) {
+        if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess) return -2.0;
+        if (cudaMallocHost(&h[i], (size_t)bytes) != cudaSuccess || cudaMalloc(&d[i], (size_t)bytes) != cudaSuccess) return -3.0;
+        memset(h[i], i + 1, (size_t)bytes);
+    }
+    auto round = [&]() {
+        for (int i = 0; i < n_streams; ++i) {
+            if (mode == 0) cudaMemcpyAsync(d[i], h[i], (size_t)bytes, cudaMemcpyHostToDevice, st[i]);
+            else k_pull<<<grid, 256, 0, st[i]>>>((uint4 *)d[i], (const uint4 *)h[i], (size_t)bytes / 16);
+        }
+        for (int i = 0; i < n_streams; ++i) cudaStreamSynchronize(st[i]);
+    };
+    round();
+    const double t0 = now_ms();
+    for (int r = 0; r < reps; ++r) round();
+    const double dt = now_ms() - t0;
+    for (int i = 0; i < n_streams; ++i) { cudaFreeHost(h[i]); cudaFree(d[i]); cudaStreamDestroy(st[i]); }
+    if (cudaGetLastError() != cudaSuccess) return -4.0;
+    return (double)bytes * n_streams * reps / (dt * 1e-3) / 1e9;
+}
+
+// ------------------------------------------------------------------------------------
 // coordinate-only extension tasks against a device-resident reference
 // ------------------------------------------------------------------------------------
 static_assert(sizeof(csbwa_seed_task) == sizeof(SeedTask), "seed task layout");

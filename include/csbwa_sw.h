@@ -293,6 +293,11 @@ int csbwa_global_launches_per_call(void);
  * Result: 1e9 thread-instructions per second over the whole GPU (dependent-free streams). */
 int csbwa_int_peak(int device, int op, double *giga_instr_per_s);
 
+/* Diagnostic: host -> device staging bandwidth (GB/s) on the current device for n_streams concurrent
+ * copies of `bytes` from pinned memory; mode 0 = copy engine (cudaMemcpyAsync), 1 = a pull kernel
+ * over mapped pinned memory with `grid` blocks.  Negative on error. */
+double csbwa_h2d_probe(int64_t bytes, int reps, int mode, int n_streams, int grid);
+
 #ifdef __cplusplus
 }
 #endif
