@@ -204,18 +204,34 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
 
 __global__ void k_ext_scan(ExtHdr *hdr)
 {
-    // one warp per side; bins are few, a serial scan by lane 0 is enough
-    const int side = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0 && side < 2) {
-        uint32_t acc = 0;
-        int cls = 0;
-        hdr->cls_beg[side][0] = 0;
-        for (int b = EXT_NBIN - 1; b >= 0; --b) {
-            const int c = ext_class_of_bin(b);
-            while (cls < c) hdr->cls_beg[side][++cls] = acc;
-            hdr->base[side][b] = acc;
+    // one warp per side: descending exclusive prefix over the 257 bins, 32 bins per step
+    const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (side >= 2) return;
+    uint32_t acc = 0;
+    for (int top = EXT_NBIN - 1; top >= 0; top -= 32) {
+        const int b = top - lane;                                  // lane 0 takes the highest bin of the step
+        const uint32_t v = b >= 0 ? hdr->hist[side][b] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (b >= 0) {
+            hdr->base[side][b] = acc + incl - v;
             hdr->cursor[side][b] = 0;
-            acc += hdr->hist[side][b];
+        }
+        acc += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // class k starts at the first bin (descending) whose class is >= k: base of that bin
+        hdr->cls_beg[side][0] = 0;
+        int cls = 0;
+        for (int b = EXT_NBIN - 1; b >= 0 && cls < EXT_NCLS; --b) {
+            const int c = ext_class_of_bin(b);
+            while (cls < c) hdr->cls_beg[side][++cls] = hdr->base[side][b];
+            if (c == EXT_NCLS - 1) break;
         }
         while (cls < EXT_NCLS) hdr->cls_beg[side][++cls] = acc;
         for (int c = 0; c < EXT_NCLS; ++c) hdr->work[side][c] = 0;
