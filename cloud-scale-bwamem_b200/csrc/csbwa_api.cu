@@ -13,6 +13,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <chrono>
 #include <mutex>
 #include <thread>
