@@ -11,8 +11,12 @@
  * The restatement is therefore pinned against the reference's own bundled C
  * (src/main/native/ksw.c, compiled out-of-tree into oracle/_ref/ by
  * oracle/Makefile) in the regimes where Scala and C provably agree
- * (zdrop<=0 for extension; qlen*a<250 for align2) -- see tests/test_oracle_vs_ref.py.
- * Where Scala and C differ (the z-drop dangling else), the Scala text wins.
+ * (zdrop<=0 for extension; qlen*a<250 and qlen%16==0 for align2; SWGlobal == ksw_global2;
+ * the worker1 round loop == mem_chain2aln of N/bwamem.c with zdrop = 0, via oracle/_ref/
+ * libbwamem_ref.so) -- see tests/test_oracle.py, tests/test_global.py, tests/test_chain2aln.py.
+ * Where Scala and C differ (the z-drop dangling else, ...), the Scala text wins and an independent
+ * literal Python transliteration of the Scala (tests/util.py) is the second witness.
+ * NOT pinned against a run of the reference's Scala itself (impossible in this image).
  *
  * Reference citations use S/ = src/main/scala/cs/ucla/edu/bwaspark/.
  */
