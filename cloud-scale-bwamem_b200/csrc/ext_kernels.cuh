@@ -56,7 +56,12 @@ CSW_HD int ext_locate(const ExtCalls &cs, int g)
     return lo;
 }
 
-constexpr int EXT_NBIN = 257;          // bins 1..255 = query length, 0 = empty side, 256 = generic
+// sort bins: 0 = empty side, 1 + qbucket * 32 + min(h0 >> 3, 31) for the fast cores (qbucket = qlen below 64,
+// 64 + (qlen - 64) / 4 above), EXT_NBIN - 1 = generic.
+// Jobs are ordered by query length first (longest first, shared-memory class) and by h0 inside a length
+// bucket: the band of row i spans about [(i - h0) / 2, 2i + h0], so lanes with the same (qlen, h0) run
+// rows of the same width -- a warp's row costs the width of its widest lane.
+constexpr int EXT_NBIN = 2 + 112 * 32;
 constexpr int EXT_NCLS = 7;            // 0: generic, then fast classes by column capacity: 256, 192, 128, 96, 64, 32
 // extension cores (csbwa_set_ext_mode): which fast core serves the eligible sides
 constexpr int EXT_CORE_U8 = 0;         // one column per step, u8 scores (ext_core.cuh sw_extend_u8)
@@ -112,14 +117,28 @@ __host__ __device__ inline ExtScratch ext_carve(void *p, int n)
     return s;
 }
 
-CSW_HD int ext_class_of_bin(int bin)
+CSW_HD int ext_qbucket(int qlen) { return qlen < 64 ? qlen : 64 + ((qlen - 64) >> 2); }     // 0..111 for qlen <= 255
+CSW_HD int ext_sort_bin(int kind, int qlen, int h0)    // kind: ext_side_bin() = 0 empty, 256 generic, else fast
 {
-    if (bin == 256) return 0;           // a class of capacity cap holds qlen <= cap - 1 (column qlen is written)
-    if (bin >= 192) return 1;
-    if (bin >= 128) return 2;
-    if (bin >= 96) return 3;
-    if (bin >= 64) return 4;
-    if (bin >= 32) return 5;
+    if (kind == 0) return 0;
+    if (kind == 256) return EXT_NBIN - 1;
+    int hb = h0 >> 3;
+    hb = hb < 0 ? 0 : (hb > 31 ? 31 : hb);
+    return 1 + ext_qbucket(qlen) * 32 + hb;
+}
+// first (highest) sort bin of each fast class; a class of capacity cap holds qlen <= cap - 1 (column qlen is written)
+CSW_HD int ext_class_top_bin(int cls)
+{
+    const int qmax = cls == 1 ? 255 : (cls == 2 ? 191 : (cls == 3 ? 127 : (cls == 4 ? 95 : (cls == 5 ? 63 : 31))));
+    return 1 + ext_qbucket(qmax) * 32 + 31;
+}
+CSW_HD int ext_class_of_qlen(int qlen)
+{
+    if (qlen >= 192) return 1;
+    if (qlen >= 128) return 2;
+    if (qlen >= 96) return 3;
+    if (qlen >= 64) return 4;
+    if (qlen >= 32) return 5;
     return 6;
 }
 __host__ __device__ inline int ext_class_cap(int cls)
@@ -192,8 +211,8 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
             br = ext_side_bin(sopt, t.rq, h0r, core);
             if (t.lq > 0 && bl == 256 && br != 0) br = 256;   // keep score bounds trivially safe
         }
-        if (bl) atomicAdd(&sh[0][bl], 1u);
-        atomicAdd(&sh[1][br], 1u);                            // every task has a right/finalise job
+        if (bl) atomicAdd(&sh[0][ext_sort_bin(bl, t.lq, t.h0)], 1u);
+        atomicAdd(&sh[1][ext_sort_bin(br, t.rq, t.lq > 0 ? t.h0 + t.lq * sopt.max_mat : t.reg_score)], 1u);   // every task has a right/finalise job
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * EXT_NBIN; i += blockDim.x) {
@@ -204,7 +223,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
 
 __global__ void k_ext_scan(ExtHdr *hdr)
 {
-    // one warp per side: descending exclusive prefix over the 257 bins, 32 bins per step
+    // one warp per side: descending exclusive prefix over the sort bins, 32 bins per step
     const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (side >= 2) return;
     uint32_t acc = 0;
@@ -225,15 +244,10 @@ __global__ void k_ext_scan(ExtHdr *hdr)
     }
     __syncwarp();
     if (lane == 0) {
-        // class k starts at the first bin (descending) whose class is >= k: base of that bin
+        // class 0 = the generic bin (first in the descending order), class k >= 1 starts at its top bin
         hdr->cls_beg[side][0] = 0;
-        int cls = 0;
-        for (int b = EXT_NBIN - 1; b >= 0 && cls < EXT_NCLS; --b) {
-            const int c = ext_class_of_bin(b);
-            while (cls < c) hdr->cls_beg[side][++cls] = hdr->base[side][b];
-            if (c == EXT_NCLS - 1) break;
-        }
-        while (cls < EXT_NCLS) hdr->cls_beg[side][++cls] = acc;
+        for (int c = 1; c < EXT_NCLS; ++c) hdr->cls_beg[side][c] = hdr->base[side][ext_class_top_bin(c)];
+        hdr->cls_beg[side][EXT_NCLS] = acc;
         for (int c = 0; c < EXT_NCLS; ++c) hdr->work[side][c] = 0;
     }
 }
@@ -253,8 +267,10 @@ __global__ void k_ext_scatter(const uint8_t *__restrict__ base, ExtCalls cs, int
             br = ext_side_bin(o, t.rq, h0r, hdr->core);
             if (t.lq > 0 && bl == 256 && br != 0) br = 256;
         }
-        if (bl) order_l[hdr->base[0][bl] + atomicAdd(&hdr->cursor[0][bl], 1u)] = (uint32_t)k;
-        order_r[hdr->base[1][br] + atomicAdd(&hdr->cursor[1][br], 1u)] = (uint32_t)k;
+        const int sl = ext_sort_bin(bl, t.lq, t.h0);
+        const int sr = ext_sort_bin(br, t.rq, t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score);
+        if (bl) order_l[hdr->base[0][sl] + atomicAdd(&hdr->cursor[0][sl], 1u)] = (uint32_t)k;
+        order_r[hdr->base[1][sr] + atomicAdd(&hdr->cursor[1][sr], 1u)] = (uint32_t)k;
     }
 }
 
