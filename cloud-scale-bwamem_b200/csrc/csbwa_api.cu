@@ -562,6 +562,23 @@ static double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// Staging copies of the direct (one call = one submission) paths can be tens of megabytes; a single
+// core moves ~5 GB/s, so large ones are split over a few threads.
+static void par_memcpy(void *dst, const void *src, size_t n)
+{
+    const size_t kMin = (size_t)4 << 20;
+    if (n < 2 * kMin) { memcpy(dst, src, n); return; }
+    int nt = (int)(n / kMin);
+    if (nt > 6) nt = 6;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const size_t a = n * (size_t)t / nt, b = n * (size_t)(t + 1) / nt;
+        th.emplace_back([=] { memcpy((char *)dst + a, (const char *)src + a, b - a); });
+    }
+    memcpy(dst, src, n / nt);
+    for (auto &x : th) x.join();
+}
+
 // host-side sanity check of the extension buffer (cheap; the device re-validates per record)
 static int check_ext_wire(const uint8_t *in, int32_t in_bytes, int32_t *n_out)
 {
@@ -822,7 +839,7 @@ static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out
         (rc = grow_dev(c->d_in, in_bytes)) || (rc = grow_dev(c->d_out, out_bytes)) ||
         (rc = grow_dev(c->d_scratch, scr)))
         return rc;
-    memcpy(c->h_in.p, in, in_bytes);
+    par_memcpy(c->h_in.p, in, in_bytes);
     CU_TRY(cudaEventRecord(c->ev[0], c->st));
     CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
     CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
@@ -882,7 +899,7 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
         (rc = grow_dev(c->d_scratch, scr)))
         return rc;
     memcpy(c->h_in.p, jobs, jb);
-    memcpy((char *)c->h_in.p + jb_al, seqs, (size_t)seq_bytes);
+    par_memcpy((char *)c->h_in.p + jb_al, seqs, (size_t)seq_bytes);
     CU_TRY(cudaEventRecord(c->ev[0], c->st));
     CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
     CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
@@ -1220,7 +1237,7 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
     if (wire_out && wire_cap < wire_b) return fail(CSBWA_E_SHORTOUT, "wire buffer too small");
     if (n_tasks == 0 && !wire_out) return CSBWA_OK;
     memcpy(h, tasks, tb);
-    memcpy(h + off_reads, reads, (size_t)n_reads * read_len);
+    par_memcpy(h + off_reads, reads, (size_t)n_reads * read_len);
     const size_t out_bytes = (size_t)n_tasks * CSBWA_EXT_RET_SHORTS * 2;
     const size_t scr = ext_scratch_bytes(n_tasks, wire_b);
     if ((rc = grow_dev(c->d_in, in_bytes + 16)) || (rc = grow_dev(c->d_aux, (size_t)wire_b + 256)) ||
@@ -1329,8 +1346,11 @@ extern "C" int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len,
 {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
+        if (dev >= 0 && dev < 64 && g_dev[dev].sms > 0) sms = g_dev[dev].sms;       // cached by ensure_dev_attrs
+        else {
+            cudaDeviceProp p;
+            if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
+        }
     } else cudaGetLastError();
     const int warps = glb_grid_warps(n_jobs > 0 ? n_jobs : 1, sms);
     const int wpb = kGlbBlock / 32;
@@ -1376,6 +1396,7 @@ extern "C" int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const 
     if (n_jobs < 0 || seq_bytes < 0 || cigar_words < 0 || (n_jobs > 0 && (!jobs || !seqs || !res || !cigars)))
         return fail(CSBWA_E_BADARG, "null buffer or negative size");
     if (n_jobs == 0) return CSBWA_OK;
+    const double tg0 = now_ms();
     int max_q = 0;
     long long max_z = 0;
     for (int32_t k = 0; k < n_jobs; ++k) {
@@ -1399,8 +1420,10 @@ extern "C" int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const 
     if ((rc = grow_pinned(c->h_in, in_bytes)) || (rc = grow_pinned(c->h_out, out_bytes)) ||
         (rc = grow_dev(c->d_in, in_bytes)) || (rc = grow_dev(c->d_out, out_bytes)) || (rc = grow_dev(c->d_scratch, scr)))
         return rc;
+    const double tg1 = now_ms();
     memcpy(c->h_in.p, jobs, (size_t)n_jobs * sizeof(csbwa_gjob));
-    memcpy((char *)c->h_in.p + jb, seqs, (size_t)seq_bytes);
+    par_memcpy((char *)c->h_in.p + jb, seqs, (size_t)seq_bytes);
+    const double tg2 = now_ms();
     CU_TRY(cudaMemcpyAsync(c->d_in.p, c->h_in.p, in_bytes, cudaMemcpyHostToDevice, c->st));
     CU_TRY(cudaMemsetAsync(c->d_cells, 0, 8, c->st));
     CU_TRY(cudaMemsetAsync(c->d_out.p, 0, out_bytes, c->st));
@@ -1410,8 +1433,12 @@ extern "C" int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const 
     CU_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, out_bytes, cudaMemcpyDeviceToHost, c->st));
     CU_TRY(cudaMemcpyAsync(c->h_cells, c->d_cells, 8, cudaMemcpyDeviceToHost, c->st));
     CU_TRY(cudaStreamSynchronize(c->st));
+    const double tg3 = now_ms();
     memcpy(res, c->h_out.p, (size_t)n_jobs * sizeof(csbwa_gres));
-    memcpy(cigars, (char *)c->h_out.p + res_b, (size_t)cigar_words * 4);
+    par_memcpy(cigars, (char *)c->h_out.p + res_b, (size_t)cigar_words * 4);
+    if (getenv("CSBWA_GLB_TIMING"))
+        fprintf(stderr, "global_batch: validate+ctx %.2f ms, stage in %.2f ms, device %.2f ms, copy out %.2f ms\n", tg1 - tg0, tg2 - tg1,
+                tg3 - tg2, now_ms() - tg3);
     {
         std::lock_guard<std::mutex> lk(g_stats_mu);
         g_stats.glb_calls++; g_stats.glb_jobs += n_jobs; g_stats.glb_cells += (int64_t)*c->h_cells;
