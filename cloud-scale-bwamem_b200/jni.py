@@ -180,7 +180,10 @@ class MateSWJNI:
     def __init__(self, device=-1):
         self.device = device
 
-    def mateSWJNI(self, pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+    @staticmethod
+    def flatten(pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+        """Object lists -> the flat csbwa_matesw_group arguments (also used by tests/jni_lib.py to
+        build the Java object graph for the JNI glue)."""
         G = int(groupSize)
         pes_a = np.zeros(4, dtype=_lib.PESTAT_DTYPE)
         for r in range(4):
@@ -208,6 +211,12 @@ class MateSWJNI:
                     refs[x]["off"][r] = -1
         win_seqs = np.concatenate(wins) if wins else np.zeros(1, np.uint8)
         ref_count = np.asarray(refSWArraySize, dtype=np.int32)
+        return pes_a, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs
+
+    def mateSWJNI(self, pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+        G = int(groupSize)
+        pes_a, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs = self.flatten(
+            pes, G, seqsPairs, mateSWArray, refSWArray, refSWArraySize)
         cap = int(reg_start[-1]) + 4 * len(refSWArray) + 8
         out = np.zeros(cap, dtype=_lib.ALNREG_DTYPE)
         out_start = np.zeros(2 * G + 1, dtype=np.int32)

@@ -27,6 +27,52 @@ def test_error_becomes_exception_without_gpu(pkg):
     assert rc == 1 and "csbwa" in msg                     # thrown, arrays released (rc 2 would be a protocol violation)
 
 
+def _group(pkg, G=12, L=101, seed=91):
+    from tests.test_matesw_group import PES_ALL
+    rng = np.random.default_rng(seed)
+    ref = pkg.workload.make_reference(60000, seed)
+    return (len(ref), PES_ALL, G) + tuple(util.gen_matesw_group(rng, pkg, ref, G, L, PES_ALL))
+
+
+def test_matesw_object_glue_protocol_without_gpu(pkg):
+    """MateSWJNI.mateSWJNI, the reference's own object-graph signature: the whole walk over MemOptType / MemPeStat /
+    SeqSWType / MateSWType -> MemAlnRegType / RefSWType runs on the fake JVM with no unknown field, no class mix-up,
+    no leaked pin and local references inside the requested capacity -- and failures surface as RuntimeException."""
+    import torch
+    L = jni_lib.load()
+    args = _group(pkg)
+    # non-default scoring is refused loudly, before any device work
+    n, _, msg, st = jni_lib.matesw_obj(L, *args, opt_field="b", opt_value=3)
+    assert n == -1 and "opt.b" in msg and st[2] == 0
+    n, _, msg, st = jni_lib.matesw_obj(L, *args, opt_field="maxMatesw", opt_value=50)
+    assert n == -1 and "opt.maxMatesw" in msg
+    # refSWArray / refSWArraySize disagreement -> exception, not a crash
+    n, _, msg, st = jni_lib.matesw_obj(L, *args, shuffle=2)
+    assert n == -1 and "refSWArray" in msg and st[2] == 0
+    # an empty group needs no device at all
+    n, lists, msg, st = jni_lib.matesw_obj(L, args[0], args[1], 0, [], [], [], [])
+    assert n == 0 and lists == [], msg
+    if not torch.cuda.is_available():
+        n, _, msg, st = jni_lib.matesw_obj(L, *args)
+        assert n == -1 and "csbwa" in msg                 # no device: RuntimeException after a clean walk
+        assert st[2] == 0 and st[0] <= st[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shuffle", [0, 1])
+def test_matesw_object_glue_gpu(pkg, oracle, shuffle):
+    L = jni_lib.load()
+    assert pkg.lib().csbwa_init(0) >= 1
+    args = _group(pkg, G=150, L=151, seed=92 + shuffle)
+    exp, nsw = oracle.matesw_group(*args)
+    n, got, msg, st = jni_lib.matesw_obj(L, *args, shuffle=shuffle)
+    assert n == sum(len(x) for x in exp), msg
+    assert st[2] == 0 and st[0] <= st[1], st               # no JNI protocol error, local refs within capacity
+    for g, e in zip(got, exp):
+        assert [tuple(int(v) for v in r) for r in g] == [tuple(int(v) for v in r) for r in e]
+    assert sum(len(g) > len(r) for g, r in zip(got, args[4])) > 150 // 4
+
+
 @pytest.mark.gpu
 def test_glue_end_to_end(pkg, oracle):
     L = jni_lib.load()
