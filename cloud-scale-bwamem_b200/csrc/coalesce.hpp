@@ -14,6 +14,10 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -57,6 +61,13 @@ public:
         }
         cv_work_.notify_all();
         for (auto &t : workers_) t.join();
+        const char *e = getenv("CSBWA_CO_TIMING");
+        if (e && e[0] == '1' && n_calls_ > 0) {
+            const double c = 1e-3 / (double)n_calls_, g = 1e-3 / (double)(n_groups_ > 0 ? n_groups_ : 1);
+            fprintf(stderr, "[csbwa coalescer] calls %lld groups %lld | per call us: wait-slot %.1f copy-in %.1f wait-done %.1f copy-out %.1f"
+                            " | per group us: wait-copies %.1f run %.1f\n", n_calls_, n_groups_, t_slot_ * c, t_in_ * c, t_done_ * c,
+                    t_out_ * c, t_close_ * g, t_run_ * g);
+        }
     }
 
     // bytes reserved at the start of the staging buffer: the call table, then {n_calls, n_tasks}
@@ -73,6 +84,7 @@ public:
     // Blocking: returns the executor's status for the group this call travelled in.
     int submit(const uint8_t *in, int in_bytes, int16_t *out, int n_tasks)
     {
+        const long long t0 = now_ns();
         std::unique_lock<std::mutex> lk(mu_);
         Group *g = nullptr;
         for (;;) {
@@ -96,12 +108,15 @@ public:
         const unsigned my_gen = g->gen;
         cv_work_.notify_one();
         lk.unlock();
+        const long long t1 = now_ns();
         memcpy(ex_->in_staging(g->slot) + c.in_off, in, (size_t)in_bytes);   // parallel across callers
+        const long long t2 = now_ns();
         lk.lock();
         if (--g->copying == 0) cv_work_.notify_all();
         g->cv_done.wait(lk, [&] { return g->gen == my_gen && g->state == DONE; });
         const int rc = g->rc;
         lk.unlock();
+        const long long t3 = now_ns();
         if (rc == 0) memcpy(out, ex_->out_staging(g->slot) + c.out_off, (size_t)n_tasks * 20);
         lk.lock();
         if (--g->readers == 0) {
@@ -109,6 +124,7 @@ public:
             g->gen++;
             cv_free_.notify_all();
         }
+        t_slot_ += t1 - t0; t_in_ += t2 - t1; t_done_ += t3 - t2; t_out_ += now_ns() - t3;
         return rc;
     }
 
@@ -176,16 +192,19 @@ private:
             });
             if (stop_ && !g) return;
             g->state = CLOSED;                              // group commit: no more joiners
+            const long long t0 = now_ns();
             cv_work_.wait(lk, [&] { return g->copying == 0; });
             std::vector<CoCall> calls = g->calls;
             const size_t span = g->bytes;
             const int tasks = g->tasks;
             lk.unlock();
+            const long long t1 = now_ns();
             memcpy(ex_->in_staging(g->slot), calls.data(), calls.size() * sizeof(CoCall));
             const int32_t dyn[4] = {(int32_t)calls.size(), tasks, 0, 0};
             memcpy(ex_->in_staging(g->slot) + header_off(), dyn, sizeof dyn);
             const int rc = ex_->run(g->slot, calls.data(), (int)calls.size(), span, tasks);
             lk.lock();
+            t_close_ += t1 - t0; t_run_ += now_ns() - t1;
             n_groups_++;
             n_calls_ += (long long)calls.size();
             g->rc = rc;
@@ -203,6 +222,12 @@ private:
     std::vector<std::thread> workers_;
     bool stop_;
     long long n_groups_ = 0, n_calls_ = 0;
+    // phase accumulators in ns (under mu_); printed at destruction with CSBWA_CO_TIMING=1
+    long long t_slot_ = 0, t_in_ = 0, t_done_ = 0, t_out_ = 0, t_close_ = 0, t_run_ = 0;
+    static long long now_ns()
+    {
+        return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
 };
 
 } // namespace csw

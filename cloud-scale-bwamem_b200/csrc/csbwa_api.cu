@@ -615,6 +615,13 @@ struct CudaCoExec {
     size_t in_cap = 0, out_cap = 0, scratch_cap = 0, hdr_off = 0;
     int max_tasks = 0;
     bool use_graph = true;
+    // How a submission thread waits for its group (CSBWA_CO_SYNC=sleep|yield|spin).  Spinning in the driver
+    // (cudaStreamSynchronize) costs one core per group in flight and starves the caller threads that have to
+    // copy their bytes in and out (measured on the 16-vCPU box, 64 callers: 350-410 GCUPS end to end); polling the
+    // completion event between 20 us sleeps leaves the cores to the callers and allows twice the groups in flight
+    // (520-560 GCUPS).  A blocking-sync event wakes 0.4 ms late, one polling thread for all groups fights the
+    // submissions for the driver lock: both measured slower (tools/e2e_probe.sh).
+    int sync_mode = 0;          // 0 query + short sleeps, 1 query + sched_yield, 2 spin in the driver
     std::vector<Slot> slots;
 
     int init(int device, int n_slots, size_t max_bytes, int max_tasks_, size_t header_off)
@@ -627,6 +634,8 @@ struct CudaCoExec {
         scratch_cap = ext_scratch_fixed(max_tasks) + (size_t)32 * 1024 * 1024;
         const char *e = getenv("CSBWA_CO_GRAPH");
         use_graph = !(e && e[0] == '0');
+        e = getenv("CSBWA_CO_SYNC");
+        sync_mode = !e ? 0 : e[0] == 'y' ? 1 : (e[0] == 's' && e[1] == 'p') ? 2 : 0;
         CU_TRY(cudaSetDevice(dev));
         slots.resize(n_slots);
         for (auto &s : slots) {
@@ -713,7 +722,16 @@ struct CudaCoExec {
         CU_TRY(cudaEventRecord(s.ev[2], s.st));
         CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, kTrailer + reply, cudaMemcpyDeviceToHost, s.st));
         CU_TRY(cudaEventRecord(s.ev[3], s.st));
-        CU_TRY(cudaStreamSynchronize(s.st));
+        if (sync_mode == 2) {
+            CU_TRY(cudaStreamSynchronize(s.st));
+        } else {
+            cudaError_t q;
+            while ((q = cudaEventQuery(s.ev[3])) == cudaErrorNotReady) {
+                if (sync_mode == 1) std::this_thread::yield();
+                else std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            CU_TRY(q);
+        }
         float t_h2d = 0, t_k = 0, t_d2h = 0;
         cudaEventElapsedTime(&t_h2d, s.ev[0], s.ev[1]);
         cudaEventElapsedTime(&t_k, s.ev[1], s.ev[2]);
@@ -773,7 +791,7 @@ static int get_coalescer(int dev, Coalescer<CudaCoExec> **out)
         if (rc) return rc;
         CoDev *d = new CoDev();
         // group buffers / submission threads per GPU (CSBWA_CO_SLOTS / CSBWA_CO_WORKERS to tune)
-        const int n_slots = env_int("CSBWA_CO_SLOTS", 8, 2, 32);
+        const int n_slots = env_int("CSBWA_CO_SLOTS", 16, 2, 32);
         const int n_workers = env_int("CSBWA_CO_WORKERS", n_slots - 1, 1, n_slots);
         rc = d->exec.init(dev, n_slots, kCoMaxBytes, kCoMaxTasks, (size_t)kCoMaxCalls * sizeof(CoCall));
         if (rc) { d->exec.destroy(); delete d; return rc; }
