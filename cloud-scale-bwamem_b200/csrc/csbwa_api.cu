@@ -254,7 +254,7 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     if (gb > g_dev[dev].sms * 8) gb = g_dev[dev].sms * 8;     // grid-stride kernels
     const int core = ext_core();
     k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
-    k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
+    k_ext_scan<<<1, EXT_SCAN_BD, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
     launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux, core);
     launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, g_dev[dev].sms, st, aux, core);
@@ -350,7 +350,7 @@ extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ex
     CU_TRY(cudaEventRecord(ev[0], st));
     const int core = ext_core();
     k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
-    k_ext_scan<<<1, 64, 0, st>>>(sc.hdr);
+    k_ext_scan<<<1, EXT_SCAN_BD, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
     CU_TRY(cudaEventRecord(ev[1], st));
     launch_ext_side<0>(in, cs, sc, (int16_t *)d_out_base, (unsigned long long *)d_cells, n_tasks, g_dev[dev].sms, st, nullptr, core);
@@ -601,15 +601,25 @@ static int check_ext_wire(const uint8_t *in, int32_t in_bytes, int32_t *n_out)
 // 4 driver calls instead of ~45, which matters because the submission threads serialise on the
 // driver's context lock (measured: 2.4 ms per group with direct launches).
 struct CudaCoExec {
+    static constexpr int kGraphVariants = 3;
     struct Slot {
         cudaStream_t st = nullptr;
         uint8_t *h_in = nullptr; uint8_t *h_out = nullptr;     // pinned
         uint8_t *d_in = nullptr; uint8_t *d_out = nullptr; void *d_scratch = nullptr;
         AuxSet aux;
-        cudaGraphExec_t graph = nullptr;
-        int graph_core = -1;
+        // one graph per size class of the group (grids sized for <= 16384 / 65536 / max_tasks tasks): a small
+        // group must not launch the thousands of empty blocks a 262144-task grid needs
+        cudaGraphExec_t graph[kGraphVariants] = {nullptr};
+        int graph_core[kGraphVariants] = {0};
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // H2D | launch sequence | D2H
     };
+    int variant_cap(int v) const { return v == 0 ? (max_tasks < 16384 ? max_tasks : 16384) : v == 1 ? (max_tasks < 65536 ? max_tasks : 65536) : max_tasks; }
+    int graph_variant(int n_tasks) const
+    {
+        int v = 0;
+        while (v < kGraphVariants - 1 && variant_cap(v) < n_tasks) ++v;
+        return v;
+    }
     static constexpr size_t kTrailer = 16;     // d_out / h_out: {cells : 8, status : 4, pad : 4} then the replies
     int dev = 0;
     size_t in_cap = 0, out_cap = 0, scratch_cap = 0, hdr_off = 0;
@@ -621,6 +631,7 @@ struct CudaCoExec {
     // completion event between 20 us sleeps leaves the cores to the callers and allows twice the groups in flight
     // (520-560 GCUPS).  A blocking-sync event wakes 0.4 ms late, one polling thread for all groups fights the
     // submissions for the driver lock: both measured slower (tools/e2e_probe.sh).
+    bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
     int sync_mode = 0;          // 0 query + short sleeps, 1 query + sched_yield, 2 spin in the driver
     std::vector<Slot> slots;
 
@@ -634,6 +645,8 @@ struct CudaCoExec {
         scratch_cap = ext_scratch_fixed(max_tasks) + (size_t)32 * 1024 * 1024;
         const char *e = getenv("CSBWA_CO_GRAPH");
         use_graph = !(e && e[0] == '0');
+        e = getenv("CSBWA_CO_ONE_GRAPH");
+        one_graph = e && e[0] == '1';
         e = getenv("CSBWA_CO_SYNC");
         sync_mode = !e ? 0 : e[0] == 'y' ? 1 : (e[0] == 's' && e[1] == 'p') ? 2 : 0;
         CU_TRY(cudaSetDevice(dev));
@@ -648,6 +661,16 @@ struct CudaCoExec {
             if (s.aux.init() != CSBWA_OK) return CSBWA_E_CUDA;
             for (auto &e : s.ev) CU_TRY(cudaEventCreate(&e));
         }
+        if (use_graph) {                                   // all graphs up front: no capture while groups are in flight
+            const double t0 = now_ms();
+            for (auto &s : slots)
+                for (int v = 0; v < kGraphVariants; ++v) {
+                    const int rc = build_graph(s, v);
+                    if (rc) return rc;
+                }
+            const char *t = getenv("CSBWA_CO_TIMING");
+            if (t && t[0] == '1') fprintf(stderr, "[csbwa coalescer] %d graphs built in %.1f ms\n", n_slots * kGraphVariants, now_ms() - t0);
+        }
         return CSBWA_OK;
     }
     void destroy()
@@ -655,7 +678,7 @@ struct CudaCoExec {
         cudaSetDevice(dev);
         for (auto &s : slots) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
-            if (s.graph) cudaGraphExecDestroy(s.graph);
+            for (auto &g : s.graph) if (g) cudaGraphExecDestroy(g);
             for (auto &e : s.ev) if (e) cudaEventDestroy(e);
             s.aux.destroy();
             if (s.h_in) cudaFreeHost(s.h_in);
@@ -670,32 +693,33 @@ struct CudaCoExec {
     int16_t *out_staging(int slot) { return (int16_t *)(slots[slot].h_out + kTrailer); }
 
     // the launch sequence of one slot; dyn = true: sized by the device from the staging header
-    int enqueue(Slot &s, const CoCall *calls, int n_calls, int n_tasks, bool dyn)
+    int enqueue(Slot &s, const CoCall *calls, int n_calls, int n_tasks, bool dyn, int variant = kGraphVariants - 1)
     {
+        const int dyn_cap = variant_cap(variant);
         CU_TRY(cudaMemsetAsync(s.d_out, 0, kTrailer, s.st));
         ExtCalls cs;
         cs.tab = (const ExtCall *)s.d_in; cs.n_calls = n_calls;
         cs.dyn = dyn ? (const int32_t *)(s.d_in + hdr_off) : nullptr;
         if (calls) memcpy(&cs.single, &calls[0], sizeof(ExtCall)); else memset(&cs.single, 0, sizeof(ExtCall));
-        int rc = launch_extend(s.d_in, cs, dyn ? max_tasks : n_tasks, (int16_t *)(s.d_out + kTrailer),
+        int rc = launch_extend(s.d_in, cs, dyn ? dyn_cap : n_tasks, (int16_t *)(s.d_out + kTrailer),
                                (unsigned long long *)s.d_out, s.d_scratch, (int64_t)scratch_cap, s.st, dev, &s.aux);
         if (rc) return rc;
         k_ext_finish<<<1, 1, 0, s.st>>>((const ExtHdr *)s.d_scratch, (int32_t *)(s.d_out + 8));
         return CSBWA_OK;
     }
-    int build_graph(Slot &s)
+    int build_graph(Slot &s, int v)
     {
-        if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }
+        if (s.graph[v]) { cudaGraphExecDestroy(s.graph[v]); s.graph[v] = nullptr; }
         cudaGraph_t g = nullptr;
         CU_TRY(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue(s, nullptr, 0, 0, true);
+        int rc = enqueue(s, nullptr, 0, 0, true, v);
         cudaError_t e = cudaStreamEndCapture(s.st, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess || !g) return fail(CSBWA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&s.graph, g, 0);
+        e = cudaGraphInstantiate(&s.graph[v], g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) { s.graph = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-        s.graph_core = ext_core();
+        if (e != cudaSuccess) { s.graph[v] = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+        s.graph_core[v] = ext_core();
         return CSBWA_OK;
     }
 
@@ -706,15 +730,16 @@ struct CudaCoExec {
         Slot &s = slots[slot];
         CU_TRY(cudaSetDevice(dev));
         const size_t reply = (size_t)n_tasks * 20;
-        if (use_graph && (!s.graph || s.graph_core != ext_core())) {
-            int rc = build_graph(s);
+        const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks);
+        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core())) {
+            int rc = build_graph(s, v);
             if (rc) return rc;
         }
         CU_TRY(cudaEventRecord(s.ev[0], s.st));
         CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, span, cudaMemcpyHostToDevice, s.st));
         CU_TRY(cudaEventRecord(s.ev[1], s.st));
         if (use_graph) {
-            CU_TRY(cudaGraphLaunch(s.graph, s.st));
+            CU_TRY(cudaGraphLaunch(s.graph[v], s.st));
         } else {
             int rc = enqueue(s, calls, n_calls, n_tasks, false);
             if (rc) return rc;

@@ -221,33 +221,51 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
     }
 }
 
-__global__ void k_ext_scan(ExtHdr *hdr)
+// Launch with EXT_SCAN_BD threads (one block): half a block per side, EXT_SCAN_IPT consecutive bins per thread.
+// The scan sits on the critical path of every group, so all loads are issued at once: a serial warp loop
+// over 113 steps of dependent global loads took 65 us, a third of a small group's side pass.
+#define EXT_SCAN_BD 1024
+#define EXT_SCAN_IPT ((EXT_NBIN + EXT_SCAN_BD / 2 - 1) / (EXT_SCAN_BD / 2))
+__global__ void __launch_bounds__(EXT_SCAN_BD) k_ext_scan(ExtHdr *hdr)
 {
-    // one warp per side: descending exclusive prefix over the sort bins, 32 bins per step
-    const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (side >= 2) return;
-    uint32_t acc = 0;
-    for (int top = EXT_NBIN - 1; top >= 0; top -= 32) {
-        const int b = top - lane;                                  // lane 0 takes the highest bin of the step
-        const uint32_t v = b >= 0 ? hdr->hist[side][b] : 0u;
-        uint32_t incl = v;
+    // descending exclusive prefix over the sort bins: position q <-> bin EXT_NBIN - 1 - q
+    constexpr int HALF = EXT_SCAN_BD / 2, WARPS = HALF / 32;
+    __shared__ uint32_t s_warp[2][WARPS];
+    const int side = threadIdx.x / HALF, t = threadIdx.x % HALF, lane = t & 31, wid = t >> 5;
+    uint32_t v[EXT_SCAN_IPT], sum = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
-        }
+    for (int k = 0; k < EXT_SCAN_IPT; ++k) {
+        const int b = EXT_NBIN - 1 - (t * EXT_SCAN_IPT + k);
+        v[k] = b >= 0 ? hdr->hist[side][b] : 0u;
+        sum += v[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_warp[side][wid] = incl;
+    __syncthreads();
+    uint32_t acc = incl - sum;                                      // exclusive inside the warp
+    for (int w = 0; w < wid; ++w) acc += s_warp[side][w];
+#pragma unroll
+    for (int k = 0; k < EXT_SCAN_IPT; ++k) {
+        const int b = EXT_NBIN - 1 - (t * EXT_SCAN_IPT + k);
         if (b >= 0) {
-            hdr->base[side][b] = acc + incl - v;
+            hdr->base[side][b] = acc;
             hdr->cursor[side][b] = 0;
         }
-        acc += __shfl_sync(0xffffffffu, incl, 31);
+        acc += v[k];
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();                                                // base[] of this side is complete (block-wide: global writes visible)
+    if (t == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < WARPS; ++w) total += s_warp[side][w];
         // class 0 = the generic bin (first in the descending order), class k >= 1 starts at its top bin
         hdr->cls_beg[side][0] = 0;
         for (int c = 1; c < EXT_NCLS; ++c) hdr->cls_beg[side][c] = hdr->base[side][ext_class_top_bin(c)];
-        hdr->cls_beg[side][EXT_NCLS] = acc;
+        hdr->cls_beg[side][EXT_NCLS] = total;
         for (int c = 0; c < EXT_NCLS; ++c) hdr->work[side][c] = 0;
     }
 }

@@ -17,7 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=500_000)
     ap.add_argument("--threads", type=int, default=64)
-    ap.add_argument("--repeat", type=int, default=4, help="passes over the call list inside ONE csbwa_extend_calls")
+    ap.add_argument("--repeat", type=int, default=40, help="passes over the call list inside ONE csbwa_extend_calls")
     ap.add_argument("--reads-per-call", type=int, default=4096)
     ap.add_argument("--split", type=int, default=0, help="1: one csbwa_extend_calls per pass (what bench.py's step does)")
     args = ap.parse_args()

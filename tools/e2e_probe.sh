@@ -1,6 +1,9 @@
-# coalesced host seam under concurrent callers: sync mode x slots x threads (diagnosis; not a benchmark line)
+# coalesced host seam under concurrent callers: "threads slots sync [ENV=VAL ...]" per line (diagnosis; not a benchmark line)
 export CSBWA_CO_TIMING=1
-for cfg in ${PROBE_CFGS:-"64 16 sleep" "64 16 sleep2" "64 20 sleep2" "64 12 sleep2" "128 16 sleep2" "16 16 sleep2" "16 16 spin"}; do
-set -- $cfg
-CSBWA_CO_SYNC=$3 CSBWA_CO_SLOTS=$2 timeout 200 python tools/e2e_probe.py --pairs 250000 --threads $1 --repeat 8 2>&1 | grep -v Warning | tail -2
-done
+while read -r t s m extra; do
+[ -z "$t" ] && continue
+echo "== threads $t slots $s sync $m $extra"
+env CSBWA_CO_SYNC=$m CSBWA_CO_SLOTS=$s $extra timeout 200 python tools/e2e_probe.py --pairs 250000 --threads $t --repeat 40 2>&1 | grep -v Warning | tail -2
+done <<CFG
+${PROBE_CFGS:-64 16 sleep}
+CFG

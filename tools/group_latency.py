@@ -23,7 +23,8 @@ def main():
     w = pkg.workload.ext_workload(65536, 151, 20_000_000, 0.01, 400, 50, 20260103, reads_per_call=4096)
     bufs = w["bufs"]
     out = []
-    for k in (1, 2, 4, 8, 16, 32):
+    ks = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (1, 2, 4, 8, 16, 32)
+    for k in ks:
         sel = bufs[:k]
         nt = [int(np.frombuffer(b[8:12].tobytes(), dtype="<i4")[0]) for b in sel]
         tab = np.zeros(k, dtype=pkg._lib.CALL_DTYPE)
