@@ -301,6 +301,37 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
     assert "direct-ok" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("env", [{"CSBWA_CO_SYNC": "spin", "CSBWA_CO_SLOTS": "3"},
+                                 {"CSBWA_CO_SYNC": "yield", "CSBWA_CO_ONE_GRAPH": "1"},
+                                 {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_SLOTS": "2"}])
+def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):
+    """The host seam's tuning knobs (how submission threads wait, slots, graph variants, no graph) never change
+    a bit: 12 caller threads, calls of three different sizes so that groups of all graph size classes occur."""
+    import subprocess, sys, os
+    code = (
+        "import importlib,sys,ctypes as C,numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "pkg=importlib.import_module('cloud-scale-bwamem_b200')\n"
+        "from oracle import oracle as O\n"
+        "L=pkg.lib()\n"
+        "bufs=[]\n"
+        "for rpc,pairs in ((512,4096),(4096,16384),(32768,65536)):\n"
+        "    bufs+=pkg.workload.ext_workload(pairs,151,500000,0.01,400,50,5,reads_per_call=rpc)['bufs'][:12]\n"
+        "nt=[int(np.frombuffer(b[8:12].tobytes(),dtype='<i4')[0]) for b in bufs]\n"
+        "outs=[np.zeros(10*n,dtype=np.int16) for n in nt]\n"
+        "ip=(C.c_void_p*len(bufs))(*[b.ctypes.data for b in bufs]); op=(C.c_void_p*len(bufs))(*[o.ctypes.data for o in outs])\n"
+        "isz=np.array([b.size for b in bufs],dtype=np.int32); osz=np.array([o.size for o in outs],dtype=np.int32)\n"
+        "for _ in range(3):\n"
+        "    assert L.csbwa_extend_calls(ip,isz.ctypes.data,op,osz.ctypes.data,len(bufs),12,0)==0, L.csbwa_last_error()\n"
+        "for b,o in zip(bufs,outs):\n"
+        "    assert np.array_equal(o,O.extend_wire(b,n_threads=8)[0])\n"
+        "assert pkg.stats()['ext_groups']>0\n"
+        "L.csbwa_shutdown()\n"
+        "print('knobs-ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert "knobs-ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_large_batch_properties(pkg, oracle, gpu):
     """Size-independent properties at a BASELINE-scale call (32768 reads in one call):
     determinism, exact cell count, every task answered exactly once, invariants of ExtRet."""
