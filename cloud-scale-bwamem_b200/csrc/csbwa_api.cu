@@ -632,6 +632,7 @@ struct CudaCoExec {
     // (520-560 GCUPS).  A blocking-sync event wakes 0.4 ms late, one polling thread for all groups fights the
     // submissions for the driver lock: both measured slower (tools/e2e_probe.sh).
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
+    // (Shorter timer slack or naps than the defaults -- 50 us, 20 us -- were measured 3-5 % slower: more polling.)
     int sync_mode = 0;          // 0 query + short sleeps, 1 query + sched_yield, 2 spin in the driver
     std::vector<Slot> slots;
 
