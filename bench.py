@@ -180,9 +180,10 @@ def run_reference_arm(args, pkg):
         "impl": "reference", "metric": "seed-extension SW throughput (whole job)", "value": gcups, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": config_block(args, n_pairs),
+        "config": config_block(args, args.pairs),          # the b200 arm's config; the sample is stated below
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
-                         "sample": "%d seam calls (%d tasks) of the C2 workload per step" % (n_calls, n_tasks)},
+                         "sample": "%d seam calls (%d tasks) per step, drawn from %d pairs generated with the "
+                                   "workload's own generator and parameters" % (n_calls, n_tasks, n_pairs)},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "read_pairs_per_s": (n_calls * READS_PER_CALL / 2) / (t_total / args.steps),
         "gpu_launches": 0,
