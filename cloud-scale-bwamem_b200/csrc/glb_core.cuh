@@ -18,19 +18,23 @@ constexpr int GLB_MINUS_INF = -0x40000000;   // S/util/SWUtil.scala:28
 struct GlbInt2 { int h, e; };
 
 struct GlbCigar {                     // pushCigar (:401-414) into a bounded buffer
+    // the operation being extended stays in a register (`run`); it is written once, when the next
+    // operation starts or at finish() -- a read-modify-write of out[n-1] per backtrace step put a dependent
+    // global load + store on every step
     uint32_t *out;
-    int cap, n, last_op, overflow;
-    CSW_HD void init(uint32_t *o, int c) { out = o; cap = c; n = 0; last_op = -1; overflow = 0; }
+    uint32_t run;                     // len << 4 | op of entry n - 1 (valid when n > 0)
+    int cap, n, overflow;
+    CSW_HD void init(uint32_t *o, int c) { out = o; cap = c; n = 0; run = 0; overflow = 0; }
+    CSW_HD void flush()
+    {
+        if (n > 0) { if (n - 1 < cap) out[n - 1] = run; else overflow = 1; }
+    }
     CSW_HD void push(int op, int len)
     {
-        if (n == 0 || op != last_op) {
-            if (n < cap) out[n] = ((uint32_t)len << 4) | (uint32_t)op; else overflow = 1;
-            ++n;
-            last_op = op;
-        } else if (n - 1 < cap) {
-            out[n - 1] += (uint32_t)len << 4;
-        }
+        if (n > 0 && (uint32_t)op == (run & 15u)) run += (uint32_t)len << 4;
+        else { flush(); run = ((uint32_t)len << 4) | (uint32_t)op; ++n; }
     }
+    CSW_HD void finish() { flush(); }
 };
 
 // returns the score; n_cigar = -1 if the CIGAR did not fit, -2 if the backtrace left the band
@@ -110,6 +114,7 @@ CSW_HD int sw_global_thread(const SwOpt &o, const uint8_t *q, int qlen, const ui
         if (i >= 0) cb.push(2, i + 1);
         if (k >= 0) cb.push(1, k + 1);
     }
+    cb.finish();
     if (!cb.overflow && !bad)
         for (int a = 0; a < (cb.n >> 1); ++a) { uint32_t tmp = cigar[a]; cigar[a] = cigar[cb.n - 1 - a]; cigar[cb.n - 1 - a] = tmp; }
     n_cigar = bad ? -2 : (cb.overflow ? -1 : cb.n);

@@ -31,13 +31,13 @@ __global__ void k_glb_setup(GlbHdr *hdr)
     }
 }
 
-// smem_pairs: column pairs of the p2 core's shared-memory rows ({H2,E2} records first, then the
-// selectors; pair p of thread t at [p * blockDim + t]: conflict free for any band position).
-// Jobs the p2 core is eligible for (glb_p2.cuh) and that fit use it; the rest run the scalar int32
-// core on the warp's global slice.
+// Shared memory of the p2 core: ring_pairs {H2,E2} records per thread first (a ring, glb_p2.cuh), then
+// sel_pairs 16-bit selectors per thread; entry p of thread t at [p * blockDim + t]: conflict free for any
+// band position.  Jobs the p2 core is eligible for (glb_p2.cuh) and that fit both use it; the rest run the
+// scalar int32 core on the warp's global slice.
 __global__ void __launch_bounds__(64)
 k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, GlbHdr *hdr, char *slices,
-      long long max_he_cols, long long max_z_cells, int smem_pairs, int32_t *__restrict__ res2,
+      long long max_he_cols, long long max_z_cells, int ring_pairs, int sel_pairs, int32_t *__restrict__ res2,
       uint32_t *__restrict__ cigars, unsigned long long *cells_acc)
 {
     extern __shared__ uint4 glb_smem4[];
@@ -50,7 +50,7 @@ k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, 
     char *slice = slices + (size_t)warp_id * glb_warp_bytes(max_he_cols, max_z_cells);
     GlbInt2 *he_g = (GlbInt2 *)slice + lane;
     GP2Pair *he_s = (GP2Pair *)glb_smem4 + threadIdx.x;
-    uint16_t *sel_s = (uint16_t *)((GP2Pair *)glb_smem4 + (size_t)smem_pairs * blockDim.x) + threadIdx.x;
+    uint16_t *sel_s = (uint16_t *)((GP2Pair *)glb_smem4 + (size_t)ring_pairs * blockDim.x) + threadIdx.x;
     char *zbase = slice + (size_t)max_he_cols * 32 * sizeof(GlbInt2);
     unsigned long long my_cells = 0;
     for (;;) {
@@ -68,8 +68,9 @@ k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, 
                 glb_z_cells(jb.q_len, jb.t_len, jb.w) > max_z_cells) {
                 atomicExch(&hdr->err, -7);
                 nc = -3;
-            } else if (glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w) && glb_p2_pairs(jb.q_len) <= smem_pairs) {
-                score = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he_s, sel_s,
+            } else if (glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w) && glb_p2_pairs(jb.q_len) <= sel_pairs &&
+                       glb_p2_ring_need(jb.q_len, jb.t_len, jb.w) <= ring_pairs) {
+                score = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he_s, ring_pairs, sel_s,
                                      (int)blockDim.x, (uint16_t *)zbase + lane, 32, cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
             } else {
                 score = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w,

@@ -18,6 +18,10 @@
 //     into a warp-interleaved matrix indexed by (row, pair - first pair of the row's band).
 // Band edges that split a pair (one per row in the steady state, because the band is 2w+1 wide) are
 // handled by a scalar single-column step.
+//   * the {H2, E2} records live in a RING of `ring` pairs (pair p at slot p mod ring): a row only
+//     touches the pairs of columns beg-1 .. end, at most w + 3 of them, so a 151-column query with the
+//     bwaGenCigar2 band (w ~ 36) needs 40 records instead of 76 and half again as many jobs fit an SM's
+//     shared memory.  A job whose pairs all fit (pairs <= ring) never wraps and is laid out as before.
 #pragma once
 #include "glb_core.cuh"
 
@@ -35,6 +39,16 @@ CSW_HD bool glb_p2_eligible(const SwOpt &o, int qlen, int tlen, int w)
            o.e_ins >= 0 && o.e_ins <= 8;
 }
 CSW_HD int glb_p2_pairs(int qlen) { return (qlen + 2) >> 1; }
+// ring slots a job needs: all its pairs, or -- when every row has a band that ends at the last column in
+// the last row (|tlen - qlen| <= w: the caller's contract, bwaGenCigar2 passes w >= |tlen - qlen| + 3) --
+// only the pairs one row can touch (columns beg-1 .. end: at most w + 3 pairs, one spare)
+CSW_HD int glb_p2_ring_need(int qlen, int tlen, int w)
+{
+    const int np = glb_p2_pairs(qlen);
+    const int d = tlen > qlen ? tlen - qlen : qlen - tlen;
+    if (d <= w && w + 4 < np) return w + 4;
+    return np;
+}
 // direction matrix: 16-bit entries per (row, pair of the row's band); pairs per row
 CSW_HD int glb_p2_row_pairs(int qlen, int w)
 {
@@ -60,9 +74,13 @@ CSW_HD void glb_p2_stage_query(uint16_t *sel, int stride, const uint8_t *q, int 
 // returns the score; n_cigar = -1 if the CIGAR did not fit, -2 if the backtrace left the band.
 // he: pair p at he[p * stride]; sel likewise; z16: entry e at z16[e * z_stride]
 CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int w,
-                        GP2Pair *he, uint16_t *sel, int stride, uint16_t *z16, long long z_stride,
+                        GP2Pair *he, int ring, uint16_t *sel, int stride, uint16_t *z16, long long z_stride,
                         uint32_t *cigar, int cigar_cap, int &n_cigar, long long &cells)
 {
+    // ring >= glb_p2_ring_need(qlen, tlen, w) (caller).  pr = lowest pair the current row can touch,
+    // sr = its slot (pr mod ring); both stay 0 for a job that never wraps.
+    const bool wraps = glb_p2_pairs(qlen) > ring;
+    int pr = 0, sr = 0;
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
     const int e_del = o.e_del, e_ins = o.e_ins;
     const int ne_ins = -e_ins;
@@ -73,11 +91,14 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
     uint16_t *h16 = (uint16_t *)he;
     const size_t pstr = (size_t)stride * 4;
     uint8_t *z8 = (uint8_t *)z16;
-#define GP2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
-#define GP2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
+#define GP2_SLOT(p) (sr + ((p) - pr) >= ring ? sr + ((p) - pr) - ring : sr + ((p) - pr))
+#define GP2_H(c) h16[(size_t)GP2_SLOT((c) >> 1) * pstr + ((c) & 1)]
+#define GP2_E(c) h16[(size_t)GP2_SLOT((c) >> 1) * pstr + 2 + ((c) & 1)]
     glb_p2_stage_query(sel, stride, q, qlen);
     {   // first row (:271-285): Hs[c] = eh[c+1].h, E = -inf everywhere
-        const int np = glb_p2_pairs(qlen);
+        // with a ring only the first `ring` pairs exist yet: columns right of w + 1 are never read before
+        // the row that brings them into the band has set their E to -inf (GP2_E(end) below)
+        const int np = wraps ? ring : glb_p2_pairs(qlen);
         for (int p = 0; p < np; ++p) {
             const int c0 = 2 * p, c1 = 2 * p + 1;
             const int lo = (c0 + 1 <= w) ? GP2_BIAS - (o.o_ins + e_ins * (c0 + 1)) : GP2_MINF;
@@ -102,6 +123,11 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
         const int h1i = beg == 0 ? GP2_BIAS - (o.o_del + e_del * (i + 1)) : GP2_MINF;
         uint16_t *zrow = z16 + (long long)i * rp * z_stride;
         const int pb0 = beg >> 1;                       // first pair of the row's band
+        if (wraps) {                                    // the window moves right by at most one pair per row
+            const int prn = (beg > 0 ? beg - 1 : 0) >> 1;
+            sr += prn - pr; if (sr >= ring) sr -= ring;
+            pr = prn;
+        }
         if (beg < end) {
             int dg = beg == 0 ? hm1 : (int)GP2_H(beg - 1);
             int f = GP2_MINF, c = beg;
@@ -136,12 +162,15 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
             int p = c >> 1;
             if (p < pe) {
                 uint32_t hprev2 = (uint32_t)dg << 16;
-                GP2Pair *ph = he + (size_t)p * stride;
+                const int s0 = GP2_SLOT(p);
+                GP2Pair *ph = he + (size_t)s0 * stride;
                 const uint16_t *ps = sel + (size_t)p * stride;
                 uint16_t *pz = zrow + (long long)(p - pb0) * z_stride;
-                GP2Pair cur = *ph;
                 uint32_t sl = ld_u16(ps);
-                for (; p < pe; ++p) {
+                int pend = p + (ring - s0) < pe ? p + (ring - s0) : pe;   // the pairs up to the end of the ring, then the rest
+                for (;;) {
+                GP2Pair cur = *ph;
+                for (; p < pend; ++p) {
                     const GP2Pair x = cur;
                     const uint32_t sx = sl;
                     cur = ph[stride];
@@ -172,6 +201,9 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
                     f = fn;
                     ph += stride; ps += stride; pz += z_stride;
                 }
+                if (p >= pe) break;
+                ph = he; pend = pe;                                // wrapped: continue at slot 0
+                }
                 dg = (int)(hprev2 >> 16);
                 c = 2 * pe;
             }
@@ -193,26 +225,46 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
     int which = 0, bad = 0;
     const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
     int i = tlen - 1, k = (i + w + 1 < qlen) ? i + w : qlen - 1;
-    while (i >= 0 && k >= 0) {
-        const int beg = i > w ? i - w : 0;
-        const int col = k - beg;
-        if (col < 0 || col >= n_col) { bad = 1; break; }
-        const int d = z8[((long long)i * rp + ((k >> 1) - (beg >> 1))) * z_stride * 2 + (k & 1)];
-        which = (d >> (which << 1)) & 3;
-        if (which == 0) { cb.push(0, 1); --i; --k; }
-        else if (which == 1) { cb.push(2, 1); --i; }
-        else { cb.push(1, 1); --k; }
+    // The direction matrix of a job is far larger than L1 and every step depends on the byte read by the step
+    // before it, so a cell-by-cell walk is one DRAM round trip per step.  The path is a diagonal most of the time:
+    // the bytes of the next GP2_BT diagonal cells are fetched at once (independent loads) and consumed while the
+    // path stays on the diagonal; any other move ends the batch.  Same cells, same order, same result.
+    constexpr int GP2_BT = 8;
+    constexpr uint32_t GP2_NOZ = 0xffu;                 // not a direction byte (those use 6 bits): cell outside the band
+    while (i >= 0 && k >= 0 && !bad) {
+        uint32_t dz[GP2_BT];
+#pragma unroll
+        for (int s = 0; s < GP2_BT; ++s) {
+            const int ii = i - s, kk = k - s;
+            const int beg = ii > w ? ii - w : 0;
+            const int col = kk - beg;
+            dz[s] = GP2_NOZ;
+            if (ii >= 0 && kk >= 0 && col >= 0 && col < n_col)
+                dz[s] = z8[((long long)ii * rp + ((kk >> 1) - (beg >> 1))) * z_stride * 2 + (kk & 1)];
+        }
+#pragma unroll
+        for (int s = 0; s < GP2_BT; ++s) {              // here (i, k) is s steps down the diagonal of the batch
+            if (i < 0 || k < 0) break;
+            if (dz[s] == GP2_NOZ) { bad = 1; break; }
+            which = (int)(dz[s] >> (which << 1)) & 3;
+            if (which == 0) { cb.push(0, 1); --i; --k; continue; }
+            if (which == 1) { cb.push(2, 1); --i; }
+            else { cb.push(1, 1); --k; }
+            break;
+        }
     }
     if (!bad) {
         if (i >= 0) cb.push(2, i + 1);
         if (k >= 0) cb.push(1, k + 1);
     }
+    cb.finish();
     if (!cb.overflow && !bad)
         for (int a = 0; a < (cb.n >> 1); ++a) { uint32_t tmp = cigar[a]; cigar[a] = cigar[cb.n - 1 - a]; cigar[cb.n - 1 - a] = tmp; }
     n_cigar = bad ? -2 : (cb.overflow ? -1 : cb.n);
     cells = ncell;
 #undef GP2_H
 #undef GP2_E
+#undef GP2_SLOT
     return score;
 }
 

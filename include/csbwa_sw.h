@@ -286,6 +286,14 @@ int64_t csbwa_global_scratch_bytes(int32_t n_jobs, int32_t max_q_len, int64_t ma
 int csbwa_global_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
                               int64_t max_z_cells, void *d_res, void *d_cigars, void *d_cells,
                               void *d_scratch, int64_t scratch_bytes, void *stream);
+/* Same, with a hint that lets more jobs share an SM: max_ring_pairs = max over jobs of
+ * csbwa_global_ring_pairs() -- the {H,E} records a job keeps in shared memory (a ring over the columns
+ * one row of its band can touch, w + 4 column pairs when |t_len - q_len| <= w, else every pair of the
+ * query).  <= 0 = unknown (what csbwa_global_batch_device assumes): every pair gets a record. */
+int32_t csbwa_global_ring_pairs(int32_t q_len, int32_t t_len, int32_t w);
+int csbwa_global_batch_device_ring(const void *d_jobs, int32_t n_jobs, const void *d_seqs, int32_t max_q_len,
+                                   int64_t max_z_cells, int32_t max_ring_pairs, void *d_res, void *d_cigars,
+                                   void *d_cells, void *d_scratch, int64_t scratch_bytes, void *stream);
 int csbwa_global_launches_per_call(void);
 
 /* ---- roofline denominator: measured integer-pipe issue rate ----------------

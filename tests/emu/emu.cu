@@ -273,7 +273,7 @@ extern "C" void emu_co_destroy(void *h)
 extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, int32_t *res2, uint32_t *cigars, int64_t *cells,
                                 int force_scalar, int32_t *n_p2)
 {
-    int np2 = 0;
+    int np2 = 0, nring = 0;              // jobs on the column-pair core / of those, jobs whose ring wraps
     SwOpt o;
     fill_default_opt(o);
     finish_opt(o);
@@ -284,13 +284,20 @@ extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, 
         int nc = 0;
         long long c = 0;
         int sc;
-        if (!force_scalar && glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w)) {
+        if (force_scalar != 1 && glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w)) {
+            // the {H2,E2} ring gets exactly the records the job asks for (force_scalar == 2: every pair a record,
+            // the layout without wrap-around), poisoned, plus the one record past the end the pair loop prefetches
             const int stride = 3, np = glb_p2_pairs(jb.q_len);
-            std::vector<GP2Pair> hp((size_t)(np + 1) * stride);
+            const int ring = force_scalar == 2 ? np : glb_p2_ring_need(jb.q_len, jb.t_len, jb.w);
+            std::vector<GP2Pair> hp((size_t)(ring + 2) * stride);
             for (auto &x : hp) { x.h2 = 0xdeadbeefu; x.e2 = 0xdeadbeefu; }
             std::vector<uint16_t> sl((size_t)(np + 1) * stride, 0xdead);
-            sc = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, hp.data() + 1, sl.data() + 2, stride,
+            sc = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, hp.data() + 1, ring, sl.data() + 2, stride,
                               (uint16_t *)z.data() + 1, 3, cigars + jb.cigar_off, jb.cigar_cap, nc, c);
+            for (int g = 0; g < stride; ++g)        // nothing written past the ring (the other threads' columns are untouched too)
+                if (g != 1 && (hp[(size_t)(ring) * stride + g].h2 != 0xdeadbeefu || hp[g].h2 != 0xdeadbeefu)) return -9;
+            if (hp[(size_t)ring * stride + 1].h2 != 0xdeadbeefu || hp[(size_t)(ring + 1) * stride + 1].h2 != 0xdeadbeefu) return -9;
+            if (ring < np) ++nring;
             ++np2;
         } else
         sc = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he.data(), 1, z.data(), 1,
@@ -298,6 +305,6 @@ extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, 
         res2[2 * k] = sc; res2[2 * k + 1] = nc;
         if (cells) cells[k] = c;
     }
-    if (n_p2) *n_p2 = np2;
+    if (n_p2) *n_p2 = np2 | (nring << 16);
     return 0;
 }

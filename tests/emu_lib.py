@@ -118,7 +118,7 @@ GJOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t
                        ("cigar_cap", "<i4"), ("cigar_off", "<i8")])
 
 
-def emu_global_batch(emu, jobs, seqs, force_scalar=False, want_count=False):
+def emu_global_batch(emu, jobs, seqs, force_scalar=False, want_count=False, no_ring=False):
     jobs = np.ascontiguousarray(jobs, dtype=GJOB_DTYPE)
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     n = len(jobs)
@@ -129,8 +129,8 @@ def emu_global_batch(emu, jobs, seqs, force_scalar=False, want_count=False):
     emu.lib.emu_global_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     np2 = C.c_int32(0)
     rc = emu.lib.emu_global_batch(jobs.ctypes.data, n, seqs.ctypes.data, res.ctypes.data, cig.ctypes.data, cells.ctypes.data,
-                                  int(force_scalar), C.addressof(np2))
+                                  2 if no_ring else int(force_scalar), C.addressof(np2))
     assert rc == 0
-    if want_count:
-        return res, cig, cells, np2.value
+    if want_count:                      # (jobs on the column-pair core, of those: jobs whose {H,E} ring wraps)
+        return res, cig, cells, np2.value & 0xffff, np2.value >> 16
     return res, cig, cells

@@ -61,11 +61,13 @@ def test_emu_vs_oracle(pkg, oracle, emu):
     triples += [(r(30), r(30), 0), (r(254), r(260), 30), (r(255), r(250), 30), (r(151), r(151), 200)]
     jobs, seqs = build_gjobs(triples, oracle.GJOB_DTYPE)
     ref, rcig, rcells = oracle.global_batch(jobs, seqs)
-    got, gcig, gcells, np2 = emu_lib.emu_global_batch(emu, jobs, seqs, want_count=True)     # p2 core where eligible
+    got, gcig, gcells, np2, nring = emu_lib.emu_global_batch(emu, jobs, seqs, want_count=True)     # p2 core where eligible
     bad = np.flatnonzero((got != ref).any(axis=1))
     assert len(bad) == 0, (bad[:5], got[bad[:3]], ref[bad[:3]], [(len(triples[b][0]), len(triples[b][1]), triples[b][2]) for b in bad[:3]])
     assert np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
-    assert np2 >= 250
+    assert np2 >= 250 and nring >= 60          # many of them with an {H,E} ring shorter than the query (wrap-around)
+    got, gcig, gcells = emu_lib.emu_global_batch(emu, jobs, seqs, no_ring=True)                     # every pair a record
+    assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
     got, gcig, gcells = emu_lib.emu_global_batch(emu, jobs, seqs, force_scalar=True)          # scalar int32 core
     assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
     # outside the caller's contract (bwaGenCigar2 always passes w >= |tlen - qlen|): the last cell lies outside
@@ -83,6 +85,27 @@ def test_emu_vs_oracle(pkg, oracle, emu):
     assert np.array_equal(r2, g2) and (r2[:, 1] == -1).any()
 
 
+def test_emu_ring_wraps(pkg, oracle, emu):
+    """The {H,E} ring of the column-pair core (glb_p2.cuh): narrow bands on long queries, so the ring is a small
+    fraction of the query and wraps many times; targets shorter and longer than the query, band edges of both
+    parities, |t_len - q_len| == w (the last row's band just reaches the last column)."""
+    rng = np.random.default_rng(95)
+    triples = []
+    for L in (64, 101, 151, 250, 254):
+        for _ in range(40):
+            q = rng.integers(0, 4, L).astype(np.uint8)
+            t = util.mutate(rng, q, float(rng.choice([0, 0.02, 0.1])), indel=float(rng.choice([0.1, 0.5])))
+            if len(t) == 0:
+                t = q[:1].copy()
+            d = abs(len(t) - len(q))
+            triples.append((q, t, d + int(rng.choice([0, 1, 2, 3, 7, 12, 36]))))
+    jobs, seqs = build_gjobs(triples, oracle.GJOB_DTYPE)
+    ref, rcig, rcells = oracle.global_batch(jobs, seqs)
+    got, gcig, gcells, np2, nring = emu_lib.emu_global_batch(emu, jobs, seqs, want_count=True)
+    assert np2 == len(triples) and nring >= 180
+    assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
+
+
 @pytest.mark.gpu
 def test_gpu_vs_oracle(pkg, oracle):
     rng = np.random.default_rng(93)
@@ -97,6 +120,31 @@ def test_gpu_vs_oracle(pkg, oracle):
     assert pkg.stats()["glb_cells"] - before == int(rcells.sum())
     sc, cg = pkg.jni.SWGlobal(triples[0][0], triples[0][1], triples[0][2])
     assert (sc, cg) == oracle.sw_global(*triples[0])[:2]
+
+
+@pytest.mark.gpu
+def test_gpu_ring_wraps(pkg, oracle):
+    """Batches in which every job fits a short {H,E} ring, so the launch is sized for the ring and the long queries
+    wrap around it many times (the host picks the ring from the jobs' bands)."""
+    rng = np.random.default_rng(96)
+    triples = []
+    for L in (101, 151, 250, 254):
+        for _ in range(500):
+            q = rng.integers(0, 4, L).astype(np.uint8)
+            t = util.mutate(rng, q, float(rng.choice([0, 0.02, 0.1])), indel=float(rng.choice([0.1, 0.5])))
+            if len(t) == 0:
+                t = q[:1].copy()
+            triples.append((q, t, abs(len(t) - len(q)) + int(rng.choice([0, 1, 2, 3, 7, 12, 36]))))
+    jobs, seqs = build_gjobs(triples, pkg._lib.GJOB_DTYPE, cap=96)
+    L_ = pkg.lib()
+    assert max(L_.csbwa_global_ring_pairs(len(q), len(t), w) for q, t, w in triples) < 80      # < the 128 pairs of 254 columns
+    ref, rcig, rcells = oracle.global_batch(jobs, seqs, n_threads=8)
+    before = pkg.stats()["glb_cells"]
+    got, gcig = pkg.jni.swGlobalBatch(jobs, seqs, device=0)
+    assert np.array_equal(got, ref)
+    for k in range(len(jobs)):
+        assert cig_of(got, gcig, jobs, k) == cig_of(ref, rcig, jobs, k)
+    assert pkg.stats()["glb_cells"] - before == int(rcells.sum())
 
 
 @pytest.mark.gpu

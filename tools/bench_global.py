@@ -44,6 +44,13 @@ def run(pkg, pairs=65536, L_read=151, steps=3, cpu_sample_jobs=4096, device=0, p
     max_z = int(((ncol + 4) * jobs["t_len"]).max())            # == max csbwa_global_z_cells(q_len, t_len, w)
     kmax = int(np.argmax((ncol + 4) * jobs["t_len"]))
     assert max_z == L.csbwa_global_z_cells(int(jobs["q_len"][kmax]), int(jobs["t_len"][kmax]), int(jobs["w"][kmax]))
+    # {H,E} ring records per thread: max csbwa_global_ring_pairs over the jobs (w + 4 when |t_len - q_len| <= w)
+    dlen = np.abs(jobs["t_len"].astype(np.int64) - jobs["q_len"])
+    npairs = (jobs["q_len"].astype(np.int64) + 2) >> 1
+    ring = np.where((dlen <= jobs["w"]) & (jobs["w"] + 4 < npairs), jobs["w"] + 4, npairs)
+    max_ring = 0 if os.environ.get("CSBWA_GLB_NO_RING") else int(ring.max())
+    kr = int(np.argmax(ring))
+    assert int(ring[kr]) == L.csbwa_global_ring_pairs(int(jobs["q_len"][kr]), int(jobs["t_len"][kr]), int(jobs["w"][kr]))
     with torch.cuda.device(dev):
         d_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(dev)
         d_seqs = torch.from_numpy(seqs).to(dev)
@@ -55,8 +62,8 @@ def run(pkg, pairs=65536, L_read=151, steps=3, cpu_sample_jobs=4096, device=0, p
         st = torch.cuda.current_stream().cuda_stream
 
         def step():
-            rc = L.csbwa_global_batch_device(d_jobs.data_ptr(), n, d_seqs.data_ptr(), max_q, max_z, d_res.data_ptr(), d_cig.data_ptr(),
-                                             d_cells.data_ptr(), scr.data_ptr(), scr_b, C.c_void_p(st))
+            rc = L.csbwa_global_batch_device_ring(d_jobs.data_ptr(), n, d_seqs.data_ptr(), max_q, max_z, max_ring, d_res.data_ptr(),
+                                                  d_cig.data_ptr(), d_cells.data_ptr(), scr.data_ptr(), scr_b, C.c_void_p(st))
             assert rc == 0, L.csbwa_last_error()
 
         for _ in range(2):
