@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcsbwa_sw.so")
 SOURCES = ["csbwa_api.cu"]
-DEPS = ["csbwa_api.cu", "sw_common.cuh", "ext_core.cuh", "ext_kernels.cuh", "aln_core.cuh", "aln_kernels.cuh",
-        "csbwa_jni.inc", os.path.join("..", "..", "include", "csbwa_sw.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".inc"))) + \
+       [os.path.join("..", "..", "include", "csbwa_sw.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1372,7 +1372,7 @@ extern "C" int csbwa_global_launches_per_call(void) { return kGlbLaunches; }
 
 extern "C" int64_t csbwa_global_z_cells(int32_t q_len, int32_t t_len, int32_t w) { return (int64_t)glb_z_cells(q_len, t_len, w); }
 
-static const int kGlbBlock = 64;         // threads per block of k_glb
+static const int kGlbBlock = GLB_BLOCK;  // threads per block of k_glb
 static const int kGlbWarpsPerSm = 16;    // most persistent warps per SM any launch uses (scratch is sized for it)
 static int glb_grid_warps(int n, int sms, int warps_per_sm)
 {

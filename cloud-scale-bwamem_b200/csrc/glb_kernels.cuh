@@ -35,7 +35,9 @@ __global__ void k_glb_setup(GlbHdr *hdr)
 // sel_pairs 16-bit selectors per thread; entry p of thread t at [p * blockDim + t]: conflict free for any
 // band position.  Jobs the p2 core is eligible for (glb_p2.cuh) and that fit both use it; the rest run the
 // scalar int32 core on the warp's global slice.
-__global__ void __launch_bounds__(64)
+constexpr int GLB_BLOCK = 64;            // threads per block of k_glb (the p2 core's compile-time stride)
+
+__global__ void __launch_bounds__(GLB_BLOCK)
 k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, GlbHdr *hdr, char *slices,
       long long max_he_cols, long long max_z_cells, int ring_pairs, int sel_pairs, int32_t *__restrict__ res2,
       uint32_t *__restrict__ cigars, unsigned long long *cells_acc)
@@ -70,7 +72,7 @@ k_glb(const GlbJob *__restrict__ jobs, int n, const uint8_t *__restrict__ seqs, 
                 nc = -3;
             } else if (glb_p2_eligible(o, jb.q_len, jb.t_len, jb.w) && glb_p2_pairs(jb.q_len) <= sel_pairs &&
                        glb_p2_ring_need(jb.q_len, jb.t_len, jb.w) <= ring_pairs) {
-                score = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he_s, ring_pairs, sel_s,
+                score = sw_global_p2<GLB_BLOCK>(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, he_s, ring_pairs, sel_s,
                                      (int)blockDim.x, (uint16_t *)zbase + lane, 32, cigars + jb.cigar_off, jb.cigar_cap, nc, cells);
             } else {
                 score = sw_global_thread(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w,

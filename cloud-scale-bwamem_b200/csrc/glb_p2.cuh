@@ -60,11 +60,16 @@ CSW_HD long long glb_p2_z_entries(int qlen, int tlen, int w) { return (long long
 CSW_HD void glb_p2_stage_query(uint16_t *sel, int stride, const uint8_t *q, int qlen)
 {
     const int np = glb_p2_pairs(qlen);
-    for (int p = 0; p < np; ++p) {
-        int q0 = 0, q1 = 0;
-        if (2 * p < qlen) { q0 = q[2 * p]; if (q0 > 4) q0 = 4; }
-        if (2 * p + 1 < qlen) { q1 = q[2 * p + 1]; if (q1 > 4) q1 = 4; }
-        sel[(size_t)p * stride] = (uint16_t)(((uint32_t)q0 | ((uint32_t)q1 << 8)) * 0x11u + 0x8080u);
+    for (int p0 = 0; p0 < np; p0 += 4) {                // eight byte loads in flight per round trip
+        int b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b[u] = (2 * p0 + u < qlen) ? (int)q[2 * p0 + u] : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u >= np) break;
+            const int q0 = b[2 * u] > 4 ? 4 : b[2 * u], q1 = b[2 * u + 1] > 4 ? 4 : b[2 * u + 1];
+            sel[(size_t)(p0 + u) * stride] = (uint16_t)(((uint32_t)q0 | ((uint32_t)q1 << 8)) * 0x11u + 0x8080u);
+        }
     }
 #if defined(__CUDA_ARCH__)
     asm volatile("" ::: "memory");
@@ -73,10 +78,14 @@ CSW_HD void glb_p2_stage_query(uint16_t *sel, int stride, const uint8_t *q, int 
 
 // returns the score; n_cigar = -1 if the CIGAR did not fit, -2 if the backtrace left the band.
 // he: pair p at he[p * stride]; sel likewise; z16: entry e at z16[e * z_stride]
+// STRIDE: compile-time element stride between consecutive pairs (threads per block on the device, so the
+// unrolled pair loop addresses shared memory with immediate offsets); 0 = use stride_rt
+template <int STRIDE>
 CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int w,
-                        GP2Pair *he, int ring, uint16_t *sel, int stride, uint16_t *z16, long long z_stride,
+                        GP2Pair *he, int ring, uint16_t *sel, int stride_rt, uint16_t *z16, long long z_stride,
                         uint32_t *cigar, int cigar_cap, int &n_cigar, long long &cells)
 {
+    const int stride = STRIDE ? STRIDE : stride_rt;
     // ring >= glb_p2_ring_need(qlen, tlen, w) (caller).  pr = lowest pair the current row can touch,
     // sr = its slot (pr mod ring); both stay 0 for a job that never wraps.
     const bool wraps = glb_p2_pairs(qlen) > ring;
@@ -197,7 +206,7 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
                     GP2Pair y;
                     y.h2 = h2; y.e2 = en2;
                     *ph = y;
-                    *pz = (uint16_t)((d2 & 0xffu) | ((d2 >> 8) & 0xff00u));
+                    *pz = (uint16_t)(d2 | (d2 >> 8));                              // each lane's byte uses 6 bits: no masks needed
                     f = fn;
                     ph += stride; ps += stride; pz += z_stride;
                 }

@@ -292,7 +292,7 @@ extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, 
             std::vector<GP2Pair> hp((size_t)(ring + 2) * stride);
             for (auto &x : hp) { x.h2 = 0xdeadbeefu; x.e2 = 0xdeadbeefu; }
             std::vector<uint16_t> sl((size_t)(np + 1) * stride, 0xdead);
-            sc = sw_global_p2(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, hp.data() + 1, ring, sl.data() + 2, stride,
+            sc = sw_global_p2<0>(o, seqs + jb.q_off, jb.q_len, seqs + jb.t_off, jb.t_len, jb.w, hp.data() + 1, ring, sl.data() + 2, stride,
                               (uint16_t *)z.data() + 1, 3, cigars + jb.cigar_off, jb.cigar_cap, nc, c);
             for (int g = 0; g < stride; ++g)        // nothing written past the ring (the other threads' columns are untouched too)
                 if (g != 1 && (hp[(size_t)(ring) * stride + g].h2 != 0xdeadbeefu || hp[g].h2 != 0xdeadbeefu)) return -9;
