@@ -492,7 +492,7 @@ def main():
             # and the next row of the path (SWGlobal / CIGAR generation), short run
             try:
                 from tools import bench_global
-                g = bench_global.run(pkg, pairs=32768, steps=3, cpu_sample_jobs=1024, device=local, peaks=peaks)
+                g = bench_global.run(pkg, pairs=65536, steps=3, cpu_sample_jobs=1024, device=local, peaks=peaks)
                 line["swglobal"] = {k: g[k] for k in ("workload", "jobs", "kernel_gcups", "reads_per_s", "roofline_frac_alu",
                                                       "cpu_oracle_gcups", "parity_sample_ok")}
             except Exception as e:
