@@ -151,6 +151,23 @@ struct AlnMsgP {
 
 constexpr int ALN_G = 16;      // lanes per job
 
+// Row-invariant operands of AlnLaneP::step, built once per pass.  Passing the options by reference made
+// every step reload them: the kernel keeps them in global memory and stores the b-array to global memory
+// in the same loop, so the loads cannot be hoisted.
+struct AlnStepK {
+    int ne_ins;
+    uint32_t ne_del2, noe_del2, noe_ins2, sn2;
+    CSW_HD void init(const SwOpt &o)
+    {
+        ne_ins = -o.e_ins;
+        ne_del2 = pk16(-o.e_del, -o.e_del);
+        noe_del2 = pk16(-(o.o_del + o.e_del), -(o.o_del + o.e_del));
+        noe_ins2 = pk16(-(o.o_ins + o.e_ins), -(o.o_ins + o.e_ins));
+        const uint32_t sn = (uint32_t)(int)(int8_t)(o.thi[0] & 0xffu) & 0xffffu;   // mat[4][*]: the target base is N
+        sn2 = sn | (sn << 16);
+    }
+};
+
 template <int P>
 struct AlnLaneP {
     uint32_t H2[P], E2[P];
@@ -177,16 +194,12 @@ struct AlnLaneP {
 
     // one target row.  TN: the target base is N (every score is mat[4][*] = thi[0])
     template <bool TN>
-    CSW_HD void step(const SwOpt &o, const AlnMsgP &in, AlnMsgP &out)
+    CSW_HD void step(const AlnStepK &kk, const AlnMsgP &in, AlnMsgP &out)
     {
-        const int ne_ins = -o.e_ins;
-        const uint32_t ne_del2 = pk16(-o.e_del, -o.e_del);
-        const uint32_t noe_del2 = pk16(-(o.o_del + o.e_del), -(o.o_del + o.e_del));
-        const uint32_t noe_ins2 = pk16(-(o.o_ins + o.e_ins), -(o.o_ins + o.e_ins));
+        const int ne_ins = kk.ne_ins;
+        const uint32_t ne_del2 = kk.ne_del2, noe_del2 = kk.noe_del2, noe_ins2 = kk.noe_ins2, sn2 = kk.sn2;
         const uint32_t t = in.ft >> 16;
         const uint32_t sel = t * 0x1111u + 0xc480u;        // {a[t], sign, b[t], sign}
-        const uint32_t sn = (uint32_t)(int)(int8_t)(o.thi[0] & 0xffu) & 0xffffu;
-        const uint32_t sn2 = sn | (sn << 16);
         int f = (int)(in.ft & 0xffffu);
         uint32_t key2 = in.key2;
         uint32_t hprev2 = dprev;

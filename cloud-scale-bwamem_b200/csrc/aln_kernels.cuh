@@ -110,6 +110,8 @@ __device__ __forceinline__ void aln_half_pass(const SwOpt &o, bool act, const ui
     L.setup(o, q, qn, rev, qe, gl);
     AlnBook bk;
     bk.init(o, xtra);
+    AlnStepK kk;                         // by value: registers for the whole pass
+    kk.init(o);
     int rows = 0;
     AlnMsgP out;
     out.h = 0; out.ft = 0; out.key2 = 0;
@@ -135,8 +137,8 @@ __device__ __forceinline__ void aln_half_pass(const SwOpt &o, bool act, const ui
         if (gl == 0) { in.h = 0; in.ft = (uint32_t)t0 << 16; in.key2 = 0; }
         const int row = s - gl;
         if (!gdone && row >= 0 && row < tlen && gl <= LQ) {
-            if ((in.ft >> 16) > 3) L.template step<true>(o, in, out);
-            else L.template step<false>(o, in, out);
+            if ((in.ft >> 16) > 3) L.template step<true>(kk, in, out);
+            else L.template step<false>(kk, in, out);
             if (gl == LQ) {
                 int m, mj;
                 aln_decode_key2(out.key2, m, mj);
@@ -191,7 +193,7 @@ __device__ __forceinline__ void aln_second_best_group(const SwOpt &o, bool act, 
 }
 
 template <int P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, P <= 4 ? 6 : (P == 5 ? 5 : 4))   // blocks per SM the register count must keep: 6 / 5 / 4 (<= 85 / 102 / 128 registers)
 k_aln_half(const AlnJob *__restrict__ jobs, const uint8_t *__restrict__ seqs, AlnScratch sc,
            int32_t *__restrict__ out, unsigned long long *cells_acc, int cls)
 {

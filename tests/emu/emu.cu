@@ -109,6 +109,8 @@ static void emu_half_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, in
     AlnLaneP<P> L[ALN_G];
     for (int l = 0; l < ALN_G; ++l) L[l].setup(o, q, qn, rev, qe, l);
     bk.init(o, xtra);
+    AlnStepK kk;
+    kk.init(o);
     AlnMsgP out[ALN_G], nout[ALN_G];
     memset(out, 0, sizeof out);
     const int LQ = (qn - 1) / (2 * P);
@@ -124,8 +126,8 @@ static void emu_half_pass(const SwOpt &o, const uint8_t *q, const uint8_t *t, in
             nout[l] = out[l];
             const int row = s - l;
             if (row >= 0 && row < tlen && l <= LQ) {
-                if ((in.ft >> 16) > 3) L[l].template step<true>(o, in, nout[l]);
-                else L[l].template step<false>(o, in, nout[l]);
+                if ((in.ft >> 16) > 3) L[l].template step<true>(kk, in, nout[l]);
+                else L[l].template step<false>(kk, in, nout[l]);
                 if (l == LQ) {
                     int m, mj;
                     aln_decode_key2(nout[l].key2, m, mj);
