@@ -106,6 +106,34 @@ def test_emu_ring_wraps(pkg, oracle, emu):
     assert np.array_equal(got, ref) and np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
 
 
+def test_emu_ring_small_sweep(pkg, oracle, emu):
+    """Every small shape around the ring's size rule (ring = w + 4 pairs when |t - q| <= w and that is fewer than
+    the query's pairs): q = 1..48, t = q - 3 .. q + 3, w from |t - q| upward, similar and unrelated sequences."""
+    rng = np.random.default_rng(97)
+    triples = []
+    for ql in range(1, 49):
+        for d in range(-3, 4):
+            tl = ql + d
+            if tl < 1:
+                continue
+            for w in (abs(d), abs(d) + 1, abs(d) + 2, 6):
+                q = rng.integers(0, 4, ql).astype(np.uint8)
+                t = rng.integers(0, 4, tl).astype(np.uint8)
+                if rng.random() < 0.7:
+                    n = min(ql, tl)
+                    t[:n] = q[:n]
+                    if n > 4 and rng.random() < 0.5:
+                        k = int(rng.integers(1, n - 1)); t[k:n] = q[k - 1:n - 1]      # shifted tail: forces a gap
+                triples.append((q, t, w))
+    jobs, seqs = build_gjobs(triples, oracle.GJOB_DTYPE)
+    ref, rcig, rcells = oracle.global_batch(jobs, seqs)
+    got, gcig, gcells, np2, nring = emu_lib.emu_global_batch(emu, jobs, seqs, want_count=True)
+    assert np2 == len(triples) and nring >= 300
+    bad = np.flatnonzero((got != ref).any(axis=1))
+    assert len(bad) == 0, [(len(triples[b][0]), len(triples[b][1]), triples[b][2]) for b in bad[:5]]
+    assert np.array_equal(gcig, rcig) and np.array_equal(gcells, rcells)
+
+
 @pytest.mark.gpu
 def test_gpu_vs_oracle(pkg, oracle):
     rng = np.random.default_rng(93)
