@@ -178,40 +178,40 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
                 uint32_t sl = ld_u16(ps);
                 int pend = p + (ring - s0) < pe ? p + (ring - s0) : pe;   // the pairs up to the end of the ring, then the rest
                 for (;;) {
-                GP2Pair cur = *ph;
-                for (; p < pend; ++p) {
-                    const GP2Pair x = cur;
-                    const uint32_t sx = sl;
-                    cur = ph[stride];
-                    sl = ld_u16(ps + stride);
-                    const uint32_t s2 = prmt(tlo, thi, sx);
-                    const uint32_t hd2 = funnel16(hprev2, x.h2);
-                    hprev2 = x.h2;
-                    const uint32_t m2 = addmax2(hd2, s2, low2);                    // M = Hd + S
-                    const uint32_t hm2 = max2(m2, x.e2);
-                    const uint32_t tt2 = addmax2(m2, noe_del2, low2);              // M - oeDel
-                    const uint32_t en2 = addmax2(x.e2, ne_del2, tt2);              // E' = max(E - eDel, M - oeDel)
-                    const uint32_t g2 = addmax2(m2, noe_ins2, low2);               // M - oeIns
-                    const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));         // F(i, 2p+1)
-                    const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));            // F(i, 2p+2)
-                    const uint32_t fin2 = umad((uint32_t)t1, 65536u, (uint32_t)f); // F entering each column
-                    const uint32_t fout2 = umad((uint32_t)fn, 65536u, (uint32_t)t1);   // F leaving each column
-                    const uint32_t h2 = max2(hm2, fin2);
-                    // direction bits: (a > b) == min(max(a, b) - b, 1), lane-wise on positive values
-                    const uint32_t c1 = umin2(hm2 - m2, one2);                     // E > M
-                    const uint32_t c2 = umin2(h2 - hm2, one2);                     // F > max(M, E)
-                    const uint32_t c3 = umin2(en2 - tt2, one2);                    // E - eDel > M - oeDel
-                    const uint32_t c4 = umin2(fout2 - g2, one2);                   // F - eIns > M - oeIns
-                    const uint32_t d2 = umad(c4, 32u, umad(c3, 4u, umax2(c1, c2 + c2)));
-                    GP2Pair y;
-                    y.h2 = h2; y.e2 = en2;
-                    *ph = y;
-                    *pz = (uint16_t)(d2 | (d2 >> 8));                              // each lane's byte uses 6 bits: no masks needed
-                    f = fn;
-                    ph += stride; ps += stride; pz += z_stride;
-                }
-                if (p >= pe) break;
-                ph = he; pend = pe;                                // wrapped: continue at slot 0
+                    GP2Pair cur = *ph;
+                    for (; p < pend; ++p) {
+                        const GP2Pair x = cur;
+                        const uint32_t sx = sl;
+                        cur = ph[stride];
+                        sl = ld_u16(ps + stride);
+                        const uint32_t s2 = prmt(tlo, thi, sx);
+                        const uint32_t hd2 = funnel16(hprev2, x.h2);
+                        hprev2 = x.h2;
+                        const uint32_t m2 = addmax2(hd2, s2, low2);                    // M = Hd + S
+                        const uint32_t hm2 = max2(m2, x.e2);
+                        const uint32_t tt2 = addmax2(m2, noe_del2, low2);              // M - oeDel
+                        const uint32_t en2 = addmax2(x.e2, ne_del2, tt2);              // E' = max(E - eDel, M - oeDel)
+                        const uint32_t g2 = addmax2(m2, noe_ins2, low2);               // M - oeIns
+                        const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));         // F(i, 2p+1)
+                        const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));            // F(i, 2p+2)
+                        const uint32_t fin2 = umad((uint32_t)t1, 65536u, (uint32_t)f); // F entering each column
+                        const uint32_t fout2 = umad((uint32_t)fn, 65536u, (uint32_t)t1);   // F leaving each column
+                        const uint32_t h2 = max2(hm2, fin2);
+                        // direction bits: (a > b) == min(max(a, b) - b, 1), lane-wise on positive values
+                        const uint32_t c1 = umin2(hm2 - m2, one2);                     // E > M
+                        const uint32_t c2 = umin2(h2 - hm2, one2);                     // F > max(M, E)
+                        const uint32_t c3 = umin2(en2 - tt2, one2);                    // E - eDel > M - oeDel
+                        const uint32_t c4 = umin2(fout2 - g2, one2);                   // F - eIns > M - oeIns
+                        const uint32_t d2 = umad(c4, 32u, umad(c3, 4u, umax2(c1, c2 + c2)));
+                        GP2Pair y;
+                        y.h2 = h2; y.e2 = en2;
+                        *ph = y;
+                        *pz = (uint16_t)(d2 | (d2 >> 8));                              // each lane's byte uses 6 bits: no masks needed
+                        f = fn;
+                        ph += stride; ps += stride; pz += z_stride;
+                    }
+                    if (p >= pe) break;
+                    ph = he; pend = pe;                                // wrapped: continue at slot 0
                 }
                 dg = (int)(hprev2 >> 16);
                 c = 2 * pe;
