@@ -69,10 +69,12 @@ def task_count(buf):
     return int(np.frombuffer(buf[8:12].tobytes(), dtype="<i4")[0])
 
 
-def gen_workload(pkg, n_pairs, rank, ref=None):
+def gen_workload(pkg, n_pairs, rank, ref=None, numpy_packer=False):
+    """numpy_packer: build the wire buffers with the numpy restatement of the packer (byte-identical, tested) --
+    the reference arm uses it so that its process never maps libcsbwa_sw.so."""
     return pkg.workload.ext_workload(n_pairs, CFG["L"], CFG["ref_bp"], CFG["eps"], CFG["mu"], CFG["sigma"],
                                      pkg.shard.shard_seed(CFG["seed"], rank), reads_per_call=READS_PER_CALL, ref=ref,
-                                     chunk_pairs=max(65536, READS_PER_CALL // 2))
+                                     chunk_pairs=max(65536, READS_PER_CALL // 2), numpy_packer=numpy_packer)
 
 
 class ClockSampler:
@@ -163,7 +165,7 @@ def run_reference_arm(args, pkg):
     O.build()
     cores = os.cpu_count() or 1
     n_pairs = min(args.pairs, 262144)
-    w = gen_workload(pkg, n_pairs, 0)
+    w = gen_workload(pkg, n_pairs, 0, numpy_packer=True)
     n_calls = size_cpu_sample(w["bufs"], cores, True, args.cpu_step_seconds)
     sample = w["bufs"][:n_calls]
     for _ in range(args.warmup):
@@ -211,7 +213,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU")
     ap.add_argument("--streams", type=int, default=6)
     ap.add_argument("--group-calls", type=int, default=32, help="seam calls coalesced per launch sequence (resident leg)")
-    ap.add_argument("--threads", type=int, default=0, help="caller threads of the e2e leg (0 = auto)")
+    ap.add_argument("--threads", type=int, default=0, help="caller threads per GPU of the e2e leg (0 = 64)")
+    ap.add_argument("--e2e-seconds", type=float, default=3.0, help="minimum length of one timed e2e repetition")
     ap.add_argument("--cpu-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--reads-per-call", type=int, default=4096, help="experiments only; the headline is 4096")
@@ -355,46 +358,75 @@ def main():
     result_dev = d_out.cpu().numpy()
 
     # ---- e2e through the C ABI with host buffers ----
-    # concurrent seam callers: Spark task threads block inside the JNI call, so executors oversubscribe the
-    # cores (4 task threads per core here, at most 64 per GPU); reported as e2e.caller_threads_per_gpu
-    nthreads = args.threads or max(4, min(64, 4 * (os.cpu_count() or 4) // max(1, world)))
-    outs = [np.zeros(10 * n, dtype=np.int16) for n in ntasks]
+    # Concurrent seam callers: Spark task threads block inside the JNI call, so executors oversubscribe the cores.
+    # The number of caller threads PER GPU is the same at every N (default 64), reported as e2e.caller_threads_per_gpu.
+    # Headline leg: the callers' wire and reply buffers live in pinned host memory (csbwa_host_alloc), which the seam
+    # serves without a staging copy; every step still moves every input byte host -> device and every reply byte
+    # device -> host inside the timed region.  Second leg (e2e.pageable): ordinary numpy buffers, one staging copy each
+    # way made by the caller thread -- what a JVM caller gets through GetByteArrayRegion / SetShortArrayRegion.
+    nthreads = args.threads or 64
     in_sizes1 = [b.size for b in bufs]
-    out_sizes1 = [o.size for o in outs]
+    out_sizes1 = [10 * n for n in ntasks]
+    expect = result_dev
 
-    def e2e_steps(k):
-        # nthreads native caller threads, each issuing blocking seam calls (csbwa_extend_batch), over k passes of the
-        # shard's call list as ONE stream of calls: executor task threads persist from batch to batch
-        in_ptrs = (C.c_void_p * (len(bufs) * k))(*([b.ctypes.data for b in bufs] * k))
-        out_ptrs = (C.c_void_p * (len(bufs) * k))(*([o.ctypes.data for o in outs] * k))
-        in_sizes = np.array(in_sizes1 * k, dtype=np.int32)
-        out_sizes = np.array(out_sizes1 * k, dtype=np.int32)
-        return lambda: L.csbwa_extend_calls(in_ptrs, in_sizes.ctypes.data, out_ptrs, out_sizes.ctypes.data, len(bufs) * k, nthreads, local)
+    def e2e_leg(ins, outs, min_seconds, reps):
+        """reps timed repetitions of >= min_seconds each; a repetition = `passes` passes over the shard's call list as
+        ONE stream of blocking calls from nthreads native caller threads (executor task threads persist from batch to
+        batch).  Returns per-repetition seconds, passes per repetition, and the stats delta of the last repetition."""
+        def mk(k):
+            in_ptrs = (C.c_void_p * (len(ins) * k))(*([b.ctypes.data for b in ins] * k))
+            out_ptrs = (C.c_void_p * (len(ins) * k))(*([o.ctypes.data for o in outs] * k))
+            isz = np.array(in_sizes1 * k, dtype=np.int32)
+            osz = np.array(out_sizes1 * k, dtype=np.int32)
+            keep = (in_ptrs, out_ptrs, isz, osz)
+            return lambda: (keep, L.csbwa_extend_calls(in_ptrs, isz.ctypes.data, out_ptrs, osz.ctypes.data, len(ins) * k, nthreads, local))[1]
 
-    def e2e_run(fn):
-        rc = fn()
-        if rc != 0:
-            raise RuntimeError("e2e call failed: %d %s" % (rc, L.csbwa_last_error().decode()))
+        def run(fn):
+            rc = fn()
+            if rc != 0:
+                raise RuntimeError("e2e call failed: %d %s" % (rc, L.csbwa_last_error().decode()))
 
-    st_e2e0 = st_e2e1 = pkg.stats()
-    e2e_s = float("nan")
-    if not args.no_e2e:
-        e2e_run(e2e_steps(2))
-        timed = e2e_steps(args.steps)
-        torch.cuda.synchronize()
-        st_e2e0 = pkg.stats()
-        if world > 1:
-            dist.barrier()
+        run(mk(2))                                           # warm-up (graphs, staging, thread start-up)
         t0 = time.perf_counter()
-        e2e_run(timed)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        st_e2e1 = pkg.stats()
-        if world > 1:
-            dist.barrier()
+        run(mk(2))
+        est = (time.perf_counter() - t0) / 2
+        passes = int(max(args.steps, np.ceil(min_seconds / max(est, 1e-4))))
+        if world > 1:                                        # same pass count on every rank
+            passes = int(pkg.shard.reduce_job([passes], [0], device=dev)[0][0])
+        timed = mk(passes)
+        secs, st0, st1 = [], None, None
+        for _ in range(reps):
+            for o in outs:
+                o[:] = 0                                     # a stale reply from an earlier pass cannot satisfy the check below
+            torch.cuda.synchronize()
+            st0 = pkg.stats()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            run(timed)
+            torch.cuda.synchronize()
+            secs.append(time.perf_counter() - t0)
+            st1 = pkg.stats()
+            if world > 1:
+                dist.barrier()
+            if not np.array_equal(np.concatenate(outs), expect):
+                raise RuntimeError("device-resident and host-buffer paths disagree")
+        return secs, passes, st0, st1
+
+    e2e_secs, e2e_passes, st_e2e0, st_e2e1 = [float("nan")], 1, pkg.stats(), pkg.stats()
+    pg_secs, pg_passes = [float("nan")], 1
+    if not args.no_e2e:
+        arena = pkg._lib.PinnedArena(sum(x + 512 for x in in_sizes1) + sum(2 * x + 512 for x in out_sizes1) + 4096)
+        pin_ins, pin_outs = [], []
+        for b, n in zip(bufs, out_sizes1):
+            pi = arena.take(b.size)
+            pi[:] = b
+            pin_ins.append(pi)
+            pin_outs.append(arena.take(2 * n, np.int16))
+        e2e_secs, e2e_passes, st_e2e0, st_e2e1 = e2e_leg(pin_ins, pin_outs, args.e2e_seconds, 3)
+        pg_outs = [np.zeros(n, dtype=np.int16) for n in out_sizes1]
+        pg_secs, pg_passes, _, _ = e2e_leg(bufs, pg_outs, args.e2e_seconds / 2, 1)
     clocks = sampler.stop()
-    if not args.no_e2e and not np.array_equal(np.concatenate(outs), result_dev):
-        raise RuntimeError("device-resident and host-buffer paths disagree")
 
     # ---- phase split of the dominant kernel (roofline) ----
     ms3 = (C.c_float * 3)()
@@ -413,8 +445,12 @@ def main():
     st_after = pkg.stats()
 
     # ---- reduce over ranks ----
-    (ms_total_max, e2e_ms_max), (cells_all, tasks_all, reads_all, inb_all, outb_all) = pkg.shard.reduce_job(
-        [ms_total, e2e_s * 1e3], [cells_total, total_tasks, w["n_reads"], in_bytes, out_bytes], device=dev)
+    red_t, (cells_all, tasks_all, reads_all, inb_all, outb_all) = pkg.shard.reduce_job(
+        [ms_total] + [x * 1e3 for x in e2e_secs] + [x * 1e3 for x in pg_secs],
+        [cells_total, total_tasks, w["n_reads"], in_bytes, out_bytes], device=dev)
+    ms_total_max = red_t[0]
+    e2e_rep_ms = red_t[1:1 + len(e2e_secs)]                  # per repetition: max over ranks
+    pg_rep_ms = red_t[1 + len(e2e_secs):]
 
     if rank == 0:
         peaks = {}
@@ -427,16 +463,24 @@ def main():
         if os.path.exists(mp_path):
             mp = json.load(open(mp_path))
         gcups = cells_all / (ms_total_max * 1e-3) / 1e9
-        e2e_gcups = cells_all / (e2e_ms_max * 1e-3) / 1e9
+        cells_step_all = cells_all / args.steps               # all ranks, one pass over every shard
+        e2e_rep_gcups = [cells_step_all * e2e_passes / (t * 1e-3) / 1e9 for t in e2e_rep_ms]
+        e2e_gcups = float(np.median(e2e_rep_gcups))
+        e2e_ms_step = float(np.median(e2e_rep_ms)) / e2e_passes
+        pg_gcups = cells_step_all * pg_passes / (pg_rep_ms[0] * 1e-3) / 1e9
+        n_sub = max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])
         alu_peak = peaks.get("VIADDMNMX")                      # 1e9 ALU-pipe thread-instr/s (max-class ops)
         dual_peak = peaks.get("IADD3")                         # adds dual-issue onto the FMA pipe as IMAD.IADD
         side_ms = left + right
         side_gops = sample_cells * OPS_PER_CELL / (side_ms * 1e-3) / 1e9 if side_ms > 0 else None
         hbm_peak = mp.get("hbm_gbs", 6650.0)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        # DRAM bytes of the dominant kernels come from an ncu capture of the CURRENT round's build (profiles/,
+        # written by tools/ncu_traffic.py from the committed CSV); bench.py cannot run ncu inside itself
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch_sequence"), tj.get("source")
         line = {
             "metric": "seed-extension SW throughput (whole job)", "value": gcups, "unit": "GCUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
@@ -445,36 +489,45 @@ def main():
             "read_pairs_per_s": (reads_all / 2) * args.steps / (ms_total_max * 1e-3),
             "tasks_per_step": tasks_all, "cells_per_step": cells_all / args.steps,
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": inb_all, "d2h_bytes_per_step": outb_all,
-                    "read_pairs_per_s": (reads_all / 2) * args.steps / (e2e_ms_max * 1e-3),
-                    "ms_per_step": e2e_ms_max / args.steps, "caller_threads_per_gpu": nthreads,
-                    "api": "csbwa_extend_batch (host buffers, pinned staging, H2D+kernels+D2H per call); the K steps are "
-                           "one stream of blocking calls from caller threads that persist across steps"},
+                    "read_pairs_per_s": (reads_all / 2) / (e2e_ms_step * 1e-3),
+                    "ms_per_step": e2e_ms_step, "caller_threads_per_gpu": nthreads,
+                    "repetitions_gcups": e2e_rep_gcups, "min": min(e2e_rep_gcups), "max": max(e2e_rep_gcups),
+                    "passes_per_repetition": e2e_passes, "seconds_per_repetition": [t * 1e-3 for t in e2e_rep_ms],
+                    "host_buffers": "pinned (csbwa_host_alloc): zero host staging copies; every pass moves all input bytes H2D and "
+                                    "all reply bytes D2H inside the timed region",
+                    "zero_copy_calls_frac": (st_e2e1["ext_zero_copy_calls"] - st_e2e0["ext_zero_copy_calls"]) /
+                                            max(1, st_e2e1["ext_calls"] - st_e2e0["ext_calls"]),
+                    "pageable": {"value": pg_gcups, "unit": "GCUPS", "passes": pg_passes, "seconds": pg_rep_ms[0] * 1e-3,
+                                 "host_buffers": "ordinary numpy arrays: one staging copy each way by the caller thread"},
+                    "api": "csbwa_extend_batch (blocking, host buffers; concurrent calls coalesced into one device submission: "
+                           "gather kernel H2D + launch sequence + scatter kernel D2H per group); value = median of 3 repetitions, "
+                           "each one stream of blocking calls from caller threads that persist across passes"},
             "gpu_launches": int(kernels_per_step * args.steps * world),
             "ext_core": {0: "u8, one column per step",
                          1: "p2 s16x2 (two adjacent query columns per DPX instruction)"}.get(ext_mode),
             "cuda_graph": graph is not None, "streams": nstreams, "calls_per_launch_sequence": gsz,
-            "e2e_calls_per_device_submission": ((st_e2e1["ext_calls"] - st_e2e0["ext_calls"]) /
-                                                max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
-            "e2e_ms_per_device_submission": ((st_e2e1["host_ms"] - st_e2e0["host_ms"]) /
-                                             max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])),
-            "e2e_device_ms_per_submission": {k: (st_e2e1[k] - st_e2e0[k]) / max(1, st_e2e1["ext_groups"] - st_e2e0["ext_groups"])
-                                             for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+            "e2e_calls_per_device_submission": (st_e2e1["ext_calls"] - st_e2e0["ext_calls"]) / n_sub,
+            "e2e_ms_launch_to_done_per_submission": (st_e2e1["host_ms"] - st_e2e0["host_ms"]) / n_sub,
             "host_cpus": os.cpu_count(),
             "clocks": clocks,
             "roofline": {
                 "bound": "int_alu", "kernel": "k_ext_side (left + right, all size classes)",
-                "achieved": gcups * OPS_PER_CELL, "peak": (alu_peak or 0), "unit": "Gop/s",
-                "frac": (gcups * OPS_PER_CELL / alu_peak) if alu_peak else None,
+                "achieved": gcups / world * OPS_PER_CELL, "peak": (alu_peak or 0), "unit": "Gop/s per GPU",
+                "frac": (gcups / world * OPS_PER_CELL / alu_peak) if alu_peak else None,
+                "frac_alu_pipe": (gcups / world * OPS_PER_CELL / alu_peak) if alu_peak else None,
+                "frac_dual_issue": (gcups / world * OPS_PER_CELL / dual_peak) if dual_peak else None,
                 "ops_per_cell": OPS_PER_CELL,
-                "how": "algorithmic int32 ops of the timed steps (13 x exact DP cells) / CUDA-event time of the steps; "
-                       "the side kernels overlap across streams, their share of a step is side_kernel_share",
+                "how": "PER GPU: algorithmic int32 ops of the timed steps (13 x exact DP cells, all ranks) / number of GPUs / "
+                       "CUDA-event time of the steps (max over ranks); the side kernels overlap across streams, their share of "
+                       "a step is side_kernel_share.  frac = frac_alu_pipe: against the measured max-class (VIADDMNMX) issue rate, "
+                       "one ALU pipe; frac_dual_issue: against the measured IADD3 rate, where adds dual-issue on the FMA pipe. "
+                       "Packed s16x2 instructions update two cells each, so neither fraction is a pipe-utilisation counter.",
                 "isolated_launch_gops": side_gops,
                 "isolated_launch_frac": (side_gops / alu_peak) if (side_gops and alu_peak) else None,
                 "peak_source": "measured here: dependent-free VIADDMNMX stream on all SMs (csbwa_int_peak), 1e9 thread-instr/s",
-                "frac_vs_dual_pipe_iadd3": (gcups * OPS_PER_CELL / dual_peak) if dual_peak else None,
                 "phase_ms_sample": {"prepare": prep, "left": left, "right": right, "groups": len(sample_groups),
                                     "side_kernel_share": (left + right) / max(prep + left + right, 1e-9)},
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "hbm": {"achieved": (inb_all + outb_all) / world * args.steps / (ms_total_max * 1e-3) / 1e9, "peak": hbm_peak,
                         "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json" if mp else "fallback"},
             },

@@ -33,13 +33,14 @@ EXPORTS = [
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
     "csbwa_global_batch_device", "csbwa_global_batch_device_ring", "csbwa_global_ring_pairs", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat", "csbwa_h2d_probe",
+    "csbwa_extend_batch_cb", "csbwa_host_alloc", "csbwa_host_free", "csbwa_host_register", "csbwa_host_unregister", "csbwa_host_is_pinned",
 ]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("ext_calls", "ext_tasks", "ext_cells", "ext_in_bytes", "ext_out_bytes",
                                          "aln_calls", "aln_jobs", "aln_cells", "aln_in_bytes", "aln_out_bytes",
-                                         "kernel_launches", "ext_groups", "glb_calls", "glb_jobs", "glb_cells")] + \
+                                         "kernel_launches", "ext_groups", "glb_calls", "glb_jobs", "glb_cells", "ext_zero_copy_calls")] + \
                [(n, C.c_double) for n in ("h2d_ms", "kernel_ms", "d2h_ms", "host_ms")]
 
 
@@ -106,6 +107,12 @@ def lib():
     L.csbwa_chain2aln_flat.restype = C.c_int
     L.csbwa_h2d_probe.argtypes = [i64, C.c_int, C.c_int, C.c_int, C.c_int]; L.csbwa_h2d_probe.restype = C.c_double
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
+    L.csbwa_extend_batch_cb.argtypes = [vp, i32, vp, vp, vp, C.c_int]; L.csbwa_extend_batch_cb.restype = C.c_int
+    L.csbwa_host_alloc.argtypes = [i64]; L.csbwa_host_alloc.restype = vp
+    L.csbwa_host_free.argtypes = [vp]; L.csbwa_host_free.restype = C.c_int
+    L.csbwa_host_register.argtypes = [vp, i64]; L.csbwa_host_register.restype = C.c_int
+    L.csbwa_host_unregister.argtypes = [vp]; L.csbwa_host_unregister.restype = C.c_int
+    L.csbwa_host_is_pinned.argtypes = [vp, i64]; L.csbwa_host_is_pinned.restype = C.c_int
     _lib = L
     return L
 
@@ -134,3 +141,32 @@ def int_peak(device=0):
         check(lib().csbwa_int_peak(device, i, C.byref(v)))
         out[name] = v.value
     return out
+
+
+class PinnedArena:
+    """Pinned, device-mapped host memory from csbwa_host_alloc, handed out as numpy views.  Seam calls whose
+    buffers live here are zero-copy on the host (include/csbwa_sw.h: csbwa_extend_batch)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().csbwa_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise CsbwaError(E_NOMEM, lib().csbwa_last_error().decode())
+        self._buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.mem = np.frombuffer(self._buf, dtype=np.uint8)
+        self.used = 0
+
+    def take(self, nbytes, dtype=np.uint8, align=256):
+        """A fresh view of nbytes bytes (aligned), as an array of dtype."""
+        off = (self.used + align - 1) & ~(align - 1)
+        if off + nbytes > self.nbytes:
+            raise MemoryError("pinned arena exhausted")
+        self.used = off + int(nbytes)
+        return self.mem[off:off + int(nbytes)].view(dtype)
+
+    def close(self):
+        if self.ptr:
+            self.mem = None
+            self._buf = None
+            lib().csbwa_host_free(self.ptr)
+            self.ptr = None

@@ -6,11 +6,12 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcsbwa_sw.so")
-SOURCES = ["csbwa_api.cu"]
+SOURCES = ["api_core.cu", "api_extend.cu", "api_align.cu", "api_global.cu", "api_pack.cu", "api_jni.cu"]
 DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".inc"))) + \
        [os.path.join("..", "..", "include", "csbwa_sw.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJDIR = os.path.join(HERE, "build")
 
 
 def _nvcc():
@@ -52,12 +53,26 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB):
             return LIB       # GPU box without toolkit changes: use the prebuilt library
         raise RuntimeError("nvcc not found and %s is not built" % LIB)
-    cmd = [nvcc] + NVCC_FLAGS
+    # one object per translation unit, compiled in parallel, then one link: a single .so, no -rdc
+    import concurrent.futures
+    os.makedirs(OBJDIR, exist_ok=True)
+    flags = list(NVCC_FLAGS)
     for inc in jni_include_dirs():
-        cmd += ["-I", inc]
+        flags += ["-I", inc]
     if jni_include_dirs():
-        cmd += ["-DCSBWA_WITH_JNI=1"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        flags += ["-DCSBWA_WITH_JNI=1"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, cwd=CSRC)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 2)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)

@@ -76,6 +76,7 @@ struct ExtHdr {
     int32_t err;
     int32_t core;                      // EXT_CORE_*
     int32_t pad_;
+    uint32_t bad_call_bits[8];         // bit c: call c (< 256) carried a record that points outside its buffer
     uint32_t hist[2][EXT_NBIN];
     uint32_t base[2][EXT_NBIN];        // start of each bin in the descending order
     uint32_t cursor[2][EXT_NBIN];
@@ -204,6 +205,8 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
         int bl = 0, br = 0;
         if (!ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
             atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
+            const int c = (int)(&cl - &ext_call(cs, 0));             // which call: the host seam fails only that one
+            if (c >= 0 && c < 256) atomicOr(&hdr->bad_call_bits[c >> 5], 1u << (c & 31));
         } else {
             // the right side's h0 is the left score, bounded by h0 + lq * max(mat)
             bl = ext_side_bin(sopt, t.lq, t.h0, core);

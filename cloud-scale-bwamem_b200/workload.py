@@ -118,11 +118,69 @@ def longest_seeds(rb, opt):
     return valid, seed6
 
 
-def pack_ext_calls(ref, rb, seed6, reads_per_call, opt=None):
+def pack_ext_from_seeds_np(reads, read_len, ref, seed6, o7):
+    """numpy restatement of csbwa_pack_ext_from_seeds (and so of the caller's packing, reference
+    S/worker1/MemChainToAlignBatched.scala:76-172, 500-563): byte-identical wire buffer, no native library
+    involved -- the reference arm of bench.py builds its workload with this so that its process never maps
+    libcsbwa_sw.so."""
+    s6 = np.asarray(seed6, dtype=np.int64)
+    n = len(s6)
+    rd, qb, ln, rbeg, r0, r1 = (s6[:, i] for i in range(6))
+    lq = qb
+    rq = read_len - (qb + ln)
+    lr = np.where(lq > 0, rbeg - r0, 0)
+    rr = np.where(rq > 0, r1 - (rbeg + ln), 0)
+    tot = lq + rq + lr + rr
+    words = ((tot + 1) // 2 + 3) // 4
+    pos = 8 + 8 * n + np.concatenate([[0], np.cumsum(words)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+    total_words = int(8 + 8 * n + words.sum())
+    out = np.zeros(total_words, dtype="<u4")
+    hdr = out[:8].view(np.uint8)
+    hdr[:7] = np.asarray(o7[:7], dtype=np.int64).astype(np.uint8)
+    out[2] = n
+    if n == 0:
+        return out.view(np.uint8)
+    o_del, e_del, o_ins, e_ins, c5, c3 = (int(o7[i]) for i in range(6))
+
+    def maxgap(q, clip, o, e):                      # ((q * maxMat + clip - o).toDouble / e + 1.0).toInt then .toShort
+        return np.trunc((q + clip - o) / float(e) + 1.0).astype(np.int64).astype(np.int16)
+
+    rec = np.zeros((n, 16), dtype="<i2")
+    rec[:, 0] = lq; rec[:, 1] = lr; rec[:, 2] = rq; rec[:, 3] = rr
+    rec[:, 4:6] = pos.astype("<i4").view("<i2").reshape(n, 2)
+    rec[:, 6] = ln; rec[:, 7] = qb; rec[:, 8] = ln
+    rec[:, 9] = np.arange(n, dtype=np.int64).astype(np.int16)
+    rec[:, 10] = maxgap(lq, c5, o_ins, e_ins); rec[:, 11] = maxgap(lq, c5, o_del, e_del)
+    rec[:, 12] = maxgap(rq, c3, o_ins, e_ins); rec[:, 13] = maxgap(rq, c3, o_del, e_del)
+    rec[:, 14:16] = np.arange(n, dtype="<i4").view("<i2").reshape(n, 2)
+    out[8:8 + 8 * n] = rec.reshape(-1).view("<u4")
+    # nibbles: wire order leftQ (reversed), rightQ, leftR (reversed), rightR
+    T = int(tot.sum())
+    rep = np.repeat(np.arange(n), tot)
+    w = np.arange(T, dtype=np.int64) - np.repeat(np.concatenate([[0], np.cumsum(tot)[:-1]]), tot)
+    lq_r, rq_r, lr_r = lq[rep], rq[rep], lr[rep]
+    qb_r, ln_r, rb_r, rd_r = qb[rep], ln[rep], rbeg[rep], rd[rep]
+    reads = np.asarray(reads).reshape(-1, read_len)
+    val = np.empty(T, dtype=np.uint8)
+    m0 = w < lq_r
+    m1 = ~m0 & (w < lq_r + rq_r)
+    m2 = ~m0 & ~m1 & (w < lq_r + rq_r + lr_r)
+    m3 = ~(m0 | m1 | m2)
+    val[m0] = reads[rd_r[m0], lq_r[m0] - 1 - w[m0]]
+    val[m1] = reads[rd_r[m1], qb_r[m1] + ln_r[m1] + (w[m1] - lq_r[m1])]
+    val[m2] = ref[rb_r[m2] - 1 - (w[m2] - lq_r[m2] - rq_r[m2])]
+    val[m3] = ref[rb_r[m3] + ln_r[m3] + (w[m3] - lq_r[m3] - rq_r[m3] - lr_r[m3])]
+    nib = np.zeros(int(words.sum()) * 8, dtype=np.uint32)
+    nib[np.repeat(np.concatenate([[0], np.cumsum(words * 8)[:-1]]), tot) + w] = val & 15
+    nib = nib.reshape(-1, 8)
+    out[8 + 8 * n:] = (nib << (28 - 4 * np.arange(8, dtype=np.uint32))[None, :]).sum(axis=1, dtype=np.uint32)
+    return out.view(np.uint8)
+
+
+def pack_ext_calls(ref, rb, seed6, reads_per_call, opt=None, numpy_packer=False):
     """Group tasks by read index into seam calls of `reads_per_call` reads (-bSWExtSize) and pack
-    each with the library's task builder.  Returns a list of uint8 wire buffers."""
+    each with the library's task builder (or its numpy restatement).  Returns a list of uint8 wire buffers."""
     opt = opt or MemOptType()
-    L = _lib.lib()
     o7 = opt.opt7()
     bufs = []
     G = len(ref)
@@ -131,10 +189,14 @@ def pack_ext_calls(ref, rb, seed6, reads_per_call, opt=None):
     seed6[:, 5] = np.clip(seed6[:, 5], 0, G)
     call_id = seed6[:, 0] // reads_per_call
     bounds = np.flatnonzero(np.diff(call_id)) + 1
+    L = None if numpy_packer else _lib.lib()
     for part in np.split(np.arange(len(seed6)), bounds):
         if len(part) == 0:
             continue
         s6 = np.ascontiguousarray(seed6[part])
+        if numpy_packer:
+            bufs.append(pack_ext_from_seeds_np(rb.reads, rb.L, ref, s6, o7))
+            continue
         nb = _lib.check(L.csbwa_pack_ext_from_seeds(len(s6), rb.reads.ctypes.data, rb.L, ref.ctypes.data, G,
                                                     s6.ctypes.data, o7.ctypes.data, None, 0))
         out = np.zeros(nb, dtype=np.uint8)
@@ -144,7 +206,7 @@ def pack_ext_calls(ref, rb, seed6, reads_per_call, opt=None):
     return bufs
 
 
-def ext_workload(n_pairs, L, ref_bp, eps, mu, sigma, seed, reads_per_call=4096, chunk_pairs=65536, ref=None):
+def ext_workload(n_pairs, L, ref_bp, eps, mu, sigma, seed, reads_per_call=4096, chunk_pairs=65536, ref=None, numpy_packer=False):
     """Extension workload of one config: list of wire buffers (one per seam call), plus counts."""
     opt = MemOptType()
     rng = np.random.default_rng(seed)
@@ -159,7 +221,7 @@ def ext_workload(n_pairs, L, ref_bp, eps, mu, sigma, seed, reads_per_call=4096, 
         s6 = seed6[valid]
         n_tasks += len(s6)
         n_reads += rb.n
-        bufs += pack_ext_calls(ref, rb, s6, reads_per_call, opt)
+        bufs += pack_ext_calls(ref, rb, s6, reads_per_call, opt, numpy_packer=numpy_packer)
         done += m
     return dict(bufs=bufs, n_tasks=n_tasks, n_reads=n_reads, n_pairs=n_pairs, L=L, ref=ref)
 

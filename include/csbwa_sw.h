@@ -86,6 +86,7 @@ typedef struct {
     int64_t kernel_launches;     /* our kernels only */
     int64_t ext_groups;          /* coalesced device submissions that served ext_calls */
     int64_t glb_calls, glb_jobs, glb_cells;
+    int64_t ext_zero_copy_calls; /* coalesced seam calls served without any host staging copy (pinned caller buffers) */
     double  h2d_ms, kernel_ms, d2h_ms, host_ms; /* CUDA-event / wall split, summed over calls */
 } csbwa_stats;
 
@@ -102,10 +103,35 @@ int csbwa_reset_stats(void);
 
 /* ---- seam (1): host buffers in, host buffers out ------------------------
  * Replaces Java_cs_ucla_edu_bwaspark_jni_SWExtendFPGAJNI_swExtendFPGAJNI
- * (F/sw_extend_fpga.c:116-193).  `in`/`out` are ordinary (pageable) host memory;
- * device = -1 picks a GPU round-robin per call.  Blocks until `out` is filled. */
+ * (F/sw_extend_fpga.c:116-193).  `in`/`out` are host memory; device = -1 picks a GPU round-robin
+ * per call.  Blocks until `out` is filled, like the reference's shim (:164-173).
+ * Calls that are pending at the same time are coalesced into one device submission.  Ordinary
+ * (pageable) buffers are copied once into / out of pinned staging by the calling thread; buffers
+ * that lie in pinned memory obtained from csbwa_host_alloc / csbwa_host_register (`in` 16-byte,
+ * `out` 4-byte aligned) are read and written by the device directly: no host copy at all.
+ * A record that points outside its buffer fails only the call that carries it (CSBWA_E_BADWIRE),
+ * never the unrelated calls it was coalesced with. */
 int csbwa_extend_batch(const uint8_t *in, int32_t in_bytes,
                        int16_t *out, int32_t out_shorts, int device);
+
+/* Same call for hosts whose arrays cannot be handed over as stable pointers (the JNI glue: JVM heap
+ * arrays move, so GetPrimitiveArrayCritical would have to be held across the GPU work).  hdr32: the
+ * first 32 bytes of the wire buffer; `fill` must write all in_bytes wire bytes to dst (pinned staging),
+ * `drain` receives the 10 * taskNum reply shorts.  Both run on the calling thread, outside any lock:
+ * one copy each way, made by the host's own accessor (GetByteArrayRegion / SetShortArrayRegion). */
+typedef void (*csbwa_fill_fn)(void *user, uint8_t *dst, int32_t in_bytes);
+typedef void (*csbwa_drain_fn)(void *user, const int16_t *src, int32_t n_shorts);
+int csbwa_extend_batch_cb(const uint8_t *hdr32, int32_t in_bytes, csbwa_fill_fn fill, csbwa_drain_fn drain,
+                          void *user, int device);
+
+/* Pinned (page-locked, device-mapped, portable across GPUs) host memory for seam buffers.  A seam call
+ * whose buffers lie inside such a range is zero-copy on the host (see csbwa_extend_batch).
+ * csbwa_host_register pins memory the caller already owns (cudaHostRegister; page granularity). */
+void *csbwa_host_alloc(int64_t bytes);
+int csbwa_host_free(void *p);
+int csbwa_host_register(void *p, int64_t bytes);
+int csbwa_host_unregister(void *p);
+int csbwa_host_is_pinned(const void *p, int64_t bytes);
 
 /* Many seam calls driven by n_threads caller threads (what an executor JVM with that many task
  * threads does), for C/C++ hosts; every call goes through csbwa_extend_batch. */

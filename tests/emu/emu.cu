@@ -211,50 +211,94 @@ extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, 
 // as the CUDA path, the "device" is the emulation above.  Tests the group-commit logic (slot
 // reuse, parallel staging copies, per-call reply routing) with many threads and no GPU.
 // ---------------------------------------------------------------------------------------------
+#include <atomic>
 #include <chrono>
 #include <thread>
 #include "../../cloud-scale-bwamem_b200/csrc/coalesce.hpp"
 
+// asynchronous like the CUDA executor: launch() hands the group to a worker thread, poll() looks at a flag
 struct HostCoExec {
     std::vector<std::vector<uint8_t>> hin;
     std::vector<std::vector<int16_t>> hout;
-    int delay_us;
+    std::vector<std::thread> th;
+    std::vector<std::atomic<unsigned>> done;
+    std::vector<std::vector<uint8_t>> bad;
+    std::vector<int> rcs;
+    size_t hdr_off = 0, ext_off = 0;
+    int delay_us = 0;
+    HostCoExec(int n_slots, size_t max_bytes, int max_tasks, int max_calls, int delay)
+        : hin(n_slots, std::vector<uint8_t>(max_bytes)), hout(n_slots, std::vector<int16_t>((size_t)max_tasks * 10 + 32)), th(n_slots),
+          done(n_slots), bad(n_slots, std::vector<uint8_t>((size_t)max_calls, 0)), rcs(n_slots, 0), delay_us(delay)
+    {
+        for (auto &d : done) d.store(0);
+    }
+    ~HostCoExec() { for (auto &t : th) if (t.joinable()) t.join(); }
     uint8_t *in_staging(int slot) { return hin[slot].data(); }
     int16_t *out_staging(int slot) { return hout[slot].data(); }
-    int run(int slot, const CoCall *calls, int n_calls, size_t span, int n_tasks)
+    unsigned long long in_staging_dev(int slot) { return (unsigned long long)(uintptr_t)hin[slot].data(); }
+    unsigned long long out_staging_dev(int slot) { return (unsigned long long)(uintptr_t)hout[slot].data(); }
+    const char *detail(int) { return "host executor failure"; }
+    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen)
     {
         (void)span; (void)n_tasks;
-        if (delay_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));
-        // the device reads the call table from the start of the staging buffer
-        const CoCall *tab = (const CoCall *)hin[slot].data();
-        for (int c = 0; c < n_calls; ++c) {
-            if (memcmp(&tab[c], &calls[c], sizeof(CoCall)) != 0) return -100;
-            int rc = emu_extend_wire(hin[slot].data() + tab[c].in_off, tab[c].in_bytes,
-                                     hout[slot].data() + tab[c].out_off, nullptr, nullptr, 0);
-            if (rc) return rc;
-        }
+        if (th[slot].joinable()) th[slot].join();
+        th[slot] = std::thread([this, slot, n_calls, n_units, gen] {
+            if (delay_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));
+            // the "device" reads the tables from the start of the staging buffer, the wire bytes from CoExt::src
+            const CoCall *tab = (const CoCall *)hin[slot].data();
+            const int32_t *dyn = (const int32_t *)(hin[slot].data() + hdr_off);
+            const CoExt *ext = (const CoExt *)(hin[slot].data() + ext_off);
+            int rc = 0, units = 0;
+            if (dyn[0] != n_calls || dyn[2] != n_units || (unsigned)dyn[3] != gen) rc = -100;
+            for (int c = 0; c < n_calls && rc == 0; ++c) {
+                bad[slot][c] = 0;
+                if (ext[c].unit_base != units || ext[c].n_units != (tab[c].in_bytes + 15) / 16) { rc = -101; break; }
+                units += ext[c].n_units;
+                int r1 = emu_extend_wire((const uint8_t *)(uintptr_t)ext[c].src, tab[c].in_bytes, (int16_t *)(uintptr_t)ext[c].dst,
+                                         nullptr, nullptr, 0);
+                if (r1) bad[slot][c] = 1;                       // a bad record fails its own call only
+            }
+            rcs[slot] = rc;
+            done[slot].store(gen, std::memory_order_release);
+        });
         return 0;
+    }
+    int poll(int slot, unsigned gen) { return done[slot].load(std::memory_order_acquire) == gen ? 1 : 0; }
+    int finish(int slot, int n_calls, int n_tasks, uint8_t *call_bad)
+    {
+        (void)n_tasks;
+        for (int c = 0; c < n_calls; ++c) call_bad[c] = bad[slot][c];
+        return rcs[slot];
     }
 };
 struct EmuCo {
     HostCoExec ex;
     Coalescer<HostCoExec> *co;
+    EmuCo(int n_slots, size_t max_bytes, int max_tasks, int max_calls, int delay) : ex(n_slots, max_bytes, max_tasks, max_calls, delay), co(nullptr) {}
 };
 
-extern "C" void *emu_co_create(int n_slots, int n_workers, long long max_bytes, int max_tasks, int max_calls, int delay_us)
+extern "C" void *emu_co_create(int n_slots, int max_inflight, long long max_bytes, int max_tasks, int max_calls, int delay_us)
 {
-    EmuCo *e = new EmuCo();
-    e->ex.delay_us = delay_us;
-    e->ex.hin.assign(n_slots, std::vector<uint8_t>((size_t)max_bytes));
-    e->ex.hout.assign(n_slots, std::vector<int16_t>((size_t)max_tasks * 10 + 32));
+    EmuCo *e = new EmuCo(n_slots, (size_t)max_bytes, max_tasks, max_calls, delay_us);
     Coalescer<HostCoExec>::Limits lim{(size_t)max_bytes, max_tasks, max_calls};
-    e->co = new Coalescer<HostCoExec>(&e->ex, n_slots, n_workers, lim);
+    e->ex.hdr_off = (size_t)max_calls * sizeof(CoCall);
+    e->ex.ext_off = e->ex.hdr_off + 16;
+    e->co = new Coalescer<HostCoExec>(&e->ex, n_slots, max_inflight, lim);
     return e;
 }
 extern "C" int emu_co_fits(void *h, int in_bytes, int n) { return ((EmuCo *)h)->co->fits(in_bytes, n) ? 1 : 0; }
-extern "C" int emu_co_submit(void *h, const uint8_t *in, int in_bytes, int16_t *out, int n)
+struct EmuCoUser { const uint8_t *in; int16_t *out; };
+static void emu_co_fill(void *u, uint8_t *dst, int n) { memcpy(dst, ((EmuCoUser *)u)->in, (size_t)n); }
+static void emu_co_drain(void *u, const int16_t *src, int n) { memcpy(((EmuCoUser *)u)->out, src, (size_t)n * 2); }
+// zero_copy: the executor reads `in` and writes `out` directly (what pinned caller buffers get on the GPU path)
+extern "C" int emu_co_submit(void *h, const uint8_t *in, int in_bytes, int16_t *out, int n, int zero_copy)
 {
-    return ((EmuCo *)h)->co->submit(in, in_bytes, out, n);
+    EmuCoUser u{in, out};
+    CoRequest rq;
+    rq.hdr = in; rq.in_bytes = in_bytes; rq.n_tasks = n;
+    rq.src_dev = zero_copy ? in : nullptr; rq.dst_dev = zero_copy ? out : nullptr;
+    rq.fill = emu_co_fill; rq.drain = emu_co_drain; rq.user = &u;
+    return ((EmuCo *)h)->co->submit(rq);
 }
 extern "C" void emu_co_stats(void *h, long long *groups, long long *calls)
 {

@@ -81,22 +81,22 @@ def load():
 class EmuCoalescer:
     """The product's Coalescer<> template instantiated with a host executor (tests/emu/emu.cu)."""
 
-    def __init__(self, emu, n_slots=3, n_workers=2, max_bytes=1 << 22, max_tasks=20000, max_calls=16, delay_us=2000):
+    def __init__(self, emu, n_slots=3, max_inflight=2, max_bytes=1 << 22, max_tasks=20000, max_calls=16, delay_us=2000):
         L = emu.lib
         L.emu_co_create.restype = C.c_void_p
         L.emu_co_create.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int]
-        L.emu_co_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.emu_co_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.emu_co_fits.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.emu_co_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.emu_co_destroy.argtypes = [C.c_void_p]
         self.L = L
-        self.h = L.emu_co_create(n_slots, n_workers, max_bytes, max_tasks, max_calls, delay_us)
+        self.h = L.emu_co_create(n_slots, max_inflight, max_bytes, max_tasks, max_calls, delay_us)
 
-    def submit(self, wire):
+    def submit(self, wire, zero_copy=False):
         wire = np.ascontiguousarray(wire, dtype=np.uint8)
         n = int(np.frombuffer(wire[8:12].tobytes(), dtype="<i4")[0])
         out = np.zeros(10 * n, dtype=np.int16)
-        rc = self.L.emu_co_submit(self.h, wire.ctypes.data, wire.size, out.ctypes.data, n)
+        rc = self.L.emu_co_submit(self.h, wire.ctypes.data, wire.size, out.ctypes.data, n, int(zero_copy))
         return rc, out
 
     def fits(self, wire):

@@ -47,6 +47,7 @@ typedef jarray jobjectArray;
 
 struct JNIEnv {
     int pins = 0;              // Get* without Release*
+    int n_critical = 0;        // GetPrimitiveArrayCritical calls (the glue must not need any: it would span GPU work)
     int n_thrown = 0;
     char thrown[512] = {0};
     int n_errors = 0;          // protocol violations a JVM would punish (bad field, wrong class, bounds, null)
@@ -135,7 +136,7 @@ struct JNIEnv {
     void ReleaseIntArrayElements(jintArray a, jint *p, jint mode) { put_back(a, p, mode); }
     jlong *GetLongArrayElements(jlongArray a, jboolean *) { return (jlong *)get_copy(a); }
     void ReleaseLongArrayElements(jlongArray a, jlong *p, jint mode) { put_back(a, p, mode); }
-    void *GetPrimitiveArrayCritical(jarray a, jboolean *) { return get_copy(a); }
+    void *GetPrimitiveArrayCritical(jarray a, jboolean *) { ++n_critical; return get_copy(a); }
     void ReleasePrimitiveArrayCritical(jarray a, void *p, jint mode) { put_back(a, p, mode); }
 
     jshortArray NewShortArray(jsize n) { return make(n, 2); }

@@ -21,7 +21,7 @@ extern "C" int jt_extend(const uint8_t *wire, int n_bytes, int ret_n, int16_t *o
     jarray in = from(wire, n_bytes, 1);
     jshortArray r = Java_cs_ucla_edu_bwaspark_jni_SWExtendFPGAJNI_swExtendFPGAJNI(&env, nullptr, ret_n, in);
     int rc = 0;
-    if (env.pins != 0) rc = 2;
+    if (env.pins != 0 || env.n_critical != 0) rc = 2;
     else if (env.n_thrown) { rc = 1; snprintf(msg, (size_t)msg_cap, "%s", env.thrown); }
     else if (!r || r->len != ret_n) rc = 2;
     else memcpy(out, r->data, (size_t)ret_n * 2);
@@ -36,7 +36,7 @@ extern "C" int jt_align2(int n_jobs, const int32_t *jobs8, const uint8_t *seqs, 
     jarray j = from(jobs8, 8 * n_jobs, 4), s = from(seqs, seq_bytes, 1);
     jintArray r = Java_cs_ucla_edu_bwaspark_jni_MateSWFlatJNI_align2Flat(&env, nullptr, n_jobs, j, s);
     int rc = 0;
-    if (env.pins != 0) rc = 2;
+    if (env.pins != 0 || env.n_critical != 0) rc = 2;
     else if (env.n_thrown) { rc = 1; snprintf(msg, (size_t)msg_cap, "%s", env.thrown); }
     else if (!r || r->len != 7 * n_jobs) rc = 2;
     else memcpy(out7, r->data, (size_t)7 * n_jobs * 4);
@@ -57,7 +57,7 @@ extern "C" int jt_coords(const uint8_t *pac, long long l_pac, int read_len, cons
     jarray rd = from(reads, read_bytes, 1), tk = from(tasks, task_bytes, 1);
     jshortArray r = nullptr;
     if (!env.n_thrown) r = Java_cs_ucla_edu_bwaspark_jni_SWExtendCoordsJNI_swExtendCoords(&env, nullptr, read_len, rd, n_tasks, tk);
-    if (env.pins != 0) rc = 2;
+    if (env.pins != 0 || env.n_critical != 0) rc = 2;
     else if (env.n_thrown) { rc = 1; snprintf(msg, (size_t)msg_cap, "%s", env.thrown); }
     else if (!r || r->len != 10 * n_tasks) rc = 2;
     else memcpy(out, r->data, (size_t)10 * n_tasks * 2);
@@ -74,7 +74,7 @@ extern "C" long long jt_chain2aln(int read_len, const uint8_t *reads, int read_b
     jarray rd = from(reads, read_bytes, 1), ro = from(rco, n_reads + 1, 4), ch = from(chains2, 2 * n_chains, 4), sd = from(seeds2, 2 * n_seeds, 8);
     jlongArray r = Java_cs_ucla_edu_bwaspark_jni_SWExtendCoordsJNI_chainToAlnFlat(&env, nullptr, read_len, rd, ro, ch, sd);
     long long rc = 0;
-    if (env.pins != 0) rc = -2;
+    if (env.pins != 0 || env.n_critical != 0) rc = -2;
     else if (env.n_thrown) { rc = -1; snprintf(msg, (size_t)msg_cap, "%s", env.thrown); }
     else if (!r) rc = -2;
     else { memcpy(out, r->data, (size_t)r->len * 8); rc = r->len; }

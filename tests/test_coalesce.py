@@ -15,7 +15,7 @@ def test_coalescer_many_threads(pkg, oracle, emu):
         tuples = [util.rand_ext_task(rng, L=int(rng.choice([76, 101, 151]))) for _ in range(int(rng.integers(1, 60)))]
         wires.append(pkg.jni.packTasks(util.make_ext_params(pkg, tuples)))
     refs = [oracle.extend_wire(w)[0] for w in wires]
-    co = emu_lib.EmuCoalescer(emu, n_slots=3, n_workers=2, max_bytes=64 * 1024, max_tasks=400, max_calls=6, delay_us=1500)
+    co = emu_lib.EmuCoalescer(emu, n_slots=3, max_inflight=2, max_bytes=64 * 1024, max_tasks=400, max_calls=6, delay_us=1500)
     try:
         assert all(co.fits(w) for w in wires)
         errs = []
@@ -23,7 +23,7 @@ def test_coalescer_many_threads(pkg, oracle, emu):
         def work(tid):
             for rep in range(6):
                 for i in range(tid, len(wires), 8):
-                    rc, out = co.submit(wires[i])
+                    rc, out = co.submit(wires[i], zero_copy=(i % 3 == 0))
                     if rc != 0 or not np.array_equal(out, refs[i]):
                         errs.append((tid, i, rc))
 
@@ -59,7 +59,7 @@ def test_coalescer_rejects_mixed_headers_into_separate_groups(pkg, oracle, emu):
     w2 = w1.copy()
     w2[7] = 1; w2[12] = 0; w2[13] = 0        # optional header: zdrop = 0
     r1, r2 = oracle.extend_wire(w1)[0], oracle.extend_wire(w2)[0]
-    co = emu_lib.EmuCoalescer(emu, n_slots=4, n_workers=1, delay_us=3000)
+    co = emu_lib.EmuCoalescer(emu, n_slots=4, max_inflight=1, delay_us=3000)
     try:
         res = {}
 
@@ -72,5 +72,35 @@ def test_coalescer_rejects_mixed_headers_into_separate_groups(pkg, oracle, emu):
         for k in range(8):
             rc, out = res[k]
             assert rc == 0 and np.array_equal(out, r1 if k % 2 == 0 else r2)
+    finally:
+        co.close()
+
+
+def test_coalescer_bad_record_fails_only_its_call(pkg, oracle, emu):
+    """Fault isolation: a call whose record points outside its buffer gets BADWIRE; the calls it was
+    coalesced with get their correct replies."""
+    rng = np.random.default_rng(64)
+    good = pkg.jni.packTasks(util.make_ext_params(pkg, [util.rand_ext_task(rng) for _ in range(12)]))
+    bad = good.copy()
+    bad[32 + 8:32 + 12] = np.frombuffer(np.int32(10 ** 8).tobytes(), dtype=np.uint8)     # taskPos of record 0 far outside
+    ref = oracle.extend_wire(good)[0]
+    co = emu_lib.EmuCoalescer(emu, n_slots=3, max_inflight=1, delay_us=4000)
+    try:
+        res = {}
+
+        def work(k):
+            res[k] = co.submit(bad if k == 3 else good, zero_copy=(k % 2 == 0))
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        groups, calls = co.stats()
+        assert calls == 8 and groups < 8            # the bad call really shared a group with good ones
+        for k in range(8):
+            rc, out = res[k]
+            if k == 3:
+                assert rc == -3
+            else:
+                assert rc == 0 and np.array_equal(out, ref)
     finally:
         co.close()

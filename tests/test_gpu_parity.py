@@ -282,6 +282,67 @@ def test_multi_call_device_api(pkg, oracle, gpu):
     assert (err == -7).any()
 
 
+def test_ext_pinned_zero_copy_and_fault_isolation(pkg, oracle, gpu):
+    """Pinned caller buffers are read / written by the device directly (no staging copy), pageable and pinned calls
+    mix freely in one group, and a call with a bad record fails alone: the calls coalesced with it succeed."""
+    L = pkg.lib()
+    rng = np.random.default_rng(57)
+    wires = [pkg.jni.packTasks(util.make_ext_params(pkg, [util.rand_ext_task(rng, L=int(rng.choice([101, 151, 250])))
+                                                         for _ in range(int(rng.integers(5, 600)))])) for _ in range(16)]
+    refs = [oracle.extend_wire(w, n_threads=8)[0] for w in wires]
+    bad_i = 5
+    wires[bad_i] = wires[bad_i].copy()
+    wires[bad_i][32 + 8:32 + 12] = np.frombuffer(np.int32(1 << 28).tobytes(), dtype=np.uint8)
+    arena = pkg._lib.PinnedArena(sum(w.size + 512 for w in wires) + sum(r.nbytes + 512 for r in refs))
+    ins, outs = [], []
+    for i, w in enumerate(wires):
+        if i % 2 == 0 or i == bad_i:
+            p = arena.take(w.size)
+            p[:] = w
+            ins.append(p)
+            outs.append(arena.take(refs[i].nbytes, np.int16))
+            assert L.csbwa_host_is_pinned(p.ctypes.data, p.size) == 1
+        else:
+            ins.append(w)
+            outs.append(np.zeros(refs[i].size, dtype=np.int16))
+    assert L.csbwa_host_is_pinned(wires[1].ctypes.data, 16) == 0
+    z0 = pkg.stats()["ext_zero_copy_calls"]
+    rcs = {}
+
+    def work(i):
+        for rep in range(4):
+            outs[i][:] = -1
+            rcs[(i, rep)] = L.csbwa_extend_batch(ins[i].ctypes.data, ins[i].size, outs[i].ctypes.data, outs[i].size, 0)
+            if i != bad_i and not np.array_equal(outs[i], refs[i]):
+                rcs[(i, rep)] = -99
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(wires))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for (i, rep), rc in rcs.items():
+        assert rc == (pkg._lib.E_BADWIRE if i == bad_i else 0), (i, rep, rc)
+    assert pkg.stats()["ext_zero_copy_calls"] - z0 == 4 * 8
+    arena.close()
+
+
+def test_ext_callback_entry(pkg, oracle, gpu):
+    """csbwa_extend_batch_cb (what the JNI glue calls): the host writes its bytes straight into pinned staging."""
+    import ctypes as C
+    L = pkg.lib()
+    rng = np.random.default_rng(58)
+    wire = pkg.jni.packTasks(util.make_ext_params(pkg, [util.rand_ext_task(rng) for _ in range(300)]))
+    ref = oracle.extend_wire(wire, n_threads=4)[0]
+    got = np.zeros_like(ref)
+    FILL = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32)
+    DRAIN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32)
+    fill = FILL(lambda u, dst, n: C.memmove(dst, wire.ctypes.data, n))
+    drain = DRAIN(lambda u, src, n: C.memmove(got.ctypes.data, src, 2 * n))
+    hdr = wire[:32].copy()
+    assert L.csbwa_extend_batch_cb(hdr.ctypes.data, wire.size, fill, drain, None, 0) == 0
+    assert np.array_equal(got, ref)
+    assert L.csbwa_extend_batch_cb(hdr.ctypes.data, 16, fill, drain, None, 0) == pkg._lib.E_BADWIRE
+
+
 def test_direct_path_subprocess(pkg, oracle, gpu):
     """CSBWA_COALESCE=0 selects the one-call-per-submission path; same bits."""
     import subprocess, sys, os
@@ -301,12 +362,13 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
     assert "direct-ok" in out.stdout, out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("env", [{"CSBWA_CO_SYNC": "spin", "CSBWA_CO_SLOTS": "3"},
-                                 {"CSBWA_CO_SYNC": "yield", "CSBWA_CO_ONE_GRAPH": "1"},
+@pytest.mark.parametrize("env", [{"CSBWA_CO_SLOTS": "3", "CSBWA_CO_INFLIGHT": "1"},
+                                 {"CSBWA_CO_ONE_GRAPH": "1", "CSBWA_CO_INFLIGHT": "4"},
                                  {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_SLOTS": "2"}])
 def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):
-    """The host seam's tuning knobs (how submission threads wait, slots, graph variants, no graph) never change
-    a bit: 12 caller threads, calls of three different sizes so that groups of all graph size classes occur."""
+    """The host seam's tuning knobs (slots, groups in flight, graph variants, no graph) never change a bit: 12 caller
+    threads, calls of three different sizes so that groups of all graph size classes occur; every third call uses
+    pinned buffers (zero-copy), the others pageable ones."""
     import subprocess, sys, os
     code = (
         "import importlib,sys,ctypes as C,numpy as np\n"
@@ -319,13 +381,16 @@ def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):
         "    bufs+=pkg.workload.ext_workload(pairs,151,500000,0.01,400,50,5,reads_per_call=rpc)['bufs'][:12]\n"
         "nt=[int(np.frombuffer(b[8:12].tobytes(),dtype='<i4')[0]) for b in bufs]\n"
         "outs=[np.zeros(10*n,dtype=np.int16) for n in nt]\n"
+        "arena=pkg._lib.PinnedArena(sum(b.size+512 for b in bufs)+sum(o.nbytes+512 for o in outs))\n"
+        "for i in range(0,len(bufs),3):\n"
+        "    p=arena.take(bufs[i].size); p[:]=bufs[i]; bufs[i]=p; outs[i]=arena.take(outs[i].nbytes,np.int16)\n"
         "ip=(C.c_void_p*len(bufs))(*[b.ctypes.data for b in bufs]); op=(C.c_void_p*len(bufs))(*[o.ctypes.data for o in outs])\n"
         "isz=np.array([b.size for b in bufs],dtype=np.int32); osz=np.array([o.size for o in outs],dtype=np.int32)\n"
         "for _ in range(3):\n"
         "    assert L.csbwa_extend_calls(ip,isz.ctypes.data,op,osz.ctypes.data,len(bufs),12,0)==0, L.csbwa_last_error()\n"
         "for b,o in zip(bufs,outs):\n"
         "    assert np.array_equal(o,O.extend_wire(b,n_threads=8)[0])\n"
-        "assert pkg.stats()['ext_groups']>0\n"
+        "assert pkg.stats()['ext_groups']>0 and pkg.stats()['ext_zero_copy_calls']>0\n"
         "L.csbwa_shutdown()\n"
         "print('knobs-ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)

@@ -20,7 +20,11 @@ def main():
     ap.add_argument("--repeat", type=int, default=40, help="passes over the call list inside ONE csbwa_extend_calls")
     ap.add_argument("--reads-per-call", type=int, default=4096)
     ap.add_argument("--split", type=int, default=0, help="1: one csbwa_extend_calls per pass (what bench.py's step does)")
+    ap.add_argument("--pinned", type=int, default=1, help="1: caller buffers in pinned memory (zero-copy seam), 0: pageable numpy arrays")
+    ap.add_argument("--cpus", type=int, default=0, help="restrict the process to this many cores (what one rank of an 8-GPU box gets: 4)")
     args = ap.parse_args()
+    if args.cpus > 0:
+        os.sched_setaffinity(0, set(sorted(os.sched_getaffinity(0))[:args.cpus]))
     pkg = importlib.import_module("cloud-scale-bwamem_b200")
     import bench
     bench.CFG = bench.CFGS["C2"]
@@ -31,6 +35,15 @@ def main():
     ntasks = [bench.task_count(b) for b in bufs]
     n = len(bufs)
     outs = [np.zeros(10 * k, dtype=np.int16) for k in ntasks]
+    if args.pinned:
+        arena = pkg._lib.PinnedArena(sum(b.size + 512 for b in bufs) + sum(o.nbytes + 512 for o in outs) + 4096)
+        pb = []
+        for b in bufs:
+            p = arena.take(b.size)
+            p[:] = b
+            pb.append(p)
+        bufs = pb
+        outs = [arena.take(o.nbytes, np.int16) for o in outs]
     R = 1 if args.split else args.repeat
     in_ptrs = (C.c_void_p * (n * R))(*([b.ctypes.data for b in bufs] * R))
     out_ptrs = (C.c_void_p * (n * R))(*([o.ctypes.data for o in outs] * R))
@@ -51,7 +64,8 @@ def main():
     dt = time.perf_counter() - t0
     s1 = pkg.stats()
     g = max(1, s1["ext_groups"] - s0["ext_groups"])
-    res = {"threads": args.threads, "slots": os.environ.get("CSBWA_CO_SLOTS", "default"), "split": args.split,
+    res = {"threads": args.threads, "slots": os.environ.get("CSBWA_CO_SLOTS", "default"), "inflight": os.environ.get("CSBWA_CO_INFLIGHT", "default"),
+           "pinned": args.pinned, "cpus": len(os.sched_getaffinity(0)), "split": args.split, "zero_copy_calls": s1["ext_zero_copy_calls"] - s0["ext_zero_copy_calls"],
            "calls": n * args.repeat, "calls_per_ms": n * args.repeat / dt / 1e3,
            "gcups": (s1["ext_cells"] - s0["ext_cells"]) / dt / 1e9,
            "calls_per_group": (s1["ext_calls"] - s0["ext_calls"]) / g,
