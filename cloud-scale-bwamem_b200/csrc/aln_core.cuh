@@ -38,14 +38,16 @@ struct AlnBook {
     int last_te, last_sc;   // copy of the last entry
     int min_sc, end_sc, sat;
     bool stop;
-    CSW_HD void init(const SwOpt &o, int xtra)
+    bool nosat;             // 16-bit regime of the native ksw_align2 (no saturation, no stop at 255 - |b|): native-semantics jobs only
+    CSW_HD void init(const SwOpt &o, int xtra, bool no_sat = false)
     {
+        nosat = no_sat;
         best = ALN_MINUS_INF; best_i = -1; best_j = -1;
         nb = 0; last_te = -2; last_sc = 0; stop = false;
         min_sc = (xtra & XSUBO) ? (xtra & 0xffff) : 0x10000;
         end_sc = (xtra & XSTOP) ? (xtra & 0xffff) : 0x10000;
         int ab = o.b < 0 ? -o.b : o.b;
-        sat = 255 - ab;
+        sat = no_sat ? 0x3fffffff : 255 - ab;
     }
     // b entries: bsc[k], bte[k]
     CSW_HD void row(int i, int m, int mj, int *bsc, int *bte)
@@ -68,12 +70,12 @@ CSW_HD void aln_finish_head(const AlnBook &bk, AlnRes &r)
     if (sc >= bk.sat) sc = 255;
     r.score = sc; r.te = bk.best_i;
     r.qe = -1; r.score2 = -1; r.te2 = -1; r.tb = -1; r.qb = -1;
-    if (sc != 255) r.qe = bk.best_j;
+    if (bk.nosat || sc != 255) r.qe = bk.best_j;
 }
 
 CSW_HD void aln_second_best_serial(const SwOpt &o, const AlnBook &bk, const int *bsc, const int *bte, AlnRes &r)
 {
-    if (r.score == 255 || bk.nb <= 0) return;
+    if ((r.score == 255 && !bk.nosat) || bk.nb <= 0) return;
     const int tmp = (r.score + o.a - 1) / o.a;
     const int low = r.te - tmp, high = r.te + tmp;
     for (int k = 0; k < bk.nb; ++k)
@@ -85,11 +87,11 @@ CSW_HD void aln_second_best_serial(const SwOpt &o, const AlnBook &bk, const int 
 // ---------------------------------------------------------------------------------
 CSW_HD long long sw_align_pass_generic(const SwOpt &o, const uint8_t *q, const uint8_t *t, int qn, int tlen,
                                        bool rev, int qe, int te, int xtra,
-                                       int *H, int *E, int *bsc, int *bte, AlnRes &r)
+                                       int *H, int *E, int *bsc, int *bte, AlnRes &r, bool no_sat = false)
 {
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
     AlnBook bk;
-    bk.init(o, xtra);
+    bk.init(o, xtra, no_sat);
     if (qn < 0) qn = 0;
     for (int j = 0; j < qn; ++j) { H[j] = 0; E[j] = 0; }
     long long cells = 0;
@@ -122,13 +124,13 @@ CSW_HD long long sw_align_pass_generic(const SwOpt &o, const uint8_t *q, const u
 
 // SWAlign2 on read-only inputs (the in-place reversal is expressed through index maps)
 CSW_HD long long sw_align2_generic(const SwOpt &o, const uint8_t *q, int qlen, const uint8_t *t, int tlen,
-                                   int xtra, int *H, int *E, int *bsc, int *bte, AlnRes &r)
+                                   int xtra, int *H, int *E, int *bsc, int *bte, AlnRes &r, bool no_sat = false)
 {
-    long long cells = sw_align_pass_generic(o, q, t, qlen, tlen, false, 0, 0, xtra, H, E, bsc, bte, r);
+    long long cells = sw_align_pass_generic(o, q, t, qlen, tlen, false, 0, 0, xtra, H, E, bsc, bte, r, no_sat);
     if ((xtra & XSTART) == 0 || ((xtra & XSUBO) && r.score < (xtra & 0xffff))) return cells;
     AlnRes rr;
     cells += sw_align_pass_generic(o, q, t, r.qe + 1, tlen, true, r.qe, r.te, XSTOP | r.score,
-                                   H, E, bsc, bte, rr);
+                                   H, E, bsc, bte, rr, no_sat);
     if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
     return cells;
 }
@@ -234,6 +236,9 @@ CSW_HD void aln_decode_key2(uint32_t key2, int &m, int &mj)
     m = (int)(k >> 8);
     mj = m > 0 ? 255 - (int)(k & 0xffu) : -1;
 }
+
+// job.pad bit 0: native ksw_align2 semantics -- 16-bit (no saturation) when KSW_XBYTE is clear (N/ksw.c:349-351)
+CSW_HD bool aln_job_nosat(int xtra, int pad) { return (pad & 1) && !(xtra & XBYTE); }
 
 // limits of the packed path: 16 lanes x 2P columns, column index and valid scores fit 8 bits
 CSW_HD bool aln_packed_eligible(const SwOpt &o, int qlen, int tlen, int pmax)

@@ -53,9 +53,10 @@ __host__ __device__ inline AlnScratch aln_carve(void *p, int n)
     return s;
 }
 
-CSW_HD int aln_class_of(const SwOpt &o, int qlen, int tlen)
+CSW_HD int aln_class_of(const SwOpt &o, int qlen, int tlen, int xtra = 0, int pad = 0)
 {
     if (!aln_packed_eligible(o, qlen, tlen, 8)) return 0;
+    if (aln_job_nosat(xtra, pad)) return 0;          // scores may pass 255: the packed keys hold 8 bits, the int32 core takes it
     if (qlen > 160) return 1;
     if (qlen > 128) return 2;
     if (qlen > 64) return 3;
@@ -73,7 +74,7 @@ __global__ void k_aln_classify(const AlnJob *__restrict__ jobs, int n, AlnScratc
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const int cls = aln_class_of(sopt, jobs[k].q_len, jobs[k].t_len);
+    const int cls = aln_class_of(sopt, jobs[k].q_len, jobs[k].t_len, jobs[k].xtra, jobs[k].pad);
     // warp-aggregated append
     const unsigned act = __activemask();
     const unsigned same = __match_any_sync(act, cls);
@@ -281,7 +282,7 @@ k_aln_generic(const AlnJob *__restrict__ jobs, const uint8_t *__restrict__ seqs,
         int *E = H + (qn + 2);
         AlnRes r;
         my_cells += (unsigned long long)sw_align2_generic(o, seqs + jb.q_off, qn, seqs + jb.t_off, tn, jb.xtra,
-                                                          H, E, bsc, bte, r);
+                                                          H, E, bsc, bte, r, aln_job_nosat(jb.xtra, jb.pad));
         o7[0] = r.score; o7[1] = r.te; o7[2] = r.qe; o7[3] = r.score2; o7[4] = r.te2; o7[5] = r.tb; o7[6] = r.qb;
     }
     if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);

@@ -122,3 +122,110 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
 }
 
 #include "matesw_group.inc"
+
+// ------------------------------------------------------------------------------------
+// insert-size statistics: memPeStatPrep (S/worker2/MemSamPe.scala:912-945) and memPeStatCompute (:991-1093).
+// Host code: the reference runs it on the Spark driver, once per batch, on two ints per pair.
+// ------------------------------------------------------------------------------------
+namespace {
+
+// calSub (:77-100): score of the first region whose query span overlaps the best one's by maskLevel
+int pe_cal_sub(const csbwa_alnreg *r, int n)
+{
+    const float kMaskLevel = 0.5f;                               // MemOptType.maskLevel
+    for (int j = 1; j < n; ++j) {
+        const int b_max = std::max(r[j].qb, r[0].qb), e_min = std::min(r[j].qe, r[0].qe);
+        if (e_min > b_max) {
+            const int min_l = std::min(r[j].qe - r[j].qb, r[0].qe - r[0].qb);
+            if ((float)(e_min - b_max) >= (float)min_l * kMaskLevel) return r[j].score;
+        }
+    }
+    return 19;                                                    // minSeedLen * a
+}
+
+// Scala Double.toInt: toward zero, saturating
+int pe_to_int(double x)
+{
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return 2147483647;
+    if (x <= -2147483648.0) return -2147483647 - 1;
+    return (int)x;
+}
+
+} // namespace
+
+extern "C" int csbwa_pestat_prep(int64_t l_pac, int32_t n_pairs, const csbwa_alnreg *regs, const int32_t *reg_start,
+                                 int32_t *dir, int32_t *dist)
+{
+    if (n_pairs < 0 || (n_pairs > 0 && (!reg_start || !dir || !dist))) return fail(CSBWA_E_BADARG, "bad argument");
+    const double kMinRatio = 0.8;
+    for (int32_t k = 0; k < n_pairs; ++k) {
+        dir[k] = 0; dist[k] = 0;                                  // PeStatPrepType defaults: the pair does not count
+        const int s0 = reg_start[2 * k], s1 = reg_start[2 * k + 1], s2 = reg_start[2 * k + 2];
+        if (s1 < s0 || s2 < s1) return fail(CSBWA_E_BADARG, "reg_start not monotone");
+        if (s1 == s0 || s2 == s1) continue;
+        if (!regs) return fail(CSBWA_E_BADARG, "null regs");
+        const csbwa_alnreg *a = regs + s0, *b = regs + s1;
+        if (!((double)pe_cal_sub(a, s1 - s0) <= kMinRatio * a[0].score)) continue;
+        if (!((double)pe_cal_sub(b, s2 - s1) <= kMinRatio * b[0].score)) continue;
+        const bool r1 = a[0].rb >= l_pac, r2 = b[0].rb >= l_pac;  // mem_infer_dir, inlined like the Scala
+        const int64_t p2 = r1 != r2 ? (l_pac << 1) - 1 - b[0].rb : b[0].rb;
+        dist[k] = (int32_t)(p2 > a[0].rb ? p2 - a[0].rb : a[0].rb - p2);
+        dir[k] = (r1 == r2 ? 0 : 1) ^ (p2 > a[0].rb ? 0 : 3);
+    }
+    return CSBWA_OK;
+}
+
+extern "C" int csbwa_pestat_compute(int32_t n, const int32_t *dir, const int32_t *dist, int32_t max_ins, csbwa_pestat pes[4])
+{
+    if (n < 0 || max_ins < 1 || !pes || (n > 0 && (!dir || !dist))) return fail(CSBWA_E_BADARG, "bad argument");
+    const int kMinDirCnt = 10;
+    const double kMinDirRatio = 0.05, kOutlier = 2.0, kMapping = 3.0, kMaxStd = 4.0;
+    // counting sort (:955-981): one histogram over [1, max_ins] per orientation IS the sorted array
+    std::vector<int32_t> hist((size_t)4 * ((size_t)max_ins + 1), 0);
+    int64_t cnt[4] = {0, 0, 0, 0};
+    for (int32_t i = 0; i < n; ++i) {
+        if (dist[i] <= 0 || dist[i] > max_ins) continue;
+        if (dir[i] < 0 || dir[i] > 3) return fail(CSBWA_E_BADARG, "orientation outside 0..3");
+        ++hist[(size_t)dir[i] * ((size_t)max_ins + 1) + (size_t)dist[i]];
+        ++cnt[dir[i]];
+    }
+    for (int d = 0; d < 4; ++d) {
+        csbwa_pestat &r = pes[d];
+        r.low = r.high = r.failed = r.pad = 0; r.avg = r.std = 0.0;
+        const int32_t *h = hist.data() + (size_t)d * ((size_t)max_ins + 1);
+        const int64_t m = cnt[d];
+        if (m < kMinDirCnt) { r.failed = 1; continue; }
+        // q(idx) of the sorted array = smallest value whose cumulative count exceeds idx
+        const int64_t want[3] = {pe_to_int(0.25 * (double)m + 0.499), pe_to_int(0.50 * (double)m + 0.499), pe_to_int(0.75 * (double)m + 0.499)};
+        int q[3] = {0, 0, 0};
+        int64_t acc = 0;
+        for (int v = 1, got = 0; v <= max_ins && got < 3; ++v) {
+            acc += h[v];
+            while (got < 3 && acc > want[got]) q[got++] = v;
+        }
+        const int p25 = q[0], p75 = q[2];
+        r.low = std::max(1, pe_to_int(p25 - kOutlier * (p75 - p25) + 0.499));
+        r.high = pe_to_int(p75 + kOutlier * (p75 - p25) + 0.499);
+        double avg = 0.0, sd = 0.0;
+        int64_t x = 0;
+        const int lo = std::max(r.low, 1), hi = std::min(r.high, (int)max_ins);
+        for (int v = lo; v <= hi; ++v)                            // ascending like the sorted array; sums of ints are exact in double
+            for (int32_t c = 0; c < h[v]; ++c) { avg += v; ++x; }
+        avg /= (double)x;
+        for (int v = lo; v <= hi; ++v)
+            for (int32_t c = 0; c < h[v]; ++c) sd += (v - avg) * (v - avg);
+        sd = sqrt(sd / (double)x);
+        r.avg = avg; r.std = sd;
+        r.low = pe_to_int(p25 - kMapping * (p75 - p25) + .499);
+        r.high = pe_to_int(p75 + kMapping * (p75 - p25) + .499);
+        if (r.low > avg - kMaxStd * sd) r.low = pe_to_int(avg - kMaxStd * sd + .499);
+        if (r.high < avg - kMaxStd * sd) r.high = pe_to_int(avg - kMaxStd * sd + .499);      // the Scala's MINUS on both sides (:1066)
+        if (r.low < 1) r.low = 1;
+    }
+    int64_t mx = 0;
+    for (int d = 0; d < 4; ++d) mx = std::max(mx, cnt[d]);
+    for (int d = 0; d < 4; ++d)
+        if (pes[d].failed == 0 && (double)cnt[d] < (double)mx * kMinDirRatio) pes[d].failed = 1;
+    return CSBWA_OK;
+}

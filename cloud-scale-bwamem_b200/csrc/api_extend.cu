@@ -336,6 +336,11 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
+    // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma: one cudaMemcpyAsync per call and direction around the
+    // graph (copy engines: transfers of one group overlap the kernels of the others without needing SM resources).
+    // sm: gather / scatter kernels inside the graph (one driver call per group, but the copy blocks have to find room
+    // on SMs that the side kernels fill).
+    bool dma = true;
     std::vector<Slot> slots;
 
     int init(int device, int n_slots, size_t max_bytes, int max_tasks_, size_t header_off, size_t ext_off_, size_t table_bytes_)
@@ -350,6 +355,8 @@ struct CudaCoExec {
         use_graph = !(e && e[0] == '0');
         e = getenv("CSBWA_CO_ONE_GRAPH");
         one_graph = e && e[0] == '1';
+        e = getenv("CSBWA_CO_COPY");
+        dma = !(e && e[0] == 's');
         CU_TRY(cudaSetDevice(dev));
         slots.resize(n_slots);
         for (auto &s : slots) {
@@ -402,15 +409,17 @@ struct CudaCoExec {
     unsigned long long out_staging_dev(int slot) { return (unsigned long long)(uintptr_t)(slots[slot].dv_out + kTrailer); }
     const char *detail(int slot) { return slots[slot].detail.c_str(); }
 
-    // the device side of one group; everything is sized by the device from the staging header.
+    // the kernels of one group; everything is sized by the device from the staging header.
     // timed: record the phase events (never inside a graph capture)
     int enqueue(Slot &s, int variant, bool timed)
     {
         const int dyn_cap = variant_cap(variant);
-        if (timed) CU_TRY(cudaEventRecord(s.ev[0], s.st));
+        if (timed && !dma) CU_TRY(cudaEventRecord(s.ev[0], s.st));
         CU_TRY(cudaMemsetAsync(s.d_out, 0, kTrailer, s.st));
-        k_co_head<<<4, 256, 0, s.st>>>((uint4 *)s.d_in, (const uint4 *)s.dv_in, (int)(table_bytes / 16));
-        k_co_gather<<<variant == 0 ? 16 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off);
+        if (!dma) {
+            k_co_head<<<4, 256, 0, s.st>>>((uint4 *)s.d_in, (const uint4 *)s.dv_in, (int)(table_bytes / 16));
+            k_co_gather<<<variant == 0 ? 16 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off);
+        }
         if (timed) CU_TRY(cudaEventRecord(s.ev[1], s.st));
         ExtCalls cs;
         cs.tab = (const ExtCall *)s.d_in; cs.n_calls = 0;
@@ -419,11 +428,13 @@ struct CudaCoExec {
         int rc = launch_extend(s.d_in, cs, dyn_cap, (int16_t *)(s.d_out + kTrailer), (unsigned long long *)s.d_out, s.d_scratch,
                                (int64_t)scratch_cap, s.st, dev, &s.aux);
         if (rc) return rc;
+        if (dma) k_co_finish<<<1, 32, 0, s.st>>>(s.d_in, hdr_off, (const ExtHdr *)s.d_scratch, (CoTrailer *)s.d_out);
         if (timed) CU_TRY(cudaEventRecord(s.ev[2], s.st));
-        k_co_scatter<<<variant == 0 ? 8 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
-                                                             (const unsigned long long *)s.d_out, (const ExtHdr *)s.d_scratch,
-                                                             (CoTrailer *)s.dv_out, s.d_count);
-        if (timed) CU_TRY(cudaEventRecord(s.ev[3], s.st));
+        if (!dma)
+            k_co_scatter<<<variant == 0 ? 8 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
+                                                                 (const unsigned long long *)s.d_out, (const ExtHdr *)s.d_scratch,
+                                                                 (CoTrailer *)s.dv_out, s.d_count);
+        if (timed && !dma) CU_TRY(cudaEventRecord(s.ev[3], s.st));
         CU_TRY(cudaGetLastError());
         return CSBWA_OK;
     }
@@ -463,15 +474,36 @@ struct CudaCoExec {
     {
         CU_TRY(cudaSetDevice(dev));
         const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks);
-        if (use_graph) {
-            if (!s.graph[v] || s.graph_core[v] != ext_core()) {
-                int rc = build_graph(s, v);
-                if (rc) return rc;
-            }
-            CU_TRY(cudaGraphLaunch(s.graph[v], s.st));
-            return CSBWA_OK;
+        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core())) {
+            int rc = build_graph(s, v);
+            if (rc) return rc;
         }
-        return enqueue(s, v, true);
+        // copy-engine mode: the tables, then every call's wire bytes from wherever they are (caller's pinned buffer or
+        // the slot's staging); replies and the trailer after the kernels.  The trailer travels last: its done_gen word
+        // is the completion signal.
+        const CoCall *tab = (const CoCall *)s.h_in;
+        const int n_calls = ((const int32_t *)(s.h_in + hdr_off))[0];
+        const CoExt *ext = (const CoExt *)(s.h_in + ext_off);
+        if (dma) {
+            if (!use_graph) CU_TRY(cudaEventRecord(s.ev[0], s.st));
+            CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, table_bytes, cudaMemcpyHostToDevice, s.st));
+            for (int c = 0; c < n_calls; ++c)
+                CU_TRY(cudaMemcpyAsync(s.d_in + tab[c].in_off, (const void *)(uintptr_t)ext[c].src, (size_t)tab[c].in_bytes,
+                                       cudaMemcpyDefault, s.st));
+        }
+        if (use_graph) CU_TRY(cudaGraphLaunch(s.graph[v], s.st));
+        else {
+            int rc = enqueue(s, v, true);
+            if (rc) return rc;
+        }
+        if (dma) {
+            for (int c = 0; c < n_calls; ++c)
+                CU_TRY(cudaMemcpyAsync((void *)(uintptr_t)ext[c].dst, s.d_out + kTrailer + (size_t)tab[c].out_off * 2,
+                                       (size_t)tab[c].n_tasks * 20, cudaMemcpyDefault, s.st));
+            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, kTrailer, cudaMemcpyDeviceToHost, s.st));
+            if (!use_graph) CU_TRY(cudaEventRecord(s.ev[3], s.st));
+        }
+        return CSBWA_OK;
     }
     // 0 = running, 1 = finished, < 0 = failed.  The fast path is one load from pinned memory; the stream is
     // queried now and then so that a faulted kernel cannot leave the callers waiting for ever.
@@ -518,7 +550,7 @@ struct CudaCoExec {
             std::lock_guard<std::mutex> lk(g_stats_mu);
             g_stats.ext_calls += n_calls; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)t->cells;
             g_stats.ext_in_bytes += (int64_t)s.span; g_stats.ext_out_bytes += (int64_t)n_tasks * 20;
-            g_stats.kernel_launches += kExtLaunches + 3;
+            g_stats.kernel_launches += kExtLaunches + (dma ? 1 : 3);
             g_stats.ext_groups += 1;
             g_stats.h2d_ms += t_h2d; g_stats.kernel_ms += t_k; g_stats.d2h_ms += t_d2h;
             g_stats.host_ms += dt;

@@ -115,4 +115,14 @@ __global__ void __launch_bounds__(256) k_co_scatter(const uint8_t *__restrict__ 
     }
 }
 
+// copy-engine mode of the seam: the transfers are cudaMemcpyAsync calls around the graph; this kernel closes
+// the launch sequence by assembling the trailer in device memory ({cells} is already there), which the last
+// device -> host copy of the group delivers -- its done_gen word is what the host polls
+__global__ void k_co_finish(const uint8_t *__restrict__ d_in, size_t hdr_off, const ExtHdr *hdr, CoTrailer *d_trailer)
+{
+    const int32_t *dyn = (const int32_t *)(d_in + hdr_off);
+    if (threadIdx.x < 8) d_trailer->bad_bits[threadIdx.x] = hdr->bad_call_bits[threadIdx.x];
+    if (threadIdx.x == 8) { d_trailer->status = hdr->err; d_trailer->done_gen = (uint32_t)dyn[3]; }
+}
+
 } // namespace csw

@@ -65,7 +65,8 @@ typedef struct {
     int64_t q_off, t_off;   /* byte offsets of query / target inside seqs[] */
     int32_t q_len, t_len;
     int32_t xtra;           /* KSW_X* flags | minScore, S/util/SWUtil.scala:29-32 */
-    int32_t pad;
+    int32_t pad;            /* 0 = Scala SWAlign2.  bit 0: native ksw_align2 semantics -- when KSW_XBYTE is clear the job runs
+                               without the 255 - |b| saturation (the 16-bit ksw_i16 regime, N/ksw.c:349-351) */
 } csbwa_job;
 
 /* = SWAlnType (S/datatype/SWAlnType.scala:21-29) = kswr_t (N/ksw.h:40-46) */
@@ -166,11 +167,30 @@ typedef struct {
 } csbwa_alnreg;
 typedef struct { int32_t low, high, failed, pad; double avg, std; } csbwa_pestat;
 typedef struct { int64_t rb[4], re[4], len[4], off[4]; } csbwa_refsw;
+/* Which driver csbwa_matesw_group (and the MateSWJNI symbol on top of it) replays: 0 = the Scala one above
+ * (default), 1 = the NATIVE library the JNI symbol replaces (mem_matesw_precompute, N/bwamem_pair.c:159-228):
+ * non-reversed hits get rb = rBeg + tb (:206; the Scala has rb = re = rBeg + te + 1, MemSamPe.scala:1203-1204),
+ * hits are inserted in descending score order and the mate list is de-duplicated in place after every
+ * orientation (:213-222), mem_sort_and_dedup sorts by rEnd only (N/bwamem.c:385-398), and mates with
+ * l_ms * a >= 250 are aligned without 8-bit saturation (ksw_i16, N/ksw.c:349-351).  Start-up default from the
+ * environment (CSBWA_MATESW_NATIVE=1).  Returns the previous setting; any other argument only queries. */
+int csbwa_set_matesw_semantics(int native);
 int csbwa_matesw_group(int64_t l_pac, const csbwa_pestat *pes, int32_t group_size,
                        const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                        const csbwa_alnreg *regs, const int32_t *reg_start,
                        const csbwa_refsw *refs, const int32_t *ref_count, const uint8_t *win_seqs,
                        csbwa_alnreg *out_regs, int32_t out_cap, int32_t *out_start, int device);
+
+/* ---- insert-size statistics: memPeStatPrep + memPeStatCompute ----------------
+ * (S/worker2/MemSamPe.scala:912-945 and :991-1093; native originals mem_pestat / cal_sub, N/bwamem_pair.c:36-112).
+ * Pure host code -- the reference runs it on the Spark driver between worker1 and worker2.
+ * regs / reg_start: region lists per (pair k, end i), CSR over 2k+i.  dir / dist: PeStatPrepType per pair
+ * (dist = 0: the pair does not qualify).  csbwa_pestat_compute keeps the Scala text's quirks: counting sort over
+ * [1, max_ins], quantile index (f * n + .499).toInt, and the high bound tested against and replaced by
+ * avg MINUS 4 sd (:1066; the C has avg + 4 sd on the right-hand side, N/bwamem_pair.c:100). */
+int csbwa_pestat_prep(int64_t l_pac, int32_t n_pairs, const csbwa_alnreg *regs, const int32_t *reg_start,
+                      int32_t *dir, int32_t *dist);
+int csbwa_pestat_compute(int32_t n, const int32_t *dir, const int32_t *dist, int32_t max_ins, csbwa_pestat pes[4]);
 
 /* ---- device-resident variants (pipelines, benchmarking) -----------------
  * All pointers are DEVICE pointers on the current CUDA device; `stream` is a

@@ -223,12 +223,15 @@ static void orc_extension_with(const orc_task_t *t, const orc_opt_t *opt, orc_ex
 /* ------------------------------------------------------------------------- */
 #define ORC_MINUS_INF (-0x40000000) /* SWUtil.scala:28 */
 
-void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
-                  int m, const orc_opt_t *opt, int xtra, orc_aln_t *out)
+/* no_sat = 0: the Scala routine.  no_sat = 1: the 16-bit regime of the NATIVE library the MateSWJNI seam
+ * replaces (ksw_align2 picks ksw_i16 when KSW_XBYTE is clear, N/ksw.c:349-351: no saturation, no stop at
+ * 255 - |b|) -- only used by the native-semantics mode of the mate-rescue driver. */
+void orc_sw_align_ex(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                     int m, const orc_opt_t *opt, int xtra, int no_sat, orc_aln_t *out)
 {
     const int oe_del = opt->o_del + opt->e_del, oe_ins = opt->o_ins + opt->e_ins;
     const int e_del = opt->e_del, e_ins = opt->e_ins;
-    const int sat = 255 - abs(opt->b);                  /* maxScore (:423) */
+    const int sat = no_sat ? 0x3fffffff : 255 - abs(opt->b);   /* maxScore (:423) */
     const int qmax = opt->a;                            /* (:424) */
     const int min_sc = (xtra & ORC_XSUBO) ? (xtra & 0xffff) : 0x10000; /* (:434-435) */
     const int end_sc = (xtra & ORC_XSTOP) ? (xtra & 0xffff) : 0x10000; /* (:436-437) */
@@ -277,7 +280,7 @@ void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 
     out->score = best; out->te = best_i;
     out->qe = -1; out->score2 = -1; out->te2 = -1; out->tb = -1; out->qb = -1;
-    if (best != 255) {                                  /* (:549-567) */
+    if (no_sat || best != 255) {                        /* (:549-567) */
         out->qe = best_j;
         if (nb > 0) {
             int tmp = (best + qmax - 1) / qmax;
@@ -292,6 +295,12 @@ void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
     free(H); free(E); free(prof); free(bsc); free(bte);
 }
 
+void orc_sw_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  int m, const orc_opt_t *opt, int xtra, orc_aln_t *out)
+{
+    orc_sw_align_ex(qlen, query, tlen, target, m, opt, xtra, 0, out);
+}
+
 static void flip(int n, uint8_t *s)                     /* revSeq (:572-581) */
 {
     for (int i = 0; i < (n >> 1); ++i) { uint8_t c = s[i]; s[i] = s[n - 1 - i]; s[n - 1 - i] = c; }
@@ -301,13 +310,19 @@ static void flip(int n, uint8_t *s)                     /* revSeq (:572-581) */
 void orc_sw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target,
                    int m, const orc_opt_t *opt, int xtra, orc_aln_t *out)
 {
-    orc_sw_align(qlen, query, tlen, target, m, opt, xtra, out);
+    orc_sw_align2_ex(qlen, query, tlen, target, m, opt, xtra, 0, out);
+}
+
+void orc_sw_align2_ex(int qlen, uint8_t *query, int tlen, uint8_t *target,
+                      int m, const orc_opt_t *opt, int xtra, int no_sat, orc_aln_t *out)
+{
+    orc_sw_align_ex(qlen, query, tlen, target, m, opt, xtra, no_sat, out);
     if ((xtra & ORC_XSTART) == 0 || ((xtra & ORC_XSUBO) && out->score < (xtra & 0xffff))) return;
     orc_aln_t rev;
     flip(out->qe + 1, query);
     flip(out->te + 1, target);
     /* QUIRK: the reverse pass keeps the FULL tlen (:590) */
-    orc_sw_align(out->qe + 1, query, tlen, target, m, opt, ORC_XSTOP | out->score, &rev);
+    orc_sw_align_ex(out->qe + 1, query, tlen, target, m, opt, ORC_XSTOP | out->score, no_sat, &rev);
     flip(out->qe + 1, query);
     flip(out->te + 1, target);
     out->cells += rev.cells;
@@ -450,7 +465,8 @@ static void orc_al_body(int32_t k, void *vctx)
     memcpy(q, c->seqs + jb->q_off, (size_t)jb->q_len);
     memcpy(t, c->seqs + jb->t_off, (size_t)jb->t_len);
     orc_aln_t a;
-    orc_sw_align2(jb->q_len, q, jb->t_len, t, 5, &c->opt, jb->xtra, &a);
+    /* pad bit 0: native ksw_align2 semantics for this job -- 16-bit (no saturation) when KSW_XBYTE is clear */
+    orc_sw_align2_ex(jb->q_len, q, jb->t_len, t, 5, &c->opt, jb->xtra, (jb->pad & 1) && !(jb->xtra & ORC_XBYTE), &a);
     int32_t *o = c->out7 + (size_t)7 * k;
     o[0] = a.score; o[1] = a.te; o[2] = a.qe; o[3] = a.score2; o[4] = a.te2; o[5] = a.tb; o[6] = a.qb;
     if (c->cells) c->cells[k] = a.cells;
@@ -633,11 +649,134 @@ static void orc_mate_precompute(const orc_opt_t *opt, int64_t l_pac, const orc_p
     free(upd); free(last); free(rev);
 }
 
+/* mem_matesw_precompute of the NATIVE library the MateSWJNI seam replaces (N/bwamem_pair.c:159-228), restated:
+ * the "native semantics" mode of the mate-rescue driver.  Against the Scala routine above it differs in
+ *   - the non-reversed coordinate map: rb = rBeg + tb, re = rBeg + te + 1 (:206-207; Scala :1203-1204 has the quirk);
+ *   - the mate list is edited in place: a hit is inserted before the first OLD element with a smaller score
+ *     (:213-219) and mem_sort_and_dedup runs on the list itself after every orientation (:222), so the next
+ *     orientation sees the de-duplicated list (Scala: append + ascending stable sort, dedup on a copy);
+ *   - mem_sort_and_dedup sorts by rEnd only (N/bwamem.c:385-398; Scala sorts by (rEnd, rBeg)); ties are kept in
+ *     arrival order here, the C's introsort leaves them in an implementation-defined order;
+ *   - ksw_align2 runs 16-bit, i.e. without saturation, when l_ms * a >= 250 (:200, N/ksw.c:349-351).
+ * Used to pin the driver against the reference's own compiled bwamem_pair.c (tests/test_matesw_ref.py). */
+static int orc_sort_dedup_native(orc_pool_t *p, int *lst, int n, float mask_level_redun)
+{
+    if (n <= 1) return n;
+    orc_alnreg_t *R = p->pool;
+    orc_key3 *keys = (orc_key3 *)malloc((size_t)n * sizeof(orc_key3));
+    for (int i = 0; i < n; ++i) { keys[i].a = R[lst[i]].re; keys[i].b = 0; keys[i].c = 0; }
+    stable_sort_idx(lst, keys, n);
+    for (int i = 1; i < n; ++i) {
+        orc_alnreg_t *ri = &R[lst[i]];
+        if (ri->rb >= R[lst[i - 1]].re) continue;
+        for (int j = i - 1; j >= 0 && ri->rb < R[lst[j]].re; --j) {
+            orc_alnreg_t *rj = &R[lst[j]];
+            if (rj->qe == rj->qb) continue;
+            const int64_t orr = rj->re - ri->rb;
+            const int64_t oq = rj->qb < ri->qb ? rj->qe - ri->qb : ri->qe - rj->qb;
+            const int64_t mr = rj->re - rj->rb < ri->re - ri->rb ? rj->re - rj->rb : ri->re - ri->rb;
+            const int64_t mq = rj->qe - rj->qb < ri->qe - ri->qb ? rj->qe - rj->qb : ri->qe - ri->qb;
+            if ((float)orr > mask_level_redun * (float)mr && (float)oq > mask_level_redun * (float)mq) {
+                if (ri->score < rj->score) { ri->qe = ri->qb; break; }
+                rj->qe = rj->qb;
+            }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (R[lst[i]].qe > R[lst[i]].qb) lst[m++] = lst[i];
+    for (int i = 0; i < m; ++i) { keys[i].a = -(int64_t)R[lst[i]].score; keys[i].b = R[lst[i]].rb; keys[i].c = R[lst[i]].qb; }
+    stable_sort_idx(lst, keys, m);
+    for (int i = 1; i < m; ++i) {
+        orc_alnreg_t *x = &R[lst[i]], *y = &R[lst[i - 1]];
+        if (x->score == y->score && x->rb == y->rb && x->qb == y->qb) x->qe = x->qb;
+    }
+    int m2 = m > 0 ? 1 : 0;                             /* the C keeps a[0] unconditionally (:429) */
+    for (int i = 1; i < m; ++i) if (R[lst[i]].qe > R[lst[i]].qb) lst[m2++] = lst[i];
+    free(keys);
+    return m2;
+}
+
+static void orc_mate_precompute_native(const orc_opt_t *opt, int64_t l_pac, const orc_pestat_t *pes,
+                                       const orc_alnreg_t *a, int mate_len, const uint8_t *mate,
+                                       orc_pool_t *p, int **plst, int *pn, int *pcap,
+                                       const orc_refsw_t *w, const uint8_t *win_seqs, int64_t *n_sw)
+{
+    const int min_seed_len = 19;
+    const float mask_level_redun = 0.95f;
+    int skip[4];
+    for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+    for (int i = 0; i < *pn; ++i) {
+        const orc_alnreg_t *m = &p->pool[(*plst)[i]];
+        int r1 = a->rb >= l_pac, r2 = m->rb >= l_pac;
+        int64_t p2 = r1 == r2 ? m->rb : (l_pac << 1) - 1 - m->rb;
+        int64_t dist = p2 > a->rb ? p2 - a->rb : a->rb - p2;
+        int r = (r1 == r2 ? 0 : 1) ^ (p2 > a->rb ? 0 : 3);
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+    }
+    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return;
+    int n = 0;
+    uint8_t *rev = NULL;
+    for (int r = 0; r < 4; ++r) {
+        if (skip[r]) continue;
+        const int is_rev = ((r >> 1) != (r & 1));
+        const uint8_t *seq = mate;
+        if (is_rev) {
+            if (!rev) rev = (uint8_t *)malloc((size_t)mate_len + 1);
+            for (int i = 0; i < mate_len; ++i) rev[mate_len - 1 - i] = mate[i] < 4 ? (uint8_t)(3 - mate[i]) : 4;
+            seq = rev;
+        }
+        if (w->len[r] == w->re[r] - w->rb[r]) {
+            const int xbyte = mate_len * opt->a < 250;
+            const int xtra = ORC_XSUBO | ORC_XSTART | (xbyte ? ORC_XBYTE : 0) | (min_seed_len * opt->a);
+            uint8_t *q = (uint8_t *)malloc((size_t)mate_len + 1);
+            uint8_t *t = (uint8_t *)malloc((size_t)w->len[r] + 1);
+            memcpy(q, seq, (size_t)mate_len);
+            if (w->len[r] > 0) memcpy(t, win_seqs + w->off[r], (size_t)w->len[r]);
+            orc_aln_t aln;
+            orc_sw_align2_ex(mate_len, q, (int)w->len[r], t, 5, opt, xtra, !xbyte, &aln);
+            free(q); free(t);
+            if (n_sw) ++*n_sw;
+            if (aln.score >= min_seed_len && aln.qb >= 0) {
+                orc_alnreg_t b;
+                memset(&b, 0, sizeof b);
+                b.qb = is_rev ? mate_len - (aln.qe + 1) : aln.qb;
+                b.qe = is_rev ? mate_len - aln.qb : aln.qe + 1;
+                b.rb = is_rev ? (l_pac << 1) - (w->rb[r] + aln.te + 1) : w->rb[r] + aln.tb;
+                b.re = is_rev ? (l_pac << 1) - (w->rb[r] + aln.tb) : w->rb[r] + aln.te + 1;
+                b.score = aln.score; b.csub = aln.score2; b.secondary = -1;
+                const int64_t rl = b.re - b.rb, ql = b.qe - b.qb;
+                b.seedcov = (int)((rl < ql ? rl : ql) >> 1);
+                const int nb = pool_add(p, &b);
+                if (*pn + 1 > *pcap) { *pcap = *pn + 9; *plst = (int *)realloc(*plst, (size_t)*pcap * sizeof(int)); }
+                int at = 0;
+                while (at < *pn && !(p->pool[(*plst)[at]].score < b.score)) ++at;     /* first old element with a smaller score */
+                for (int i = *pn; i > at; --i) (*plst)[i] = (*plst)[i - 1];
+                (*plst)[at] = nb;
+                ++*pn;
+            }
+            ++n;
+        }
+        if (n) *pn = orc_sort_dedup_native(p, *plst, *pn, mask_level_redun);
+    }
+    free(rev);
+}
+
 int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
                      const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                      const orc_alnreg_t *regs, const int32_t *reg_start,
                      const orc_refsw_t *refs, const int32_t *ref_count, const uint8_t *win_seqs,
                      orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start, int64_t *n_sw_calls)
+{
+    return orc_matesw_group_ex(l_pac, pes, group_size, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs,
+                               out_regs, out_cap, out_start, n_sw_calls, 0);
+}
+
+/* native = 0: the Scala driver (the parity target of the seam); native = 1: the native library's semantics */
+int orc_matesw_group_ex(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
+                        const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                        const orc_alnreg_t *regs, const int32_t *reg_start,
+                        const orc_refsw_t *refs, const int32_t *ref_count, const uint8_t *win_seqs,
+                        orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start, int64_t *n_sw_calls, int native)
 {
     orc_opt_t opt;
     orc_default_opt(&opt);
@@ -665,8 +804,12 @@ int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
             const int ib = 1 - i;
             for (int j = 0; j < ref_count[2 * k + i]; ++j) {
                 const orc_alnreg_t a = pool.pool[sel[i][j]];   /* anchor (only rBeg is read) */
-                orc_mate_precompute(&opt, l_pac, pes, &a, seq_len[2 * k + ib], seqs + seq_off[2 * k + ib],
-                                    &pool, &cur[ib], &ncur[ib], &capcur[ib], &refs[ref_pos], win_seqs, n_sw_calls);
+                if (native)
+                    orc_mate_precompute_native(&opt, l_pac, pes, &a, seq_len[2 * k + ib], seqs + seq_off[2 * k + ib],
+                                               &pool, &cur[ib], &ncur[ib], &capcur[ib], &refs[ref_pos], win_seqs, n_sw_calls);
+                else
+                    orc_mate_precompute(&opt, l_pac, pes, &a, seq_len[2 * k + ib], seqs + seq_off[2 * k + ib],
+                                        &pool, &cur[ib], &ncur[ib], &capcur[ib], &refs[ref_pos], win_seqs, n_sw_calls);
                 ++ref_pos;
             }
         }
@@ -682,6 +825,109 @@ int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
     }
     out_start[2 * group_size] = out_n;
     return out_n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Insert-size statistics (S/worker2/MemSamPe.scala:912-1093)                 */
+/* ------------------------------------------------------------------------- */
+/* calSub (:77-100) */
+static int orc_cal_sub(const orc_alnreg_t *r, int n)
+{
+    const float mask_level = 0.5f;                       /* MemOptType.maskLevel */
+    int j = 1, brk = 0;
+    while (j < n && !brk) {
+        int b_max = r[0].qb, e_min = r[0].qe;
+        if (r[j].qb > r[0].qb) b_max = r[j].qb;
+        if (r[j].qe < r[0].qe) e_min = r[j].qe;
+        if (e_min > b_max) {
+            int min_l = r[0].qe - r[0].qb;
+            if (r[j].qe - r[j].qb < min_l) min_l = r[j].qe - r[j].qb;
+            if ((float)(e_min - b_max) >= (float)min_l * mask_level) { brk = 1; --j; }
+        }
+        ++j;
+    }
+    return j < n ? r[j].score : 19 * 1;                  /* minSeedLen * a */
+}
+
+/* memPeStatPrep (:912-945): {dir, dist} of one pair; dist = 0 when the pair does not qualify (PeStatPrepType
+ * defaults).  The Scala dereferences regs(0) of a non-null EMPTY array (an exception there); empty = not qualified here. */
+void orc_pestat_prep(int64_t l_pac, int32_t n_pairs, const orc_alnreg_t *regs, const int32_t *reg_start,
+                     int32_t *dir, int32_t *dist)
+{
+    for (int32_t k = 0; k < n_pairs; ++k) {
+        dir[k] = 0; dist[k] = 0;
+        const orc_alnreg_t *r0 = regs + reg_start[2 * k], *r1 = regs + reg_start[2 * k + 1];
+        const int n0 = reg_start[2 * k + 1] - reg_start[2 * k], n1 = reg_start[2 * k + 2] - reg_start[2 * k + 1];
+        if (n0 <= 0 || n1 <= 0) continue;
+        if (!((double)orc_cal_sub(r0, n0) <= 0.8 * r0[0].score)) continue;       /* MIN_RATIO */
+        if (!((double)orc_cal_sub(r1, n1) <= 0.8 * r1[0].score)) continue;
+        const int s1 = r0[0].rb >= l_pac, s2 = r1[0].rb >= l_pac;
+        int64_t larger = r1[0].rb;
+        if (s1 != s2) larger = (l_pac << 1) - 1 - r1[0].rb;
+        dist[k] = (int32_t)(r0[0].rb - larger);
+        if (larger > r0[0].rb) dist[k] = (int32_t)(larger - r0[0].rb);
+        dir[k] = (s1 == s2 ? 0 : 1) ^ (larger > r0[0].rb ? 0 : 3);
+    }
+}
+
+/* Scala Double.toInt: truncation toward zero, saturating */
+static int orc_d2i(double x)
+{
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return 2147483647;
+    if (x <= -2147483648.0) return (-2147483647 - 1);
+    return (int)x;
+}
+
+/* memPeStatCompute (:991-1093), counting sort included (:955-981) */
+void orc_pestat_compute(int32_t n, const int32_t *dir, const int32_t *dist, int32_t max_ins, orc_pestat_t pes[4])
+{
+    int64_t cnt[4] = {0, 0, 0, 0};
+    int32_t *hist = (int32_t *)calloc((size_t)4 * ((size_t)max_ins + 1), sizeof(int32_t));
+    for (int d = 0; d < 4; ++d) { pes[d].low = pes[d].high = pes[d].failed = pes[d].pad = 0; pes[d].avg = pes[d].std = 0.0; }
+    for (int32_t i = 0; i < n; ++i)
+        if (dist[i] > 0 && dist[i] <= max_ins) { ++hist[(size_t)(dir[i] & 3) * ((size_t)max_ins + 1) + (size_t)dist[i]]; ++cnt[dir[i] & 3]; }
+    for (int d = 0; d < 4; ++d) {
+        const int32_t *h = hist + (size_t)d * ((size_t)max_ins + 1);
+        const int64_t m = cnt[d];
+        if (m < 10) { pes[d].failed = 1; continue; }     /* MIN_DIR_CNT */
+        /* q(k) of the counting-sorted array: smallest v with cumulative count > k */
+        int64_t want[3] = { (int64_t)orc_d2i(0.25 * m + 0.499), (int64_t)orc_d2i(0.50 * m + 0.499), (int64_t)orc_d2i(0.75 * m + 0.499) };
+        int pq[3] = {0, 0, 0};
+        int64_t acc = 0;
+        int got = 0;
+        for (int v = 1; v <= max_ins && got < 3; ++v) {
+            acc += h[v];
+            while (got < 3 && acc > want[got]) pq[got++] = v;
+        }
+        const int p25 = pq[0], p75 = pq[2];
+        pes[d].low = orc_d2i(p25 - 2.0 * (p75 - p25) + 0.499);                   /* OUTLIER_BOUND */
+        if (pes[d].low < 1) pes[d].low = 1;
+        pes[d].high = orc_d2i(p75 + 2.0 * (p75 - p25) + 0.499);
+        double avg = 0.0;
+        int64_t x = 0;
+        for (int v = 1; v <= max_ins; ++v)               /* same summation order as the sorted array */
+            if (v >= pes[d].low && v <= pes[d].high)
+                for (int32_t c = 0; c < h[v]; ++c) { avg += v; ++x; }
+        avg /= (double)x;
+        double sd = 0.0;
+        for (int v = 1; v <= max_ins; ++v)
+            if (v >= pes[d].low && v <= pes[d].high)
+                for (int32_t c = 0; c < h[v]; ++c) sd += (v - avg) * (v - avg);
+        sd = sqrt(sd / (double)x);
+        pes[d].avg = avg; pes[d].std = sd;
+        pes[d].low = orc_d2i(p25 - 3.0 * (p75 - p25) + .499);                    /* MAPPING_BOUND */
+        pes[d].high = orc_d2i(p75 + 3.0 * (p75 - p25) + .499);
+        if (pes[d].low > avg - 4.0 * sd) pes[d].low = orc_d2i(avg - 4.0 * sd + .499);     /* MAX_STDDEV */
+        /* QUIRK (:1066): the high bound is tested against AND replaced by avg MINUS 4 sd (the C has avg + 4 sd on the right, N/bwamem_pair.c:100) */
+        if (pes[d].high < avg - 4.0 * sd) pes[d].high = orc_d2i(avg - 4.0 * sd + .499);
+        if (pes[d].low < 1) pes[d].low = 1;
+    }
+    int64_t mx = 0;
+    for (int d = 0; d < 4; ++d) if (mx < cnt[d]) mx = cnt[d];
+    for (int d = 0; d < 4; ++d)
+        if (pes[d].failed == 0 && (double)cnt[d] < (double)mx * 0.05) pes[d].failed = 1;   /* MIN_DIR_RATIO */
+    free(hist);
 }
 
 /* ------------------------------------------------------------------------- */

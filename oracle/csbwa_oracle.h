@@ -140,6 +140,27 @@ int orc_matesw_group(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
                      orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start,
                      int64_t *n_sw_calls);
 
+/* native = 1: the semantics of the NATIVE library the MateSWJNI seam replaces (N/bwamem_pair.c:115-228) instead of
+ * the Scala driver's -- see orc_mate_precompute_native in the .c for the list of differences.  Pinned against the
+ * reference's own compiled bwamem_pair.c by tests/test_matesw_ref.py. */
+int orc_matesw_group_ex(int64_t l_pac, const orc_pestat_t *pes, int32_t group_size,
+                        const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                        const orc_alnreg_t *regs, const int32_t *reg_start,
+                        const orc_refsw_t *refs, const int32_t *ref_count, const uint8_t *win_seqs,
+                        orc_alnreg_t *out_regs, int32_t out_cap, int32_t *out_start,
+                        int64_t *n_sw_calls, int native);
+/* SWAlign / SWAlign2 with the 16-bit regime of the native ksw_align2 (no saturation) selectable */
+void orc_sw_align_ex(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                     int m, const orc_opt_t *opt, int xtra, int no_sat, orc_aln_t *out);
+void orc_sw_align2_ex(int qlen, uint8_t *query, int tlen, uint8_t *target,
+                      int m, const orc_opt_t *opt, int xtra, int no_sat, orc_aln_t *out);
+
+/* ---- insert-size statistics (S/worker2/MemSamPe.scala:912-945 memPeStatPrep, :991-1093 memPeStatCompute) ----
+ * regs / reg_start: region lists per (pair k, end i), CSR over 2k+i.  dir / dist: PeStatPrepType per pair. */
+void orc_pestat_prep(int64_t l_pac, int32_t n_pairs, const orc_alnreg_t *regs, const int32_t *reg_start,
+                     int32_t *dir, int32_t *dist);
+void orc_pestat_compute(int32_t n, const int32_t *dir, const int32_t *dist, int32_t max_ins, orc_pestat_t pes[4]);
+
 /* ---- SWGlobal (S/util/SWUtil.scala:233-397): banded global alignment + backtrace ----
  * cigar: BAM encoding len << 4 | op (0 = M, 1 = I, 2 = D), forward order, at most cigar_cap
  * entries written.  Returns the score; *n_cigar = number of CIGAR operations. */

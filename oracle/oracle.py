@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libcsbwa_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libksw_ref.so")
 _REF_MEM = os.path.join(_HERE, "_ref", "libbwamem_ref.so")
+_REF_SHIM = os.path.join(_HERE, "_ref", "libref_shim.so")
 
 XBYTE, XSTOP, XSUBO, XSTART = 0x10000, 0x20000, 0x40000, 0x80000
 
@@ -27,9 +28,11 @@ XBYTE, XSTOP, XSUBO, XSTART = 0x10000, 0x20000, 0x40000, 0x80000
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIB) or \
-            os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "csbwa_oracle.c")):
+            os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("csbwa_oracle.c", "csbwa_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "libcsbwa_oracle.so"], stdout=subprocess.DEVNULL)
-    if (force or not os.path.exists(_REF) or not os.path.exists(_REF_MEM)) and os.path.exists("/root/reference/src/main/native/ksw.c"):
+    if (force or not os.path.exists(_REF) or not os.path.exists(_REF_MEM) or not os.path.exists(_REF_SHIM) or
+            os.path.getmtime(_REF_SHIM) < os.path.getmtime(os.path.join(_HERE, "ref_shim.c"))) and \
+            os.path.exists("/root/reference/src/main/native/ksw.c"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -235,9 +238,7 @@ PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("p
 REFSW_DTYPE = np.dtype([("rb", "<i8", (4,)), ("re", "<i8", (4,)), ("len", "<i8", (4,)), ("off", "<i8", (4,))])
 
 
-def matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
-    """Oracle counterpart of jni.MateSWJNI.mateSWJNI (same arguments); also returns the number of
-    SWAlign2 calls the sequential driver actually made."""
+def _flatten_group(pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
     G = int(groupSize)
     pes_a = np.zeros(4, dtype=PESTAT_DTYPE)
     for r in range(4):
@@ -265,19 +266,101 @@ def matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, ref
                 refs[x]["off"][r] = -1
     win_seqs = np.concatenate(wins) if wins else np.zeros(1, np.uint8)
     ref_count = np.asarray(refSWArraySize, dtype=np.int32)
+    return G, pes_a, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs
+
+
+def matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize, native=False):
+    """Oracle counterpart of jni.MateSWJNI.mateSWJNI (same arguments); also returns the number of
+    SWAlign2 calls the sequential driver actually made.  native: the semantics of the native library the
+    seam replaces (N/bwamem_pair.c) instead of the Scala driver's."""
+    G, pes_a, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs = _flatten_group(
+        pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize)
     cap = int(reg_start[-1]) + 4 * len(refSWArray) + 8
     out = np.zeros(cap, dtype=ALNREG_DTYPE)
     out_start = np.zeros(2 * G + 1, dtype=np.int32)
     nsw = C.c_int64(0)
     L = lib()
-    L.orc_matesw_group.argtypes = [C.c_int64, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
-    L.orc_matesw_group.restype = C.c_int
-    n = L.orc_matesw_group(int(pacLen), pes_a.ctypes.data, G, seqs.ctypes.data, seq_off.ctypes.data, seq_len.ctypes.data,
-                           regs.ctypes.data, reg_start.ctypes.data, refs.ctypes.data, ref_count.ctypes.data,
-                           win_seqs.ctypes.data, out.ctypes.data, cap, out_start.ctypes.data, C.addressof(nsw))
+    L.orc_matesw_group_ex.argtypes = [C.c_int64, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_matesw_group_ex.restype = C.c_int
+    n = L.orc_matesw_group_ex(int(pacLen), pes_a.ctypes.data, G, seqs.ctypes.data, seq_off.ctypes.data, seq_len.ctypes.data,
+                              regs.ctypes.data, reg_start.ctypes.data, refs.ctypes.data, ref_count.ctypes.data,
+                              win_seqs.ctypes.data, out.ctypes.data, cap, out_start.ctypes.data, C.addressof(nsw), int(native))
     if n < 0:
         raise RuntimeError("orc_matesw_group failed: %d" % n)
     return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)], nsw.value
+
+
+_shim = None
+
+
+def ref_shim():
+    """oracle/_ref/libref_shim.so: flat drivers around the REFERENCE's own compiled mem_group_matesw / mem_pestat."""
+    global _shim
+    if _shim is None:
+        path = os.path.join(_HERE, "_ref", "libref_shim.so")
+        if not os.path.exists(path):
+            return None
+        _shim = C.CDLL(path)
+    return _shim
+
+
+def ref_matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize):
+    """The same call served by the reference's own C (mem_group_matesw, N/bwamem_pair.c:115-228) through the shim."""
+    G, pes_a, seqs, seq_off, seq_len, regs, reg_start, refs, ref_count, win_seqs = _flatten_group(
+        pes, groupSize, seqsPairs, mateSWArray, refSWArray, refSWArraySize)
+    cap = int(reg_start[-1]) + 4 * len(refSWArray) + 8
+    out = np.zeros(cap, dtype=ALNREG_DTYPE)
+    out_start = np.zeros(2 * G + 1, dtype=np.int32)
+    S = ref_shim()
+    S.refshim_group_matesw.argtypes = [C.c_int64, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int32, C.c_void_p]
+    S.refshim_group_matesw.restype = C.c_int
+    n = S.refshim_group_matesw(int(pacLen), pes_a.ctypes.data, G, seqs.ctypes.data, seq_off.ctypes.data, seq_len.ctypes.data,
+                               regs.ctypes.data, reg_start.ctypes.data, refs.ctypes.data, ref_count.ctypes.data,
+                               win_seqs.ctypes.data, out.ctypes.data, cap, out_start.ctypes.data)
+    if n < 0:
+        raise RuntimeError("refshim_group_matesw failed: %d" % n)
+    return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)]
+
+
+def _flatten_regs(reg_lists):
+    n = len(reg_lists)
+    reg_start = np.zeros(n + 1, dtype=np.int32)
+    for x in range(n):
+        reg_start[x + 1] = reg_start[x] + len(reg_lists[x])
+    regs = np.zeros(max(1, int(reg_start[-1])), dtype=ALNREG_DTYPE)
+    for x in range(n):
+        for j, rg in enumerate(reg_lists[x]):
+            regs[reg_start[x] + j] = rg
+    return regs, reg_start
+
+
+def pestat(pacLen, reg_lists, max_ins=10000):
+    """memPeStatPrep + memPeStatCompute (S/worker2/MemSamPe.scala:912-1093) over region lists indexed 2k+i.
+    Returns (pes structured array[4], dir, dist)."""
+    regs, reg_start = _flatten_regs(reg_lists)
+    n_pairs = len(reg_lists) // 2
+    d = np.zeros(max(1, n_pairs), dtype=np.int32)
+    ds = np.zeros(max(1, n_pairs), dtype=np.int32)
+    L = lib()
+    L.orc_pestat_prep.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_pestat_prep.restype = None
+    L.orc_pestat_compute.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.orc_pestat_compute.restype = None
+    L.orc_pestat_prep(int(pacLen), n_pairs, regs.ctypes.data, reg_start.ctypes.data, d.ctypes.data, ds.ctypes.data)
+    pes = np.zeros(4, dtype=PESTAT_DTYPE)
+    L.orc_pestat_compute(n_pairs, d.ctypes.data, ds.ctypes.data, int(max_ins), pes.ctypes.data)
+    return pes, d[:n_pairs], ds[:n_pairs]
+
+
+def ref_pestat(pacLen, reg_lists):
+    """The reference's own mem_pestat (N/bwamem_pair.c:50-112) through the shim."""
+    regs, reg_start = _flatten_regs(reg_lists)
+    pes = np.zeros(4, dtype=PESTAT_DTYPE)
+    S = ref_shim()
+    S.refshim_pestat.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    S.refshim_pestat.restype = C.c_int
+    S.refshim_pestat(int(pacLen), len(reg_lists) // 2, regs.ctypes.data, reg_start.ctypes.data, pes.ctypes.data)
+    return pes
 
 
 # --------------------------------------------------------------------------

@@ -182,7 +182,7 @@ extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, 
     for (int k = 0; k < n; ++k) {
         const AlnJob &jb = jobs[k];
         const uint8_t *q = seqs + jb.q_off, *t = seqs + jb.t_off;
-        int cls = aln_class_of(o, jb.q_len, jb.t_len);
+        int cls = aln_class_of(o, jb.q_len, jb.t_len, jb.xtra, jb.pad);
         if (force_generic) cls = 0;
         AlnRes r;
         long long c = 0;
@@ -190,7 +190,7 @@ extern "C" int emu_align2_batch(const AlnJob *jobs, int n, const uint8_t *seqs, 
             const int qn = jb.q_len > 0 ? jb.q_len : 0, tn = jb.t_len > 0 ? jb.t_len : 0;
             std::vector<int> buf((size_t)2 * (tn / 2 + 2) + 2 * (qn + 2));
             int *bsc = buf.data(), *bte = bsc + (tn / 2 + 2), *H = bte + (tn / 2 + 2), *E = H + (qn + 2);
-            c = sw_align2_generic(o, q, qn, t, tn, jb.xtra, H, E, bsc, bte, r);
+            c = sw_align2_generic(o, q, qn, t, tn, jb.xtra, H, E, bsc, bte, r, aln_job_nosat(jb.xtra, jb.pad));
         } else {
             ++nf;
             if (cls == 1) c = emu_align2_half<8>(o, q, jb.q_len, t, jb.t_len, jb.xtra, r);

@@ -118,3 +118,12 @@ def test_wire_roundtrip_through_oracle(pkg, oracle):
         assert (int(r[0]) | (int(r[1]) << 16), int(r[2]), int(r[3]), int(r[4]), int(r[5]), int(r[6]), int(r[7]), int(r[8])) == \
             (k, e["q_beg"], e["q_end"], e["r_beg"], e["r_end"], e["score"], e["true_score"], e["width"])
         assert cells[k] == e["cells"]
+
+
+def test_numpy_packer_is_byte_identical(pkg):
+    """workload.pack_ext_from_seeds_np (what bench.py's reference arm builds its calls with, so that its process never
+    maps libcsbwa_sw.so) == csbwa_pack_ext_from_seeds, byte for byte."""
+    for L, eps in ((151, 0.01), (101, 0.02), (250, 0.05)):
+        a = pkg.workload.ext_workload(1500, L, 300000, eps, 400, 50, 5, reads_per_call=512)["bufs"]
+        b = pkg.workload.ext_workload(1500, L, 300000, eps, 400, 50, 5, reads_per_call=512, numpy_packer=True)["bufs"]
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))

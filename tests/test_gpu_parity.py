@@ -363,8 +363,10 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
 
 
 @pytest.mark.parametrize("env", [{"CSBWA_CO_SLOTS": "3", "CSBWA_CO_INFLIGHT": "1"},
-                                 {"CSBWA_CO_ONE_GRAPH": "1", "CSBWA_CO_INFLIGHT": "4"},
-                                 {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_SLOTS": "2"}])
+                                 {"CSBWA_CO_ONE_GRAPH": "1", "CSBWA_CO_INFLIGHT": "4", "CSBWA_CO_COPY": "sm"},
+                                 {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_SLOTS": "2"},
+                                 {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_COPY": "sm"},
+                                 {"CSBWA_CO_COPY": "dma", "CSBWA_CO_SLOTS": "32"}])
 def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):
     """The host seam's tuning knobs (slots, groups in flight, graph variants, no graph) never change a bit: 12 caller
     threads, calls of three different sizes so that groups of all graph size classes occur; every third call uses

@@ -502,8 +502,10 @@ def aln_reg_ref(ref, pes, reg_rb, mate_len):
     return out
 
 
-def gen_matesw_group(rng, pkg, ref, G, L, pes, p_anchor=0.85, p_mate_present=0.4):
-    """Synthetic input of the MateSWJNI seam: reads, current region lists, windows of the selected regions."""
+def gen_matesw_group(rng, pkg, ref, G, L, pes, p_anchor=0.85, p_mate_present=0.4, p_same_strand=0.0):
+    """Synthetic input of the MateSWJNI seam: reads, current region lists, windows of the selected regions.
+    p_same_strand: fraction of pairs whose mate lies on the anchor's strand (FF), so that the non-reversed
+    orientations rescue something."""
     l_pac = len(ref)
     mk = pkg.jni.make_alnreg
     seqs, reg_lists = [], []
@@ -513,11 +515,13 @@ def gen_matesw_group(rng, pkg, ref, G, L, pes, p_anchor=0.85, p_mate_present=0.4
         r1 = mutate(rng, ref[p:p + L], 0.01)[:L]
         r1 = np.concatenate([r1, rng.integers(0, 4, L - len(r1)).astype(np.uint8)])
         frag2 = ref[p + ins - L:p + ins]
-        r2 = mutate(rng, (3 - frag2[::-1]).astype(np.uint8), 0.01)[:L]
+        same = rng.random() < p_same_strand
+        r2 = mutate(rng, frag2.copy() if same else (3 - frag2[::-1]).astype(np.uint8), 0.01)[:L]
         r2 = np.concatenate([r2, rng.integers(0, 4, L - len(r2)).astype(np.uint8)])
         seqs += [r1, r2]
+        rb2 = p + ins - L if same else 2 * l_pac - (p + ins)
         true = [mk(p, p + L, 0, L, L - int(rng.integers(0, 12)), L - 12, 0, 0, 0, 100, L - 20, -1, 7),
-                mk(2 * l_pac - (p + ins), 2 * l_pac - (p + ins) + L, 0, L, L - int(rng.integers(0, 12)), L - 12, 0, 0, 0, 100, L - 20, -1, 9)]
+                mk(rb2, rb2 + L, 0, L, L - int(rng.integers(0, 12)), L - 12, 0, 0, 0, 100, L - 20, -1, 9)]
         for i in range(2):
             lst = []
             present = rng.random() < (p_anchor if i == 0 else p_mate_present)
