@@ -158,7 +158,7 @@ __device__ __forceinline__ void aln_half_pass(const SwOpt &o, bool act, const ui
     bk_out.best_j = __shfl_sync(FULL, bk.best_j, own);
     bk_out.nb = __shfl_sync(FULL, bk.nb, own);
     bk_out.min_sc = bk.min_sc; bk_out.end_sc = bk.end_sc; bk_out.sat = bk.sat;
-    bk_out.stop = false; bk_out.last_te = 0; bk_out.last_sc = 0;
+    bk_out.stop = false; bk_out.last_te = 0; bk_out.last_sc = 0; bk_out.nosat = false;
     rows_done = __shfl_sync(FULL, rows, own);
     __syncwarp();
 }

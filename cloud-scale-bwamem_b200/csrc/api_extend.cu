@@ -7,6 +7,9 @@
 #include <memory>
 #include <string>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "host_common.hpp"
 #define CSBWA_E_BADWIRE_DEV CSBWA_E_BADWIRE
@@ -41,6 +44,10 @@ static int ensure_dev_attrs(int dev)
     const int big_p2l = 128 * EXT_BD_LONG * 10;      // the 256-column class at one warp per block
     CU_TRY(cudaFuncSetAttribute((k_ext_side<0, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     CU_TRY(cudaFuncSetAttribute((k_ext_side<1, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<0, EXT_BD>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<1, EXT_BD>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<0, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<1, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     g_ext_attrs[dev] = true;
     return CSBWA_OK;
 }
@@ -121,13 +128,21 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
         } else if (core == EXT_CORE_P2) {
             // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
             const int npairs = cap / 2;
-            const bool lng = cls <= 2;                      // 256 / 192 columns: one warp per block
+            static const int one_warp_cls = env_int("CSBWA_EXT_ONE_WARP_CLS", 2, 0, 6);
+            const bool lng = cls <= one_warp_cls;           // 256 / 192 columns: one warp per block
             const int bd = lng ? EXT_BD_LONG : EXT_BD;      // the core is compiled for these strides
             const size_t smem = (size_t)npairs * bd * 10;
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 96);
             if (grid > cap_grid) grid = cap_grid;
-            if (lng)
+            // CSBWA_EXT_REFILL=0: the chunked kernel (a warp takes 32 jobs and lasts as long as the longest); default: lanes
+            // are refilled from the class cursor as their sides end
+            static const int refill = env_int("CSBWA_EXT_REFILL", 1, 0, 1);
+            if (refill && lng)
+                k_ext_side_rf<SIDE, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls, npairs);
+            else if (refill)
+                k_ext_side_rf<SIDE, EXT_BD><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls, npairs);
+            else if (lng)
                 k_ext_side<SIDE, EXT_CORE_P2, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                                                     d_out, d_cells, cls, npairs);
             else
@@ -616,7 +631,42 @@ void csw::destroy_coalescers()
 static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out, int32_t n, int device);
 
 struct MemcpyUser { const uint8_t *in; int16_t *out; };
-static void fill_memcpy(void *user, uint8_t *dst, int in_bytes) { memcpy(dst, ((MemcpyUser *)user)->in, (size_t)in_bytes); }
+// Staging copies use NON-TEMPORAL stores (CSBWA_CO_NTCOPY=0 turns this off): the bytes are read next by the GPU over
+// PCIe, not by a CPU, and every device read of a line that sits dirty in some core's cache has to snoop it out --
+// measured on the 16-vCPU box, 64 callers with pageable buffers: 437 GCUPS end to end with memcpy, 768 with streaming
+// stores (a group's time on the device 1.87 -> 0.92 ms).
+static bool nt_copy_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CSBWA_CO_NTCOPY"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+extern "C" void csbwa_stream_copy(void *dst_v, const void *src_v, int64_t n)
+{
+    uint8_t *dst = (uint8_t *)dst_v;
+    const uint8_t *src = (const uint8_t *)src_v;
+    if (n <= 0) return;
+#if defined(__SSE2__)
+    if (nt_copy_enabled() && n >= 256) {
+        size_t head = (size_t)(-(intptr_t)dst & 15);          // bytes up to the first 16-byte boundary of dst
+        if (head) { memcpy(dst, src, head); dst += head; src += head; n -= (int64_t)head; }
+        const size_t n64 = (size_t)n / 64;
+        const __m128i *s = (const __m128i *)src;
+        __m128i *d = (__m128i *)dst;
+        for (size_t i = 0; i < n64; ++i) {
+            const __m128i a = _mm_loadu_si128(s + 4 * i), b = _mm_loadu_si128(s + 4 * i + 1);
+            const __m128i c = _mm_loadu_si128(s + 4 * i + 2), e = _mm_loadu_si128(s + 4 * i + 3);
+            _mm_stream_si128(d + 4 * i, a); _mm_stream_si128(d + 4 * i + 1, b);
+            _mm_stream_si128(d + 4 * i + 2, c); _mm_stream_si128(d + 4 * i + 3, e);
+        }
+        memcpy(dst + 64 * n64, src + 64 * n64, (size_t)n - 64 * n64);
+        _mm_sfence();
+        return;
+    }
+#endif
+    memcpy(dst, src, (size_t)n);
+}
+static void fill_memcpy(void *user, uint8_t *dst, int in_bytes) { csbwa_stream_copy(dst, ((MemcpyUser *)user)->in, in_bytes); }
 static void drain_memcpy(void *user, const int16_t *src, int n_shorts) { memcpy(((MemcpyUser *)user)->out, src, (size_t)n_shorts * 2); }
 
 // shared body of the two host entries: rq.hdr / in_bytes / n_tasks / fill / drain / user are set by the caller

@@ -18,8 +18,9 @@
 //     rescan only when a zero lies right of the max.
 // Per column pair: 2 PRMT/SHF + 11 DPX/ALU + 5 FMA-pipe instructions, i.e. ~8 ALU-pipe slots per
 // cell against ~16 of the one-column core.  Scores are bounded by 511 (h0 + qlen*max(mat)), so the
-// 250 bp configs stay on the fast path.  Band edges that split a pair are handled by a scalar
-// single-column step before / after the pair loop, so no lane ever computes an out-of-band cell.
+// 250 bp configs stay on the fast path.  A band edge that splits a pair is handled inside the packed step of the
+// first / last pair (the out-of-band half is neutralised, not skipped by a branch): the edges' parities differ from
+// lane to lane in every row, and a scalar edge column cost the whole warp its ~45 instructions almost every row.
 #pragma once
 #include "sw_common.cuh"
 
@@ -53,25 +54,23 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 #endif
 }
 
+// One SWExtend call as a row-granular state machine: start() = profile-independent set-up (first row, band
+// clamp), row() = one target row (false once the call is over: rows exhausted, an all-zero row, or the z-drop),
+// result().  sw_extend_p2 below simply runs it to completion; the refilling side kernel (ext_kernels.cuh) steps
+// the calls of its 32 lanes row by row and hands a finished lane its next job while the others keep going.
 // STRIDE: compile-time element stride between consecutive pairs (threads per block on the device, so
 // the unrolled pair loop addresses shared memory with immediate offsets); 0 = use stride_rt
-template <int STRIDE>
-CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_rt, int qlen,
-                         const uint32_t *words, int t_nib, int tlen,
-                         int w, int end_bonus, int h0, SwExtRes &res)
-{
-    const int stride = STRIDE ? STRIDE : stride_rt;
-    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-    const int e_del = o.e_del, e_ins = o.e_ins, zdrop = o.zdrop;
-    const int ne_ins = -e_ins;
-    const uint32_t ne_del2 = pk16(-e_del, -e_del);
-    const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
-    uint16_t *h16 = (uint16_t *)he;
-    const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
-#define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
-#define P2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
-    // first row (:96-104): Hs[c] = eh[c+1].h, E = 0
+struct P2Run {
+    int qlen, tlen, h0, w;
+    int i, beg, end, best, best_i, best_j, best_ie, gscore, max_off, cells, hm1;
+    NibStream ts;
+
+    CSW_HD void start(const SwOpt &o, P2Pair *he, int stride, int qlen_, const uint32_t *words, int t_nib, int tlen_,
+                      int w_, int end_bonus, int h0_)
     {
+        qlen = qlen_; tlen = tlen_; h0 = h0_;
+        const int oe_ins = o.o_ins + o.e_ins, e_ins = o.e_ins;
+        // first row (:96-104): Hs[c] = eh[c+1].h, E = 0
         int v = h0 > oe_ins ? h0 - oe_ins : 0;
         const int np = p2_pairs(qlen);
         for (int p = 0; p < np; ++p) {
@@ -80,14 +79,28 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
             P2Pair x; x.h2 = (uint32_t)lo | ((uint32_t)hi << 16); x.e2 = 0;
             he[(size_t)p * stride] = x;
         }
+        w = clamp_band(o, w_, qlen, end_bonus);
+        best = h0; best_i = -1; best_j = -1; best_ie = -1; gscore = -1; max_off = 0;
+        beg = 0; end = qlen; cells = 0;
+        hm1 = h0;                                      // H(i-1, -1)
+        i = 0;
+        if (tlen > 0) ts.init(words, t_nib);
     }
-    w = clamp_band(o, w, qlen, end_bonus);
-    int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
-    int beg = 0, end = qlen, cells = 0;
-    int hm1 = h0;                                      // H(i-1, -1)
-    NibStream ts;
-    if (tlen > 0) ts.init(words, t_nib);
-    for (int i = 0; i < tlen; ++i) {
+
+    template <int STRIDE>
+    CSW_HD bool row(const SwOpt &o, P2Pair *he, const uint16_t *sel, int stride_rt)
+    {
+        if (i >= tlen) return false;
+        const int stride = STRIDE ? STRIDE : stride_rt;
+        const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+        const int e_del = o.e_del, e_ins = o.e_ins, zdrop = o.zdrop;
+        const int ne_ins = -e_ins;
+        const uint32_t ne_del2 = pk16(-e_del, -e_del);
+        const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
+        uint16_t *h16 = (uint16_t *)he;
+        const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
+#define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
+#define P2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
         int t = ts.next(); if (t > 4) t = 4;
         const uint32_t tlo = o.tlo[t], thi = o.thi[t];
         const int h1i = imax(h0 - (o.o_del + e_del * (i + 1)), 0);
@@ -96,39 +109,67 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
         uint32_t key2 = 0, zk2 = 0xffffffffu;          // zk2: packed MIN of (h << 7 | pair) ^ 127: smallest h, then last pair
         int hlast = h1i;
         if (beg < end) {
-            int dg = beg == 0 ? hm1 : (int)P2_H(beg - 1);          // H(i-1, beg-1)
-            if (beg > 0) P2_H(beg - 1) = (uint16_t)h1i;            // H(i, beg-1) := first-column value
-            int f = 0, c = beg;
-            const int pe = end >> 1;
-            // one column, scalar (band edge inside a pair)
-#define P2_COLUMN()                                                                               \
-            {                                                                                     \
-                const int lane = c & 1, p = c >> 1;                                               \
-                const int hold = (int)P2_H(c), e = (int)P2_E(c);                                  \
-                const uint32_t sl = sel[(size_t)p * stride];                                      \
-                const int s = (int)(int16_t)((prmt(tlo, thi, sl) >> (16 * lane)) & 0xffffu);      \
-                int h = imax(imax(dg + s, e), f);                                                 \
-                P2_H(c) = (uint16_t)h;                                                            \
-                P2_E(c) = (uint16_t)imax(e - e_del, imax(h - oe_del, 0));                         \
-                f = imax(f - e_ins, imax(h - oe_ins, 0));                                         \
-                key2 = umax2(key2, (uint32_t)(h * 128 + p) << (16 * lane));                       \
-                zk2 = umin2(zk2, ((uint32_t)((h * 128 + p) ^ 127) << (16 * lane)) | (0xffff0000u >> (16 * lane))); \
-                dg = hold; hlast = h; ++c;                                                        \
+            // The band [beg, end) is walked pair by pair from pb to pl.  A band edge that splits a pair does not get
+            // a scalar column step: the FIRST and the LAST pair run the same packed step with the out-of-band half
+            // neutralised -- its g forced to 0 (so F enters the band as 0), its H / E written back as the reference
+            // leaves them (eh[beg].h = h1 for the column left of the band, eh[end] = {unchanged, 0} for the column
+            // right of it) and its keys removed from the row maximum / zero search.  No lane branches on the parity
+            // of its edges, which differ from lane to lane in every row.
+            const int pb = beg >> 1, pl = (end - 1) >> 1;
+            const uint32_t lo_out = (beg & 1) ? 0x0000ffffu : 0u;      // column beg - 1 shares the first pair
+            const uint32_t hi_out = (end & 1) ? 0xffff0000u : 0u;      // column end shares the last pair
+            P2Pair *ph = he + (size_t)pb * stride;
+            uint32_t hprev2 = (uint32_t)hm1 << 16;                     // beg == 0: the diagonal is H(i-1, -1)
+            if (!lo_out && beg > 0) {                                  // column beg - 1 = high half of the pair before pb
+                uint16_t *hp = (uint16_t *)(ph - stride) + 1;
+                hprev2 = (uint32_t)*hp << 16;                          // H(i-1, beg-1)
+                *hp = (uint16_t)h1i;                                   // H(i, beg-1) := first-column value
             }
-            if (c & 1) P2_COLUMN()
-            int p = c >> 1;
-            if (p < pe) {
-                uint32_t hprev2 = (uint32_t)dg << 16;
-                uint32_t pp2 = (uint32_t)p * 0x00010001u;
-                P2Pair *ph = he + (size_t)p * stride;
-                const uint16_t *ps = sel + (size_t)p * stride;
-                uint32_t h2 = 0;
-                P2Pair cur = *ph;
-                uint32_t sl = ld_u16(ps);
-                for (; p < pe; ++p) {
+            int f = 0;
+            const uint16_t *ps = sel + (size_t)pb * stride;
+            uint32_t pp2 = (uint32_t)pb * 0x00010001u;
+            uint32_t h2 = 0;
+            P2Pair cur = *ph;
+            uint32_t sl = ld_u16(ps);
+            // one pair with `out` = halves outside the band (0 for an inner pair)
+#define P2_EDGE_STEP(out)                                                                                  \
+            {                                                                                              \
+                const P2Pair x = cur;                                                                      \
+                const uint32_t sx = sl;                                                                    \
+                cur = ph[stride];                                  /* pair p + 1 always exists (p2_pairs) */ \
+                sl = ld_u16(ps + stride);                                                                  \
+                const uint32_t keep = ~(out);                                                              \
+                const uint32_t s2 = prmt(tlo, thi, sx);                                                    \
+                const uint32_t hd2 = funnel16(hprev2, x.h2);                                               \
+                hprev2 = x.h2;                                                                             \
+                const uint32_t hp2 = addmax2(hd2, s2, x.e2);                                               \
+                const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2) & keep;                          \
+                const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));                                     \
+                const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));                                        \
+                const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);                               \
+                h2 = max2(hp2, f2);                                                                        \
+                const uint32_t e2n = addmax2(x.e2, ne_del2, addmax2_relu(h2, noe_del2, noe_del2));         \
+                /* out-of-band halves: H := {h1i | unchanged}, E := {unchanged | 0} */                   \
+                const uint32_t oh = (uint32_t)h1i | (x.h2 & 0xffff0000u), oe = x.e2 & 0x0000ffffu;         \
+                P2Pair y;                                                                                  \
+                y.h2 = (h2 & keep) | (oh & (out));                                                         \
+                y.e2 = (e2n & keep) | (oe & (out));                                                        \
+                *ph = y;                                                                                   \
+                const uint32_t kp2 = umad(h2, 128u, pp2);                                                  \
+                key2 = umax2(key2, kp2 & keep);                                                            \
+                zk2 = umin2(zk2, (kp2 ^ 0x007f007fu) | (out));                                             \
+                f = fn;                                                                                    \
+                pp2 += 0x00010001u;                                                                        \
+                ph += stride; ps += stride;                                                                \
+            }
+            if (pb == pl) {
+                P2_EDGE_STEP(lo_out | hi_out)
+            } else {
+                P2_EDGE_STEP(lo_out)
+                for (int p = pb + 1; p < pl; ++p) {
                     const P2Pair x = cur;
                     const uint32_t sx = sl;
-                    cur = ph[stride];                              // pair p + 1 always exists (p2_pairs)
+                    cur = ph[stride];
                     sl = ld_u16(ps + stride);
                     const uint32_t s2 = prmt(tlo, thi, sx);
                     const uint32_t hd2 = funnel16(hprev2, x.h2);
@@ -151,14 +192,12 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
                     pp2 += 0x00010001u;
                     ph += stride; ps += stride;
                 }
-                dg = (int)(hprev2 >> 16);
-                hlast = (int)(h2 >> 16);
-                c = 2 * pe;
+                P2_EDGE_STEP(hi_out)
             }
-            if (c < end) P2_COLUMN()
-#undef P2_COLUMN
+#undef P2_EDGE_STEP
+            hlast = hi_out ? (int)(h2 & 0xffffu) : (int)(h2 >> 16);     // H(i, end-1)
             cells += end - beg;
-            P2_E(end) = 0;                                         // eh(end) = {h1, 0}
+            if (!hi_out) P2_E(end) = 0;                                // eh(end) = {h1, 0}
         }
         hm1 = h1i;
         const int jfin = beg < end ? end : beg;
@@ -167,7 +206,7 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
         // doubling them (+1 for the odd lane) turns them into h << 8 | column, one max merges them.
         const int kk = imax((int)((key2 & 0xffffu) << 1), (int)((key2 >> 16) << 1) | 1);
         const int rm = kk >> 8, rmj = kk & 255;
-        if (rm == 0) break;
+        if (rm == 0) return false;
         if (rm > best) {
             best = rm; best_i = i; best_j = rmj;
             int off = rmj - i; if (off < 0) off = -off;
@@ -175,8 +214,8 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
         } else if (zdrop > 0) {
             const int di = i - best_i, dj = rmj - best_j;
             if (di > dj) {
-                if (best - rm - (di - dj) * e_del > zdrop) break;
-                else if (best - rm - (dj - di) * e_ins > zdrop) break;
+                if (best - rm - (di - dj) * e_del > zdrop) return false;
+                else if (best - rm - (dj - di) * e_ins > zdrop) return false;
             }
         }
         // band shrink (:201-214) in own-column terms: eh[j].h == (j == beg ? h1i : Hs[j-1])
@@ -196,11 +235,28 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
             nend = end + 1;
         }
         beg = nbeg; end = nend;
-    }
+        ++i;
+        return true;
 #undef P2_H
 #undef P2_E
-    res.score = best; res.qle = best_j + 1; res.tle = best_i + 1;
-    res.gtle = best_ie + 1; res.gscore = gscore; res.max_off = max_off; res.cells = cells;
+    }
+
+    CSW_HD void result(SwExtRes &res) const
+    {
+        res.score = best; res.qle = best_j + 1; res.tle = best_i + 1;
+        res.gtle = best_ie + 1; res.gscore = gscore; res.max_off = max_off; res.cells = cells;
+    }
+};
+
+template <int STRIDE>
+CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_rt, int qlen,
+                         const uint32_t *words, int t_nib, int tlen,
+                         int w, int end_bonus, int h0, SwExtRes &res)
+{
+    P2Run r;
+    r.start(o, he, STRIDE ? STRIDE : stride_rt, qlen, words, t_nib, tlen, w, end_bonus, h0);
+    while (r.template row<STRIDE>(o, he, sel, stride_rt)) {}
+    r.result(res);
 }
 
 } // namespace csw

@@ -208,6 +208,8 @@ CSW_HD void finish_opt(SwOpt &o)
 // toward zero, saturating, NaN -> 0.
 CSW_HD int scala_div_plus1(int num, int den)
 {
+    // e = 1 (the MemOptType default): num / 1.0 + 1.0 is exact, no double-precision divide needed
+    if (den == 1 && num < 2147483646 && num > -2147483647) return num + 1;
     double x = (double)num / (double)den + 1.0;
     if (x != x) return 0;
     if (x >= 2147483647.0) return 2147483647;

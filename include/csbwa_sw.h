@@ -125,6 +125,11 @@ typedef void (*csbwa_drain_fn)(void *user, const int16_t *src, int32_t n_shorts)
 int csbwa_extend_batch_cb(const uint8_t *hdr32, int32_t in_bytes, csbwa_fill_fn fill, csbwa_drain_fn drain,
                           void *user, int device);
 
+/* Copy for staging buffers the device reads next: non-temporal stores, so that no line is left dirty in a CPU cache
+ * for the device's reads to snoop out.  What csbwa_extend_batch uses for pageable callers; a `fill` callback
+ * (csbwa_extend_batch_cb) that gets its bytes through a small bounce buffer should use it as well. */
+void csbwa_stream_copy(void *dst, const void *src, int64_t n);
+
 /* Pinned (page-locked, device-mapped, portable across GPUs) host memory for seam buffers.  A seam call
  * whose buffers lie inside such a range is zero-copy on the host (see csbwa_extend_batch).
  * csbwa_host_register pins memory the caller already owns (cudaHostRegister; page granularity). */

@@ -322,6 +322,18 @@ def ref_matesw_group(pacLen, pes, groupSize, seqsPairs, mateSWArray, refSWArray,
     return [out[out_start[x]:out_start[x + 1]].copy() for x in range(2 * G)]
 
 
+def ref_align2_batch(jobs, seqs, n_threads=1):
+    """The reference's own SSE2 ksw_align2 (N/ksw.c:342-364) over a flat job list on n_threads host threads."""
+    jobs = np.ascontiguousarray(jobs)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    out = np.zeros((len(jobs), 7), dtype=np.int32)
+    S = ref_shim()
+    S.refshim_align2_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
+    S.refshim_align2_batch.restype = C.c_int
+    S.refshim_align2_batch(jobs.ctypes.data, len(jobs), seqs.ctypes.data, out.ctypes.data, int(n_threads))
+    return out
+
+
 def _flatten_regs(reg_lists):
     n = len(reg_lists)
     reg_start = np.zeros(n + 1, dtype=np.int32)

@@ -130,3 +130,47 @@ int refshim_pestat(int64_t l_pac, int32_t n_pairs, const shim_alnreg_t *regs, co
     free(v); free(opt);
     return 0;
 }
+
+/* ---- the reference's SSE2 ksw_align2 (N/ksw.c:342-364) over a flat job list, n_threads pthreads: the CPU arm of the
+ * mate-SW benchmark ("B-native-C": what the reference runs under -bPSWJNI 1, N/bwamem_pair.c:200) ---- */
+#include <pthread.h>
+#include "ksw.h"
+typedef struct { int64_t q_off, t_off; int32_t q_len, t_len, xtra, pad; } shim_job_t;
+typedef struct {
+    const shim_job_t *jobs; int32_t n; const uint8_t *seqs; int32_t *out7; int8_t mat[25];
+    volatile int32_t next;
+} shim_al_ctx;
+static void *shim_al_worker(void *v)
+{
+    shim_al_ctx *c = (shim_al_ctx *)v;
+    for (;;) {
+        const int32_t k = __sync_fetch_and_add(&c->next, 1);
+        if (k >= c->n) break;
+        const shim_job_t *j = &c->jobs[k];
+        /* ksw_align2 reverses its inputs in place for the start recovery: private copies, as the JNI caller has */
+        uint8_t *q = (uint8_t *)malloc((size_t)j->q_len + 1), *t = (uint8_t *)malloc((size_t)j->t_len + 1);
+        memcpy(q, c->seqs + j->q_off, (size_t)j->q_len);
+        memcpy(t, c->seqs + j->t_off, (size_t)j->t_len);
+        kswr_t r = ksw_align2(j->q_len, q, j->t_len, t, 5, c->mat, 6, 1, 6, 1, j->xtra, 0);
+        int32_t *o = c->out7 + (size_t)7 * k;
+        o[0] = r.score; o[1] = r.te; o[2] = r.qe; o[3] = r.score2; o[4] = r.te2; o[5] = r.tb; o[6] = r.qb;
+        free(q); free(t);
+    }
+    return NULL;
+}
+int refshim_align2_batch(const shim_job_t *jobs, int32_t n, const uint8_t *seqs, int32_t *out7, int n_threads)
+{
+    shim_al_ctx c;
+    c.jobs = jobs; c.n = n; c.seqs = seqs; c.out7 = out7; c.next = 0;
+    mem_opt_t *opt = mem_opt_init();
+    memcpy(c.mat, opt->mat, 25);
+    free(opt);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    int started = 0;
+    for (int i = 0; i < n_threads - 1; ++i) if (pthread_create(&th[started], NULL, shim_al_worker, &c) == 0) ++started;
+    shim_al_worker(&c);
+    for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
