@@ -538,8 +538,9 @@ def main():
             try:
                 from tools import bench_matesw
                 m = bench_matesw.run_config(pkg, "C3", 8192, pairs_per_call=4096, steps=3, cpu_sample_jobs=256, peaks=peaks, device=local)
-                line["matesw"] = {k: m[k] for k in ("workload", "jobs", "kernel_gcups", "roofline_frac_alu", "host_abi_gcups",
-                                                    "cpu_oracle_gcups", "parity_sample_ok")}
+                line["matesw"] = {k: m[k] for k in ("workload", "jobs", "kernel_gcups", "roofline_frac_alu", "host_abi_large",
+                                                    "host_abi_sbatch10", "cpu_oracle_gcups", "parity_sample_ok")}
+                line["matesw"]["reference_cpu"] = bench_matesw.run_reference(pkg, "C3", 1024, 3.0)
             except Exception as e:       # never lose the headline line over the extra leg
                 line["matesw"] = {"error": repr(e)}
             # and the next row of the path (SWGlobal / CIGAR generation), short run

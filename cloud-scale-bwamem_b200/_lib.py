@@ -34,14 +34,14 @@ EXPORTS = [
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
     "csbwa_global_batch_device", "csbwa_global_batch_device_ring", "csbwa_global_ring_pairs", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat", "csbwa_h2d_probe",
     "csbwa_extend_batch_cb", "csbwa_host_alloc", "csbwa_host_free", "csbwa_host_register", "csbwa_host_unregister", "csbwa_host_is_pinned",
-    "csbwa_set_matesw_semantics", "csbwa_pestat_prep", "csbwa_pestat_compute", "csbwa_stream_copy",
+    "csbwa_set_matesw_semantics", "csbwa_pestat_prep", "csbwa_pestat_compute", "csbwa_stream_copy", "csbwa_align2_calls",
 ]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("ext_calls", "ext_tasks", "ext_cells", "ext_in_bytes", "ext_out_bytes",
                                          "aln_calls", "aln_jobs", "aln_cells", "aln_in_bytes", "aln_out_bytes",
-                                         "kernel_launches", "ext_groups", "glb_calls", "glb_jobs", "glb_cells", "ext_zero_copy_calls")] + \
+                                         "kernel_launches", "ext_groups", "glb_calls", "glb_jobs", "glb_cells", "ext_zero_copy_calls", "aln_groups")] + \
                [(n, C.c_double) for n in ("h2d_ms", "kernel_ms", "d2h_ms", "host_ms")]
 
 
@@ -109,6 +109,7 @@ def lib():
     L.csbwa_h2d_probe.argtypes = [i64, C.c_int, C.c_int, C.c_int, C.c_int]; L.csbwa_h2d_probe.restype = C.c_double
     L.csbwa_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]; L.csbwa_int_peak.restype = C.c_int
     L.csbwa_extend_batch_cb.argtypes = [vp, i32, vp, vp, vp, C.c_int]; L.csbwa_extend_batch_cb.restype = C.c_int
+    L.csbwa_align2_calls.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_int]; L.csbwa_align2_calls.restype = C.c_int
     L.csbwa_set_matesw_semantics.argtypes = [C.c_int]; L.csbwa_set_matesw_semantics.restype = C.c_int
     L.csbwa_pestat_prep.argtypes = [i64, i32, vp, vp, vp, vp]; L.csbwa_pestat_prep.restype = C.c_int
     L.csbwa_pestat_compute.argtypes = [i32, vp, vp, i32, vp]; L.csbwa_pestat_compute.restype = C.c_int

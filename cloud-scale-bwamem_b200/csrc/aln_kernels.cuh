@@ -63,17 +63,19 @@ CSW_HD int aln_class_of(const SwOpt &o, int qlen, int tlen, int xtra = 0, int pa
     return 4;
 }
 
-__global__ void k_aln_classify(const AlnJob *__restrict__ jobs, int n, AlnScratch sc, unsigned long long dyn_bytes)
+// dyn_n (nullable): the job count lives in device memory (coalesced groups replayed as a CUDA graph); n is then the cap
+__global__ void k_aln_classify(const AlnJob *__restrict__ jobs, int n, AlnScratch sc, unsigned long long dyn_bytes,
+                               const int32_t *dyn_n = nullptr)
 {
     __shared__ SwOpt sopt;
+    if (dyn_n) n = *dyn_n;
     if (threadIdx.x == 0) {
         fill_default_opt(sopt);
         finish_opt(sopt);
         if (blockIdx.x == 0) { sc.hdr->opt = sopt; sc.hdr->n_jobs = n; sc.hdr->dyn_bytes = dyn_bytes; }
     }
     __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int cls = aln_class_of(sopt, jobs[k].q_len, jobs[k].t_len, jobs[k].xtra, jobs[k].pad);
     // warp-aggregated append
     const unsigned act = __activemask();
@@ -84,6 +86,30 @@ __global__ void k_aln_classify(const AlnJob *__restrict__ jobs, int n, AlnScratc
     if (lane == leader) base = atomicAdd(&sc.hdr->count[cls], (uint32_t)__popc(same));
     base = __shfl_sync(same, base, leader);
     sc.list[cls][base + __popc(same & ((1u << lane) - 1))] = (uint32_t)k;
+    }
+}
+
+// Coalesced groups: the calls' job arrays sit in their own regions of the group's device buffer (each followed by the
+// call's sequence pool); this builds the one contiguous job array the kernels index, offsets rebased to the buffer.
+// Table = CoCall[] at d_in, {n_calls, n_jobs} at hdr_off (csrc/coalesce.hpp).
+struct AlnCoCall { long long in_off; int in_bytes; int n_jobs; long long out_off; int job_base; int pad; };
+__global__ void k_aln_flatten(const uint8_t *__restrict__ d_in, size_t hdr_off, AlnJob *__restrict__ flat)
+{
+    const AlnCoCall *tab = (const AlnCoCall *)d_in;
+    const int32_t *dyn = (const int32_t *)(d_in + hdr_off);
+    const int n_calls = dyn[0], n = dyn[1];
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_calls - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tab[mid].job_base <= g) lo = mid; else hi = mid - 1;
+        }
+        const AlnCoCall c = tab[lo];
+        AlnJob j = ((const AlnJob *)(d_in + c.in_off))[g - c.job_base];
+        const long long seq0 = c.in_off + (long long)aln_align256((size_t)c.n_jobs * sizeof(AlnJob));
+        j.q_off += seq0; j.t_off += seq0;
+        flat[g] = j;
+    }
 }
 
 __device__ __forceinline__ char *aln_bump(AlnHdr *hdr, char *dyn, size_t bytes)

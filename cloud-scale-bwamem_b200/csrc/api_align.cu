@@ -4,8 +4,13 @@
 #include <algorithm>
 #include <math.h>
 
+#include <string>
+#include <thread>
+
 #include "host_common.hpp"
 #include "aln_kernels.cuh"
+#include "coalesce.hpp"
+#include "co_kernels.cuh"
 
 using namespace csw;
 
@@ -21,9 +26,11 @@ extern "C" int64_t csbwa_align2_scratch_bytes(int32_t n_jobs, int64_t total_q_le
     return (int64_t)aln_scratch_fixed(n_jobs) + 4 * total_t_len + 8 * total_q_len + (int64_t)64 * n_jobs + 4096;
 }
 
+// dyn_n (nullable): the job count is read from device memory and n is only the cap that sizes the grids and the job
+// lists (coalesced groups: the launch sequence is a CUDA graph replayed for every group)
 static int launch_align2(const AlnJob *d_jobs, int n, const uint8_t *d_seqs, int32_t *d_out,
                          unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
-                         cudaStream_t st, int dev)
+                         cudaStream_t st, int dev, const int32_t *dyn_n = nullptr)
 {
     if (n <= 0) return CSBWA_OK;
     const int64_t fixed = (int64_t)aln_scratch_fixed(n);
@@ -31,8 +38,10 @@ static int launch_align2(const AlnJob *d_jobs, int n, const uint8_t *d_seqs, int
     const int sms = dev_sms(dev);
     AlnScratch sc = aln_carve(d_scratch, n);
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(AlnHdr), st));
-    const int tb = 256, gb = (n + tb - 1) / tb;
-    k_aln_classify<<<gb, tb, 0, st>>>(d_jobs, n, sc, (unsigned long long)(scratch_bytes - fixed));
+    const int tb = 256;
+    int gb = (n + tb - 1) / tb;
+    if (gb > sms * 8) gb = sms * 8;              // grid-stride
+    k_aln_classify<<<gb, tb, 0, st>>>(d_jobs, n, sc, (unsigned long long)(scratch_bytes - fixed), dyn_n);
     int gw = (n + 7) / 8;                       // 4 warps per block, 2 jobs per warp
     if (gw > sms * 8) gw = sms * 8;
     if (gw < 1) gw = 1;
@@ -62,10 +71,230 @@ extern "C" int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, con
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------
+// coalesced host path of seam 2 (csrc/coalesce.hpp with a mate-SW executor)
+// ------------------------------------------------------------------------------------
+// -sbatch defaults to 10 pairs (S/commandline/BWAMEMCommand.scala): a real mateSWJNI call carries a few dozen SWAlign2
+// jobs, far too few for one launch sequence of its own (6 kernels, two copies and a synchronisation per call).  Calls
+// that are pending at the same time travel as ONE group: every caller streams {its jobs, its sequence pool} into its
+// region of the group's pinned staging, the device gathers the regions, k_aln_flatten builds the contiguous job array
+// (offsets rebased to the group's buffer), the unchanged launch sequence runs on it, the replies are scattered back.
+// The whole device side of a slot is one CUDA graph; the coalescer's pump thread is the only driver caller.
+struct CudaAlnCoExec {
+    struct Slot {
+        cudaStream_t st = nullptr;
+        uint8_t *h_in = nullptr, *h_out = nullptr, *dv_in = nullptr, *dv_out = nullptr;   // pinned + mapped, and as the device sees them
+        uint8_t *d_in = nullptr, *d_out = nullptr;
+        void *d_scratch = nullptr;
+        AlnJob *d_flat = nullptr;
+        unsigned int *d_count = nullptr;
+        cudaGraphExec_t graph = nullptr;
+        int polls = 0, n_jobs = 0;
+        double t_launch = 0;
+        size_t span = 0;
+        std::string detail;
+    };
+    static constexpr size_t kTrailer = sizeof(CoTrailer);
+    int dev = 0, max_tasks = 0;
+    size_t in_cap = 0, out_cap = 0, scratch_cap = 0, hdr_off = 0, ext_off = 0, table_bytes = 0;
+    bool use_graph = true;
+    std::vector<Slot> slots;
+
+    int init(int device, int n_slots, size_t max_bytes, int max_tasks_, size_t header_off, size_t ext_off_, size_t table_bytes_)
+    {
+        dev = device; in_cap = max_bytes; max_tasks = max_tasks_;
+        hdr_off = header_off; ext_off = ext_off_; table_bytes = table_bytes_;
+        out_cap = kTrailer + (size_t)max_tasks * sizeof(csbwa_kswr) + 64;
+        // b-arrays: 4 bytes per target base of the group at most, generic rows 8 bytes per query base (csbwa_align2_scratch_bytes)
+        scratch_cap = aln_scratch_fixed(max_tasks) + 8 * in_cap + (size_t)64 * max_tasks + 4096;
+        const char *e = getenv("CSBWA_CO_GRAPH");
+        use_graph = !(e && e[0] == '0');
+        CU_TRY(cudaSetDevice(dev));
+        slots.resize(n_slots);
+        for (auto &s : slots) {
+            CU_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            CU_TRY(cudaHostAlloc((void **)&s.h_in, in_cap, cudaHostAllocPortable | cudaHostAllocMapped));
+            CU_TRY(cudaHostAlloc((void **)&s.h_out, out_cap, cudaHostAllocPortable | cudaHostAllocMapped));
+            CU_TRY(cudaHostGetDevicePointer((void **)&s.dv_in, s.h_in, 0));
+            CU_TRY(cudaHostGetDevicePointer((void **)&s.dv_out, s.h_out, 0));
+            memset(s.h_out, 0, kTrailer);
+            CU_TRY(cudaMalloc((void **)&s.d_in, in_cap));
+            CU_TRY(cudaMalloc((void **)&s.d_out, out_cap));
+            CU_TRY(cudaMalloc(&s.d_scratch, scratch_cap));
+            CU_TRY(cudaMalloc((void **)&s.d_flat, (size_t)max_tasks * sizeof(AlnJob)));
+            CU_TRY(cudaMalloc((void **)&s.d_count, 256));
+            CU_TRY(cudaMemset(s.d_count, 0, 256));
+            if (use_graph) {
+                cudaGraph_t g = nullptr;
+                CU_TRY(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+                const int rc = enqueue(s);
+                const cudaError_t ce = cudaStreamEndCapture(s.st, &g);
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                if (ce != cudaSuccess || !g) return fail(CSBWA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+                const cudaError_t ie = cudaGraphInstantiate(&s.graph, g, 0);
+                cudaGraphDestroy(g);
+                if (ie != cudaSuccess) { s.graph = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+            }
+        }
+        return CSBWA_OK;
+    }
+    void destroy()
+    {
+        cudaSetDevice(dev);
+        for (auto &s : slots) {
+            if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            if (s.graph) cudaGraphExecDestroy(s.graph);
+            if (s.h_in) cudaFreeHost(s.h_in);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.d_scratch) cudaFree(s.d_scratch);
+            if (s.d_flat) cudaFree(s.d_flat);
+            if (s.d_count) cudaFree(s.d_count);
+        }
+        slots.clear();
+    }
+    uint8_t *in_staging(int slot) { return slots[slot].h_in; }
+    int16_t *out_staging(int slot) { return (int16_t *)(slots[slot].h_out + kTrailer); }
+    unsigned long long in_staging_dev(int slot) { return (unsigned long long)(uintptr_t)slots[slot].dv_in; }
+    unsigned long long out_staging_dev(int slot) { return (unsigned long long)(uintptr_t)(slots[slot].dv_out + kTrailer); }
+    const char *detail(int slot) { return slots[slot].detail.c_str(); }
+
+    int enqueue(Slot &s)
+    {
+        CU_TRY(cudaMemsetAsync(s.d_out, 0, kTrailer, s.st));
+        k_co_head<<<4, 256, 0, s.st>>>((uint4 *)s.d_in, (const uint4 *)s.dv_in, (int)(table_bytes / 16));
+        k_co_gather<<<32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off);
+        k_aln_flatten<<<64, 256, 0, s.st>>>(s.d_in, hdr_off, s.d_flat);
+        int rc = launch_align2(s.d_flat, max_tasks, s.d_in, (int32_t *)(s.d_out + kTrailer), (unsigned long long *)s.d_out,
+                               s.d_scratch, (int64_t)scratch_cap, s.st, dev, (const int32_t *)(s.d_in + hdr_off) + 1);
+        if (rc) return rc;
+        k_co_scatter<<<16, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
+                                           (const unsigned long long *)s.d_out, &((const AlnHdr *)s.d_scratch)->err, nullptr,
+                                           (CoTrailer *)s.dv_out, s.d_count, 7);
+        CU_TRY(cudaGetLastError());
+        return CSBWA_OK;
+    }
+    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen)
+    {
+        (void)n_calls; (void)n_units; (void)gen;
+        Slot &s = slots[slot];
+        s.polls = 0; s.n_jobs = n_tasks; s.span = span > table_bytes ? span - table_bytes : 0;
+        s.detail.clear();
+        int rc = launch_inner(s);
+        if (rc) { s.detail = csbwa_last_error(); cudaStreamSynchronize(s.st); }
+        s.t_launch = now_ms();
+        return rc;
+    }
+    int launch_inner(Slot &s)
+    {
+        CU_TRY(cudaSetDevice(dev));
+        if (use_graph) CU_TRY(cudaGraphLaunch(s.graph, s.st));
+        else return enqueue(s);
+        return CSBWA_OK;
+    }
+    int poll(int slot, unsigned gen)
+    {
+        Slot &s = slots[slot];
+        if (((volatile CoTrailer *)s.h_out)->done_gen == gen) return 1;
+        if ((++s.polls & 255) != 0) return 0;
+        cudaSetDevice(dev);
+        const cudaError_t q = cudaStreamQuery(s.st);
+        if (q == cudaErrorNotReady) return 0;
+        if (q == cudaSuccess) {
+            cudaStreamSynchronize(s.st);
+            if (((volatile CoTrailer *)s.h_out)->done_gen == gen) return 1;
+            s.detail = "the group finished without its completion word";
+        } else {
+            s.detail = std::string("device submission failed: ") + cudaGetErrorString(q);
+        }
+        return CSBWA_E_CUDA;
+    }
+    int finish(int slot, int n_calls, int n_tasks, uint8_t *call_bad)
+    {
+        (void)call_bad;
+        Slot &s = slots[slot];
+        const CoTrailer *t = (const CoTrailer *)s.h_out;
+        const double dt = now_ms() - s.t_launch;
+        int rc = CSBWA_OK;
+        if (t->status != 0) { rc = CSBWA_E_SCRATCH; s.detail = "device scratch exhausted"; }
+        std::lock_guard<std::mutex> lk(g_stats_mu);
+        g_stats.aln_calls += n_calls; g_stats.aln_jobs += n_tasks; g_stats.aln_cells += (int64_t)t->cells;
+        g_stats.aln_in_bytes += (int64_t)s.span; g_stats.aln_out_bytes += (int64_t)n_tasks * (int64_t)sizeof(csbwa_kswr);
+        g_stats.kernel_launches += kAlnLaunches + 4;
+        g_stats.aln_groups += 1;
+        g_stats.kernel_ms += dt; g_stats.host_ms += dt;
+        return rc;
+    }
+};
+
+struct AlnCoDev {
+    CudaAlnCoExec exec;
+    Coalescer<CudaAlnCoExec> *co = nullptr;
+};
+static AlnCoDev *g_aco[64] = {nullptr};
+static std::mutex g_aco_mu;
+static const size_t kAlnCoMaxBytes = (size_t)16 * 1024 * 1024;
+static const int kAlnCoMaxJobs = 32768, kAlnCoMaxCalls = 256;
+
+static bool aln_coalescing_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CSBWA_COALESCE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static int get_aln_coalescer(int dev, Coalescer<CudaAlnCoExec> **out)
+{
+    std::lock_guard<std::mutex> lk(g_aco_mu);
+    if (!g_aco[dev]) {
+        AlnCoDev *d = new AlnCoDev();
+        const int n_slots = env_int("CSBWA_ALN_CO_SLOTS", 6, 2, 16);
+        const int inflight = env_int("CSBWA_ALN_CO_INFLIGHT", n_slots - 1, 1, n_slots - 1);
+        Coalescer<CudaAlnCoExec>::Limits lim{kAlnCoMaxBytes, kAlnCoMaxJobs, kAlnCoMaxCalls, 14};
+        const size_t hdr_off = (size_t)kAlnCoMaxCalls * sizeof(CoCall), ext_off = hdr_off + 16;
+        const size_t table_bytes = (ext_off + (size_t)kAlnCoMaxCalls * sizeof(CoExt) + 255) & ~(size_t)255;
+        int rc = d->exec.init(dev, n_slots, kAlnCoMaxBytes, kAlnCoMaxJobs, hdr_off, ext_off, table_bytes);
+        if (rc) { d->exec.destroy(); delete d; return rc; }
+        d->co = new Coalescer<CudaAlnCoExec>(&d->exec, n_slots, inflight, lim);
+        d->co->set_bad_call_status(CSBWA_E_SCRATCH);
+        g_aco[dev] = d;
+    }
+    *out = g_aco[dev]->co;
+    return CSBWA_OK;
+}
+
+void csw::destroy_aln_coalescers()
+{
+    std::lock_guard<std::mutex> lk(g_aco_mu);
+    for (auto &d : g_aco)
+        if (d) { delete d->co; d->exec.destroy(); delete d; d = nullptr; }
+}
+
+struct AlnCoUser { const csbwa_job *jobs; int32_t n_jobs; const uint8_t *seqs; int64_t seq_bytes; csbwa_kswr *out; };
+static void aln_fill(void *u, uint8_t *dst, int in_bytes)
+{
+    (void)in_bytes;
+    const AlnCoUser *x = (const AlnCoUser *)u;
+    const size_t jb = (size_t)x->n_jobs * sizeof(csbwa_job);
+    csbwa_stream_copy(dst, x->jobs, (int64_t)jb);
+    csbwa_stream_copy(dst + aln_align256(jb), x->seqs, x->seq_bytes);
+}
+static void aln_drain(void *u, const int16_t *src, int n_shorts)
+{
+    memcpy(((const AlnCoUser *)u)->out, src, (size_t)n_shorts * 2);
+}
+
+static int align2_batch_direct(const csbwa_job *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes, csbwa_kswr *out,
+                               int device, int64_t tq, int64_t tt);
+
 extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes,
                                   csbwa_kswr *out, int device)
 {
-    const double t0 = now_ms();
     if (n_jobs < 0 || seq_bytes < 0 || (n_jobs > 0 && (!jobs || !seqs || !out))) return fail(CSBWA_E_BADARG, "null buffer or negative size");
     if (n_jobs == 0) return CSBWA_OK;
     int64_t tq = 0, tt = 0;
@@ -76,6 +305,37 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
             return fail(CSBWA_E_BADARG, "job sequence range outside seqs[]");
         tq += j.q_len; tt += j.t_len;
     }
+    int dev = 0;
+    int rc = pick_device(device, &dev);
+    if (rc) return rc;
+    // small calls (the reference's -sbatch 10 shape) travel coalesced with whatever else is pending
+    const size_t wire = aln_align256((size_t)n_jobs * sizeof(csbwa_job)) + (size_t)seq_bytes;
+    if (aln_coalescing_enabled() && wire + 65536 < kAlnCoMaxBytes / 2 && n_jobs <= kAlnCoMaxJobs / 4) {
+        Coalescer<CudaAlnCoExec> *co = nullptr;
+        if ((rc = get_aln_coalescer(dev, &co))) return rc;
+        if (co->fits((int)((wire + 15) & ~(size_t)15), n_jobs)) {
+            static const uint8_t key[32] = {0};
+            AlnCoUser u{jobs, n_jobs, seqs, seq_bytes, out};
+            CoRequest rq;
+            rq.hdr = key; rq.in_bytes = (int)((wire + 15) & ~(size_t)15); rq.n_tasks = n_jobs;
+            rq.src_dev = nullptr; rq.dst_dev = nullptr;
+            rq.fill = aln_fill; rq.drain = aln_drain; rq.user = &u;
+            char detail[160];
+            detail[0] = 0;
+            rc = co->submit(rq, detail, sizeof detail);
+            if (rc == CSBWA_OK) return rc;
+            if (rc != CSBWA_E_SCRATCH) return fail(rc, "coalesced device submission failed: %s (%s)", csbwa_strerror(rc), detail);
+            // scratch of the shared group exhausted: redo this call alone with its own sizing
+        }
+    }
+    return align2_batch_direct(jobs, n_jobs, seqs, seq_bytes, out, dev, tq, tt);
+}
+
+// one call = one submission (large calls, CSBWA_COALESCE=0, scratch fallback)
+static int align2_batch_direct(const csbwa_job *jobs, int32_t n_jobs, const uint8_t *seqs, int64_t seq_bytes, csbwa_kswr *out,
+                               int device, int64_t tq, int64_t tt)
+{
+    const double t0 = now_ms();
     Ctx *c = nullptr;
     int rc = acquire_ctx(device, &c);
     if (rc) return rc;
@@ -118,6 +378,38 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
         g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += d;
         g_stats.host_ms += now_ms() - t0;
     }
+    return CSBWA_OK;
+}
+
+// Many seam-2 calls, T caller threads: what an executor JVM with T task threads does, for C hosts (bench, tests).
+extern "C" int csbwa_align2_calls(const csbwa_job *const *jobs, const int32_t *n_jobs, const uint8_t *const *seqs,
+                                  const int64_t *seq_bytes, csbwa_kswr *const *outs, int32_t n_calls, int32_t n_threads, int device)
+{
+    if (n_calls < 0 || (n_calls > 0 && (!jobs || !n_jobs || !seqs || !seq_bytes || !outs))) return fail(CSBWA_E_BADARG, "bad argument");
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_calls) n_threads = n_calls > 0 ? n_calls : 1;
+    std::atomic<int> next{0}, first_err{0};
+    std::mutex err_mu;
+    std::string err_detail;
+    auto body = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n_calls) break;
+            const int rc = csbwa_align2_batch(jobs[i], n_jobs[i], seqs[i], seq_bytes[i], outs[i], device);
+            if (rc != 0) {
+                int z = 0;
+                if (first_err.compare_exchange_strong(z, rc)) {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    err_detail = csbwa_last_error();
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(body);
+    body();
+    for (auto &t : th) t.join();
+    if (first_err.load() != 0) return fail(first_err.load(), "%s", err_detail.c_str());
     return CSBWA_OK;
 }
 

@@ -252,6 +252,7 @@ extern "C" int csbwa_device_count(void) { return g_inited ? g_ndev : 0; }
 extern "C" int csbwa_shutdown(void)
 {
     destroy_coalescers();
+    destroy_aln_coalescers();
     release_refs();
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return CSBWA_OK;

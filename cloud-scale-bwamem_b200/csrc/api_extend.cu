@@ -44,10 +44,6 @@ static int ensure_dev_attrs(int dev)
     const int big_p2l = 128 * EXT_BD_LONG * 10;      // the 256-column class at one warp per block
     CU_TRY(cudaFuncSetAttribute((k_ext_side<0, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     CU_TRY(cudaFuncSetAttribute((k_ext_side<1, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
-    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<0, EXT_BD>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
-    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<1, EXT_BD>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
-    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<0, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
-    CU_TRY(cudaFuncSetAttribute((k_ext_side_rf<1, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     g_ext_attrs[dev] = true;
     return CSBWA_OK;
 }
@@ -135,14 +131,7 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 96);
             if (grid > cap_grid) grid = cap_grid;
-            // CSBWA_EXT_REFILL=0: the chunked kernel (a warp takes 32 jobs and lasts as long as the longest); default: lanes
-            // are refilled from the class cursor as their sides end
-            static const int refill = env_int("CSBWA_EXT_REFILL", 1, 0, 1);
-            if (refill && lng)
-                k_ext_side_rf<SIDE, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls, npairs);
-            else if (refill)
-                k_ext_side_rf<SIDE, EXT_BD><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, d_out, d_cells, cls, npairs);
-            else if (lng)
+            if (lng)
                 k_ext_side<SIDE, EXT_CORE_P2, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
                                                                                     d_out, d_cells, cls, npairs);
             else
@@ -443,12 +432,12 @@ struct CudaCoExec {
         int rc = launch_extend(s.d_in, cs, dyn_cap, (int16_t *)(s.d_out + kTrailer), (unsigned long long *)s.d_out, s.d_scratch,
                                (int64_t)scratch_cap, s.st, dev, &s.aux);
         if (rc) return rc;
-        if (dma) k_co_finish<<<1, 32, 0, s.st>>>(s.d_in, hdr_off, (const ExtHdr *)s.d_scratch, (CoTrailer *)s.d_out);
+        if (dma) k_co_finish<<<1, 32, 0, s.st>>>(s.d_in, hdr_off, &((const ExtHdr *)s.d_scratch)->err, ((const ExtHdr *)s.d_scratch)->bad_call_bits, (CoTrailer *)s.d_out);
         if (timed) CU_TRY(cudaEventRecord(s.ev[2], s.st));
         if (!dma)
             k_co_scatter<<<variant == 0 ? 8 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
-                                                                 (const unsigned long long *)s.d_out, (const ExtHdr *)s.d_scratch,
-                                                                 (CoTrailer *)s.dv_out, s.d_count);
+                                                                 (const unsigned long long *)s.d_out, &((const ExtHdr *)s.d_scratch)->err,
+                                                                 ((const ExtHdr *)s.d_scratch)->bad_call_bits, (CoTrailer *)s.dv_out, s.d_count, 5);
         if (timed && !dma) CU_TRY(cudaEventRecord(s.ev[3], s.st));
         CU_TRY(cudaGetLastError());
         return CSBWA_OK;
@@ -899,13 +888,26 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
     const std::shared_ptr<DevRef> refp = ref_get(c->dev);          // alive until this call returns
     if (!refp || !refp->d_pac) return fail(CSBWA_E_BADARG, "no reference uploaded on this device (csbwa_ref_upload)");
     const DevRef &ref = *refp;
-    // host: validate, size the blocks (prefix of the per-task word counts)
+    // host: validate, size the blocks (prefix of the per-task word counts), and stage the call COMPACTLY: only the
+    // reads some task refers to travel, at 4 bits per base (two bases per byte, first base in the high nibble --
+    // the wire format's own alphabet), with the tasks' read indices remapped.  At 151 bp that is 76 bytes per used
+    // read instead of 151 per read of the sub-batch: fewer PCIe bytes per task than the wire seam's nibble blocks,
+    // which carry the reference windows as well.
     const size_t tb = (size_t)n_tasks * sizeof(SeedTask), pb = ((size_t)n_tasks + 1) * 4;
     const size_t off_pos = (tb + 255) & ~(size_t)255, off_reads = (off_pos + pb + 255) & ~(size_t)255;
-    const size_t in_bytes = off_reads + (size_t)n_reads * read_len;
+    const size_t rd4 = ((size_t)read_len + 1) / 2;                 // bytes of one packed read
+    std::vector<int32_t> remap((size_t)n_reads, -1);
+    int32_t n_used = 0;
+    for (int32_t k = 0; k < n_tasks; ++k) {
+        const int32_t r = tasks[k].read_idx;
+        if (r < 0 || r >= n_reads) return fail(CSBWA_E_BADARG, "a task's read index is outside the call's reads");
+        if (remap[(size_t)r] < 0) remap[(size_t)r] = n_used++;
+    }
+    const size_t in_bytes = off_reads + (size_t)n_used * rd4;
     if ((rc = grow_pinned(c->h_in, in_bytes + 16))) return rc;
     uint8_t *h = (uint8_t *)c->h_in.p;
     int32_t *pos = (int32_t *)(h + off_pos);
+    SeedTask *ht = (SeedTask *)h;
     int64_t words = 8 + 8 * (int64_t)n_tasks;
     for (int32_t k = 0; k < n_tasks; ++k) {
         SeedTask t;
@@ -914,14 +916,30 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
         pos[k] = (int32_t)words;
         words += seed_task_words(t, read_len);
         if (words > 0x7fffffff / 4) return fail(CSBWA_E_BADARG, "call too large");
+        t.read_idx = remap[(size_t)t.read_idx];
+        ht[k] = t;
     }
     pos[n_tasks] = (int32_t)words;
     const int64_t wire_b = words * 4;
     if (wire_bytes) *wire_bytes = wire_b;
     if (wire_out && wire_cap < wire_b) return fail(CSBWA_E_SHORTOUT, "wire buffer too small");
     if (n_tasks == 0 && !wire_out) return CSBWA_OK;
-    memcpy(h, tasks, tb);
-    memcpy(h + off_reads, reads, (size_t)n_reads * read_len);
+    for (int32_t r = 0; r < n_reads; ++r) {
+        if (remap[(size_t)r] < 0) continue;
+        const uint8_t *src = reads + (size_t)r * read_len;
+        uint8_t *dst = h + off_reads + (size_t)remap[(size_t)r] * rd4;
+        int j = 0;
+#if defined(__SSE2__)
+        for (; j + 16 <= read_len; j += 16) {                      // 16 bases -> 8 bytes
+            const __m128i v = _mm_loadu_si128((const __m128i *)(src + j));          // 16-bit lanes: b0 | b1 << 8
+            const __m128i w = _mm_and_si128(_mm_or_si128(_mm_slli_epi16(v, 4), _mm_srli_epi16(v, 8)), _mm_set1_epi16(0x00ff));
+            _mm_storel_epi64((__m128i *)(dst + j / 2), _mm_packus_epi16(w, w));
+        }
+#endif
+        for (; j + 1 < read_len; j += 2) dst[j / 2] = (uint8_t)(((src[j] & 15) << 4) | (src[j + 1] & 15));
+        if (j < read_len) dst[j / 2] = (uint8_t)((src[j] & 15) << 4);
+    }
+    const int32_t n_reads_dev = n_used;
     const size_t out_bytes = (size_t)n_tasks * CSBWA_EXT_RET_SHORTS * 2;
     const size_t scr = ext_scratch_bytes(n_tasks, wire_b);
     if ((rc = grow_dev(c->d_in, in_bytes + 16)) || (rc = grow_dev(c->d_aux, (size_t)wire_b + 256)) ||
@@ -941,7 +959,7 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
     if (grid < 1) grid = 1;
     int32_t *d_err = (int32_t *)((char *)c->d_out.p + out_bytes + 16);
     CU_TRY(cudaMemsetAsync(d_err, 0, 4, c->st));
-    k_coords_expand<<<grid, 256, 0, c->st>>>((const SeedTask *)d, (const int32_t *)(d + off_pos), n_tasks, d + off_reads, n_reads,
+    k_coords_expand<<<grid, 256, 0, c->st>>>((const SeedTask *)d, (const int32_t *)(d + off_pos), n_tasks, d + off_reads, n_reads_dev,
                                              read_len, ref.d_pac, ref.l_pac, co, (uint32_t *)c->d_aux.p, d_err);
     if (out && n_tasks > 0) {
         rc = launch_extend((const uint8_t *)c->d_aux.p, single_call((int32_t)wire_b, n_tasks), n_tasks, (int16_t *)c->d_out.p,

@@ -14,7 +14,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "coalesce.hpp"
-#include "ext_kernels.cuh"
 
 namespace csw {
 
@@ -28,7 +27,7 @@ struct CoTrailer {
 };
 static_assert(sizeof(CoTrailer) == 64, "trailer layout");
 
-__global__ void k_co_head(uint4 *__restrict__ d_in, const uint4 *__restrict__ h_in, int n16)
+static __global__ void k_co_head(uint4 *__restrict__ d_in, const uint4 *__restrict__ h_in, int n16)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) d_in[i] = h_in[i];
 }
@@ -45,9 +44,9 @@ __device__ __forceinline__ int co_locate_unit(const CoExt *ext, int n_calls, int
 }
 
 constexpr int CO_GATHER_ILP = 4;
-__global__ void __launch_bounds__(256) k_co_gather(uint8_t *__restrict__ d_in, size_t hdr_off, size_t ext_off)
+static __global__ void __launch_bounds__(256) k_co_gather(uint8_t *__restrict__ d_in, size_t hdr_off, size_t ext_off)
 {
-    const ExtCall *tab = (const ExtCall *)d_in;
+    const CoCall *tab = (const CoCall *)d_in;
     const int32_t *dyn = (const int32_t *)(d_in + hdr_off);
     const CoExt *ext = (const CoExt *)(d_in + ext_off);
     const int n_calls = dyn[0], n_units = dyn[2];
@@ -81,22 +80,24 @@ __global__ void __launch_bounds__(256) k_co_gather(uint8_t *__restrict__ d_in, s
     }
 }
 
-// replies: 5 words per task; word w of the group belongs to the call with 5 * task_base <= w
-__global__ void __launch_bounds__(256) k_co_scatter(const uint8_t *__restrict__ d_in, size_t hdr_off, size_t ext_off,
+// replies: wpt 32-bit words per task (5 for the extension seam, 7 for mate-SW); word w of the group belongs to the call
+// with wpt * task_base <= w.  d_err: the launch sequence's status word; d_bad (nullable): its 8 words of bad-call bits.
+static __global__ void __launch_bounds__(256) k_co_scatter(const uint8_t *__restrict__ d_in, size_t hdr_off, size_t ext_off,
                                                     const uint32_t *__restrict__ d_replies, const unsigned long long *d_cells,
-                                                    const ExtHdr *hdr, CoTrailer *h_trailer, unsigned int *d_block_count)
+                                                    const int32_t *d_err, const uint32_t *d_bad, CoTrailer *h_trailer,
+                                                    unsigned int *d_block_count, int wpt)
 {
-    const ExtCall *tab = (const ExtCall *)d_in;
+    const CoCall *tab = (const CoCall *)d_in;
     const int32_t *dyn = (const int32_t *)(d_in + hdr_off);
     const CoExt *ext = (const CoExt *)(d_in + ext_off);
-    const int n_calls = dyn[0], n_words = 5 * dyn[1];
+    const int n_calls = dyn[0], n_words = wpt * dyn[1];
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
         int lo = 0, hi = n_calls - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (5 * tab[mid].task_base <= w) lo = mid; else hi = mid - 1;
+            if (wpt * tab[mid].task_base <= w) lo = mid; else hi = mid - 1;
         }
-        ((uint32_t *)ext[lo].dst)[w - 5 * tab[lo].task_base] = d_replies[w];
+        ((uint32_t *)ext[lo].dst)[w - wpt * tab[lo].task_base] = d_replies[w];
     }
     // the last block to finish publishes the trailer, then the completion word
     __shared__ bool s_last;
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(256) k_co_scatter(const uint8_t *__restrict__ 
     if (threadIdx.x == 0) s_last = atomicAdd(d_block_count, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
-    if (threadIdx.x < 8) h_trailer->bad_bits[threadIdx.x] = hdr->bad_call_bits[threadIdx.x];
-    if (threadIdx.x == 8) { h_trailer->cells = *d_cells; h_trailer->status = hdr->err; *d_block_count = 0; }
+    if (threadIdx.x < 8) h_trailer->bad_bits[threadIdx.x] = d_bad ? d_bad[threadIdx.x] : 0u;
+    if (threadIdx.x == 8) { h_trailer->cells = *d_cells; h_trailer->status = *d_err; *d_block_count = 0; }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -118,11 +119,12 @@ __global__ void __launch_bounds__(256) k_co_scatter(const uint8_t *__restrict__ 
 // copy-engine mode of the seam: the transfers are cudaMemcpyAsync calls around the graph; this kernel closes
 // the launch sequence by assembling the trailer in device memory ({cells} is already there), which the last
 // device -> host copy of the group delivers -- its done_gen word is what the host polls
-__global__ void k_co_finish(const uint8_t *__restrict__ d_in, size_t hdr_off, const ExtHdr *hdr, CoTrailer *d_trailer)
+static __global__ void k_co_finish(const uint8_t *__restrict__ d_in, size_t hdr_off, const int32_t *d_err, const uint32_t *d_bad,
+                            CoTrailer *d_trailer)
 {
     const int32_t *dyn = (const int32_t *)(d_in + hdr_off);
-    if (threadIdx.x < 8) d_trailer->bad_bits[threadIdx.x] = hdr->bad_call_bits[threadIdx.x];
-    if (threadIdx.x == 8) { d_trailer->status = hdr->err; d_trailer->done_gen = (uint32_t)dyn[3]; }
+    if (threadIdx.x < 8) d_trailer->bad_bits[threadIdx.x] = d_bad ? d_bad[threadIdx.x] : 0u;
+    if (threadIdx.x == 8) { d_trailer->status = *d_err; d_trailer->done_gen = (uint32_t)dyn[3]; }
 }
 
 } // namespace csw

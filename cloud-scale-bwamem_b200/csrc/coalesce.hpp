@@ -89,6 +89,7 @@ public:
         size_t max_bytes;   // staging capacity per group (input side)
         int max_tasks;      // tasks per group
         int max_calls;      // calls per group
+        int reply_shorts = 10;   // 16-bit units of reply per task (10 = the extension seam's ExtRet record)
     };
 
     // max_inflight: groups on the device at once (<= n_slots - 1: one buffer keeps accepting calls)
@@ -152,7 +153,7 @@ public:
         c.in_off = (long long)g->bytes;
         c.in_bytes = rq.in_bytes;
         c.n_tasks = rq.n_tasks;
-        c.out_off = (long long)10 * g->tasks;
+        c.out_off = (long long)lim_.reply_shorts * g->tasks;
         c.task_base = g->tasks;
         c.pad = 0;
         CoExt x;
@@ -190,7 +191,7 @@ public:
         if (rc < 0 && detail && detail_cap > 0) snprintf(detail, detail_cap, "%s", g->detail);
         if (rc == 0 && g->call_bad[(size_t)my]) rc = g->bad_rc;
         const long long t3 = now_ns();
-        if (rc == 0 && !rq.dst_dev) rq.drain(rq.user, ex_->out_staging(g->slot) + c.out_off, 10 * rq.n_tasks);
+        if (rc == 0 && !rq.dst_dev) rq.drain(rq.user, ex_->out_staging(g->slot) + c.out_off, lim_.reply_shorts * rq.n_tasks);
         if (g->readers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
             lk.lock();
             g->state = FREE;

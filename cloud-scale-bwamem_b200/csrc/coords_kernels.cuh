@@ -57,7 +57,11 @@ CSW_HD int seed_task_words(const SeedTask &t, int read_len)
 
 struct CoordsOpt { int32_t v[7]; };   // oDel, eDel, oIns, eIns, penClip5, penClip3, w
 
-// pos[k]: word offset of task k's block (pos[n] = total words); err: set to -2 on a bad task
+// base x of a read packed at 4 bits per base (two per byte, first base in the high nibble)
+CSW_HD int read4_base(const uint8_t *rd4, int x) { return (rd4[x >> 1] >> ((~x & 1) << 2)) & 0xf; }
+
+// pos[k]: word offset of task k's block (pos[n] = total words); err: set to -2 on a bad task.
+// reads: the reads the tasks refer to, 4 bits per base, (read_len + 1) / 2 bytes each.
 __global__ void k_coords_expand(const SeedTask *__restrict__ tasks, const int32_t *__restrict__ pos, int n,
                                 const uint8_t *__restrict__ reads, int n_reads, int read_len,
                                 const uint8_t *__restrict__ pac, long long l_pac, CoordsOpt opt,
@@ -109,15 +113,15 @@ __global__ void k_coords_expand(const SeedTask *__restrict__ tasks, const int32_
         if (seed_task_ok(t, n_reads, read_len, l_pac)) {
             int lq, rq, lr, rr;
             seed_task_lens(t, read_len, lq, rq, lr, rr);
-            const uint8_t *rd = reads + (size_t)t.read_idx * read_len;
+            const uint8_t *rd = reads + (size_t)t.read_idx * (size_t)((read_len + 1) >> 1);
             const int tot = lq + rq + lr + rr;
             const long long r_end = t.r_beg + t.seed_len;
             int x = (wi - pos[lo]) * 8;
 #pragma unroll
             for (int b = 0; b < 8; ++b, ++x) {
                 int v = 0;
-                if (x < lq) v = rd[lq - 1 - x];                                   // leftQ reversed (:505-510)
-                else if (x < lq + rq) v = rd[t.q_beg + t.seed_len + (x - lq)];     // rightQ (:528-533)
+                if (x < lq) v = read4_base(rd, lq - 1 - x);                       // leftQ reversed (:505-510)
+                else if (x < lq + rq) v = read4_base(rd, t.q_beg + t.seed_len + (x - lq));   // rightQ (:528-533)
                 else if (x < lq + rq + lr) v = pac_base(pac, l_pac, t.r_beg - 1 - (x - lq - rq));      // leftR reversed
                 else if (x < tot) v = pac_base(pac, l_pac, r_end + (x - lq - rq - lr));                // rightR
                 acc = (acc << 4) | (uint32_t)(v & 0xf);

@@ -434,123 +434,4 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
 }
 
-// ---------------------------------------------------------------------------------
-// refilling side kernel (column-pair core only)
-// ---------------------------------------------------------------------------------
-// k_ext_side hands a warp 32 jobs at a time and the warp lasts as long as its longest job: how many rows a side
-// runs depends on where its alignment ends (z-drop, an all-zero row), which the sort keys cannot know, and at 5 %
-// read errors (C5) 6-12 of the 32 lanes sat idle waiting for the last one.  Here a lane's SWExtend call is stepped
-// ONE ROW per loop trip (P2Run); a lane whose side is finished waits only until EXT_REFILL_MIN lanes are idle,
-// then the idle lanes take their next jobs from the class cursor together (the per-job set-up -- record, query
-// staging, first row -- is paid once for the whole batch of idle lanes, not once per lane), while rows keep being
-// the only thing the warp executes in between.  Same jobs, same arithmetic, same results; only who runs what when.
-constexpr int EXT_REFILL_MIN = 8;
-
-template <int SIDE, int BD>
-__global__ void __launch_bounds__(BD)
-k_ext_side_rf(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uint32_t *__restrict__ order,
-              SideRes *__restrict__ left, int16_t *__restrict__ out, unsigned long long *cells_acc, int cls, int npairs)
-{
-    extern __shared__ uint4 smem4[];
-    const unsigned FULL = 0xffffffffu;
-    { int n_unused = 0; ext_resolve(cs, n_unused); }
-    __shared__ SwOpt s_opt;
-    if (threadIdx.x == 0) s_opt = hdr->opt;
-    __syncthreads();
-    const SwOpt &o = s_opt;
-    const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
-    const int lane = threadIdx.x & 31;
-    P2Pair *he = (P2Pair *)smem4 + threadIdx.x;                 // pair p at he[p * BD]
-    uint16_t *sel = (uint16_t *)((P2Pair *)smem4 + (size_t)npairs * BD) + threadIdx.x;
-    unsigned long long my_cells = 0;
-    int st = 0;                                                 // 0: wants a job, 1: running a side, 2: no jobs left
-    // the running side of this lane
-    P2Run run;
-    ExtTask t;
-    const ExtCall *cl = nullptr;
-    const uint32_t *words = nullptr;
-    SideRes L;
-    int k = 0, tr = 0, prev = 0, side_cells = 0, q_nib = 0, qlen = 0, t_nib = 0, tlen = 0, bonus = 0, h0 = 0;
-    L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = 0; L.cells = 0;
-    for (;;) {
-        const unsigned need = __ballot_sync(FULL, st == 0);
-        const unsigned busy = __ballot_sync(FULL, st == 1);
-        if (need && (__popc(need) >= EXT_REFILL_MIN || !busy)) {
-            uint32_t first = 0;
-            const int leader = __ffs(need) - 1;
-            if (lane == leader) first = atomicAdd(&hdr->work[SIDE][cls], (uint32_t)__popc(need));
-            first = __shfl_sync(FULL, first, leader) + jbeg;
-            if (st == 0) {
-                const uint32_t job = first + (uint32_t)__popc(need & ((1u << lane) - 1u));
-                if (job >= jend) st = 2;
-                else {
-                    k = (int)order[job];                        // global task index
-                    cl = &ext_call(cs, ext_locate(cs, k));
-                    const uint8_t *in = base + cl->in_off;
-                    t = read_task(in, k - cl->task_base);
-                    if (!ext_task_ok(t, cl->n_tasks, cl->in_bytes)) { t.lq = t.lr = t.rq = t.rr = 0; t.pos = 8 + 8 * cl->n_tasks; }
-                    words = (const uint32_t *)in + t.pos;
-                    L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
-                    if (SIDE == 0) {
-                        q_nib = seg_lq(t); qlen = t.lq; t_nib = seg_lr(t); tlen = t.lr; bonus = o.pen_clip5; h0 = t.h0; prev = t.reg_score;
-                    } else {
-                        if (t.lq > 0) L = left[k];
-                        const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
-                        q_nib = seg_rq(t); qlen = t.rq; t_nib = seg_rr(t); tlen = t.rr; bonus = o.pen_clip3; h0 = sc0; prev = sc0;
-                    }
-                    tr = 0; side_cells = 0;
-                    if (qlen > 0) {
-                        p2_stage_query(sel, BD, words, q_nib, qlen);
-                        run.start(o, he, BD, qlen, words, t_nib, tlen, o.w, bonus, h0);
-                        st = 1;
-                    } else if (SIDE == 1) {                     // nothing to extend on the right: finalise at once
-                        SideRes R = L;
-                        R.score = 0; R.qle = R.tle = R.gtle = R.gscore = 0; R.aw = (int16_t)o.w; R.cells = 0;
-                        int16_t rec[10];
-                        ext_finalize(o, t, &L, &R, rec);
-                        uint32_t *dst = (uint32_t *)(out + cl->out_off + (size_t)10 * (k - cl->task_base));
-#pragma unroll
-                        for (int q = 0; q < 5; ++q)
-                            dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
-                    } else {
-                        left[k] = L;                            // (an empty left side never reaches the left list; defensive)
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(FULL, st == 1) == 0) {
-            if (__ballot_sync(FULL, st == 0) == 0) break;      // every lane has run out of jobs
-            continue;                                           // only trivial jobs were handed out: fetch again
-        }
-        if (st == 1 && !run.template row<BD>(o, he, sel, BD)) {
-            // one SWExtend call is over: band retry (MemChainToAlignBatched.scala:810-824) or the side is done
-            SwExtRes r;
-            run.result(r);
-            side_cells += r.cells;
-            const int aw = o.w << tr;
-            if (tr + 1 < CSW_MAX_BAND_TRY && !(r.score == prev || r.max_off < (aw >> 1) + (aw >> 2))) {
-                prev = r.score;
-                ++tr;
-                run.start(o, he, BD, qlen, words, t_nib, tlen, o.w << tr, bonus, h0);
-            } else {
-                SideRes S;
-                S.score = (int16_t)r.score; S.qle = (int16_t)r.qle; S.tle = (int16_t)r.tle;
-                S.gtle = (int16_t)r.gtle; S.gscore = (int16_t)r.gscore; S.aw = (int16_t)aw; S.cells = side_cells;
-                my_cells += (unsigned)side_cells;
-                if (SIDE == 0) left[k] = S;
-                else {
-                    int16_t rec[10];
-                    ext_finalize(o, t, &L, &S, rec);
-                    uint32_t *dst = (uint32_t *)(out + cl->out_off + (size_t)10 * (k - cl->task_base));
-#pragma unroll
-                    for (int q = 0; q < 5; ++q)
-                        dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
-                }
-                st = 0;
-            }
-        }
-    }
-    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
-}
-
 } // namespace csw

@@ -56,8 +56,10 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 
 // One SWExtend call as a row-granular state machine: start() = profile-independent set-up (first row, band
 // clamp), row() = one target row (false once the call is over: rows exhausted, an all-zero row, or the z-drop),
-// result().  sw_extend_p2 below simply runs it to completion; the refilling side kernel (ext_kernels.cuh) steps
-// the calls of its 32 lanes row by row and hands a finished lane its next job while the others keep going.
+// result().  sw_extend_p2 below simply runs it to completion.  (A side kernel that stepped the calls of its 32 lanes
+// row by row and refilled finished lanes from the class cursor was built on this and measured -- bit-exact, 8-13 %
+// slower on C1 / C2 / C5: refilled lanes run jobs from different places of the sorted order, and a warp's row costs
+// the width of its widest lane.  DESIGN.md 4.1.)
 // STRIDE: compile-time element stride between consecutive pairs (threads per block on the device, so
 // the unrolled pair loop addresses shared memory with immediate offsets); 0 = use stride_rt
 struct P2Run {

@@ -103,6 +103,7 @@ void *pinned_dev_ptr(const void *p, size_t n);
 
 // hooks of the other translation units (called by csbwa_shutdown)
 void destroy_coalescers();
+void destroy_aln_coalescers();
 void release_refs();
 
 } // namespace csw

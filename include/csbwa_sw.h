@@ -88,6 +88,7 @@ typedef struct {
     int64_t ext_groups;          /* coalesced device submissions that served ext_calls */
     int64_t glb_calls, glb_jobs, glb_cells;
     int64_t ext_zero_copy_calls; /* coalesced seam calls served without any host staging copy (pinned caller buffers) */
+    int64_t aln_groups;          /* coalesced device submissions that served aln_calls */
     double  h2d_ms, kernel_ms, d2h_ms, host_ms; /* CUDA-event / wall split, summed over calls */
 } csbwa_stats;
 
@@ -146,10 +147,17 @@ int csbwa_extend_calls(const uint8_t *const *ins, const int32_t *in_bytes, int16
 
 /* ---- seam (2): host buffers in, host buffers out ------------------------
  * Replaces the ksw_align2 loop of mem_matesw (N/bwamem_pair.c:159-228) /
- * SWAlign2 at S/worker2/MemSamPe.scala:1190.  Scoring = MemOptType defaults. */
+ * SWAlign2 at S/worker2/MemSamPe.scala:1190.  Scoring = MemOptType defaults.
+ * Small calls (the reference's -sbatch default is 10 pairs: a few dozen jobs) that are pending at the same time are
+ * coalesced into one device submission, like the extension seam's; large calls are submitted on their own. */
 int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs,
                        const uint8_t *seqs, int64_t seq_bytes,
                        csbwa_kswr *out, int device);
+
+/* Many seam-2 calls driven by n_threads caller threads (what an executor JVM with that many task threads does),
+ * for C/C++ hosts; every call goes through csbwa_align2_batch. */
+int csbwa_align2_calls(const csbwa_job *const *jobs, const int32_t *n_jobs, const uint8_t *const *seqs,
+                       const int64_t *seq_bytes, csbwa_kswr *const *outs, int32_t n_calls, int32_t n_threads, int device);
 
 /* ---- seam (2), object form: the whole of MateSWJNI.mateSWJNI, flattened ----
  * (S/jni/MateSWJNI.scala:23-26; N/jni_mate_sw.c:58-60).  Semantics = the SCALA driver

@@ -186,6 +186,36 @@ def test_aln_workloads(pkg, oracle, gpu):
         assert (ref[:, 6] >= 0).mean() > 0.9
 
 
+def test_aln_small_calls_are_coalesced(pkg, oracle, gpu):
+    """-sbatch 10 shaped mate-SW calls (a few dozen jobs each) from 12 threads: bit-exact, and served by fewer device
+    submissions than calls; a large call takes the direct path."""
+    L = pkg.lib()
+    ref = pkg.workload.make_reference(600000, 77)
+    small = pkg.workload.matesw_workload(240, 151, len(ref), 0.01, 400, 50, 1.0, seed=5, pairs_per_call=10, ref=ref)["calls"]
+    big = pkg.workload.matesw_workload(3000, 151, len(ref), 0.01, 1500, 500, 1.0, seed=6, pairs_per_call=3000, ref=ref)["calls"]
+    refs = [oracle.align2_batch(j, s, n_threads=8)[0] for j, s in small]
+    s0 = pkg.stats()
+    errs = []
+
+    def work(tid):
+        for rep in range(3):
+            for i in range(tid, len(small), 12):
+                got = pkg.jni.swAlign2Batch(small[i][0], small[i][1], device=0)
+                if not np.array_equal(got, refs[i]):
+                    errs.append((tid, i))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(12)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:5]
+    s1 = pkg.stats()
+    assert s1["aln_calls"] - s0["aln_calls"] == 3 * len(small)
+    assert 0 < s1["aln_groups"] - s0["aln_groups"] < 3 * len(small)
+    jb, sb = big[0]
+    assert np.array_equal(pkg.jni.swAlign2Batch(jb, sb, device=0), oracle.align2_batch(jb, sb, n_threads=16)[0])
+    assert pkg.stats()["aln_groups"] == s1["aln_groups"]          # too large for a group: its own submission
+
+
 def test_device_resident_api(pkg, oracle, gpu):
     """csbwa_*_batch_device on torch-owned device memory and torch's current stream."""
     import torch

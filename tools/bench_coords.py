@@ -68,15 +68,19 @@ def main():
         a = list(ex.map(run_wire, calls)); b = list(ex.map(run_coords, calls))      # warm-up + parity
         same = all(np.array_equal(x, y) for x, y in zip(a, b))
         for name, fn in (("wire", run_wire), ("coords", run_coords)):
-            c0 = pkg.stats()["ext_cells"]
+            st0 = pkg.stats()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 list(ex.map(fn, calls))
             dt = (time.perf_counter() - t0) / args.steps
-            cells = (pkg.stats()["ext_cells"] - c0) / args.steps
-            out[name] = {"ms_per_step": 1e3 * dt, "gcups": cells / dt / 1e9}
-    out["wire"]["host_bytes_per_task"] = sum(c[0].size for c in calls) / n_tasks
-    out["coords"]["host_bytes_per_task"] = sum(c[1].size + c[2].nbytes for c in calls) / n_tasks
+            st1 = pkg.stats()
+            cells = (st1["ext_cells"] - st0["ext_cells"]) / args.steps
+            out[name] = {"ms_per_step": 1e3 * dt, "gcups": cells / dt / 1e9,
+                         "h2d_bytes_per_task": (st1["ext_in_bytes"] - st0["ext_in_bytes"]) / args.steps / n_tasks}
+    # what the caller hands over (coords: one byte per base for every read of the sub-batch + 24-byte tasks; the library
+    # stages only the reads that have tasks, at 4 bits per base: h2d_bytes_per_task)
+    out["wire"]["caller_bytes_per_task"] = sum(c[0].size for c in calls) / n_tasks
+    out["coords"]["caller_bytes_per_task"] = sum(c[1].size + c[2].nbytes for c in calls) / n_tasks
     print(json.dumps({"workload": "C2 tasks, %d pairs, %d reads per call, %d caller threads" % (args.pairs, args.reads_per_call, args.threads),
                       "tasks": n_tasks, "replies_identical": bool(same), **out}))
 
