@@ -344,11 +344,17 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # profiling runs only (ncu --profile-from-start off): the timed replays are the profiled range
+    prof = os.environ.get("CSBWA_PROFILE_STEP") == "1"
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         run_step()
     e1.record()
     torch.cuda.synchronize()
+    if prof:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
@@ -480,7 +486,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic, traffic_src = tj.get("dram_bytes_per_launch_sequence"), tj.get("source")
+            traffic = tj["dram_bytes_per_cell"] * cells_all / args.steps / world      # per GPU, one step
+            traffic_src = tj.get("source", "") + "; carried per DP cell (%.4f B/cell) and scaled by this step's cells" % tj["dram_bytes_per_cell"]
         line = {
             "metric": "seed-extension SW throughput (whole job)", "value": gcups, "unit": "GCUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,

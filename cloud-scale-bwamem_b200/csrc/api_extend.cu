@@ -340,10 +340,11 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
-    // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma: one cudaMemcpyAsync per call and direction around the
-    // graph (copy engines: transfers of one group overlap the kernels of the others without needing SM resources).
-    // sm: gather / scatter kernels inside the graph (one driver call per group, but the copy blocks have to find room
-    // on SMs that the side kernels fill).
+    // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma (default): one cudaMemcpyAsync per call and direction around
+    // the graph -- the copy engines move one group's bytes while the SMs run the kernels of the others.  sm: gather /
+    // scatter kernels inside the graph -- one driver call per group, but the copy blocks need room on SMs that the side
+    // kernels fill.  Measured end to end, 64 callers per GPU, pinned caller buffers: 1 GPU / 16 vCPUs 919 (dma) vs 881-907
+    // (sm) GCUPS; 8 GPUs / 32 vCPUs 5115 vs 4709; only with the whole process pinned to 4 cores does sm win (852 vs 597).
     bool dma = true;
     std::vector<Slot> slots;
 
@@ -961,6 +962,38 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
     CU_TRY(cudaMemsetAsync(d_err, 0, 4, c->st));
     k_coords_expand<<<grid, 256, 0, c->st>>>((const SeedTask *)d, (const int32_t *)(d + off_pos), n_tasks, d + off_reads, n_reads_dev,
                                              read_len, ref.d_pac, ref.l_pac, co, (uint32_t *)c->d_aux.p, d_err);
+    if (out && n_tasks > 0 && !wire_out && coalescing_enabled()) {
+        // The expanded wire is a seam-1 call like any other: it joins the coalesced groups of the extension seam, its
+        // source being DEVICE memory (the group's gather copies it device to device).  A sub-batch of 4096 reads then
+        // shares its launch sequence with whatever else is pending instead of paying for 17 kernels of its own.
+        Coalescer<CudaCoExec> *coq = nullptr;
+        if (get_coalescer(c->dev, &coq) == CSBWA_OK && coq->fits((int)wire_b, n_tasks)) {
+            CU_TRY(cudaStreamSynchronize(c->st));                   // the wire must be complete before a group gathers it
+            int32_t dev_err = 0;
+            CU_TRY(cudaMemcpy(&dev_err, d_err, 4, cudaMemcpyDeviceToHost));
+            if (dev_err != 0) return fail(CSBWA_E_BADARG, "a task failed validation on the device");
+            uint8_t hdr32[32];
+            memset(hdr32, 0, sizeof hdr32);
+            for (int i = 0; i < 7; ++i) hdr32[i] = (uint8_t)opt7[i];
+            memcpy(hdr32 + 8, &n_tasks, 4);
+            MemcpyUser u{nullptr, out};
+            CoRequest rq;
+            rq.hdr = hdr32; rq.in_bytes = (int)wire_b; rq.n_tasks = n_tasks;
+            rq.src_dev = c->d_aux.p;
+            rq.dst_dev = ((uintptr_t)out & 3) == 0 ? pinned_dev_ptr(out, (size_t)n_tasks * 20) : nullptr;
+            rq.fill = fill_memcpy; rq.drain = drain_memcpy; rq.user = &u;
+            bool done = false;
+            rc = extend_coalesced(rq, c->dev, &done);
+            if (rc) return rc;
+            if (done) {
+                std::lock_guard<std::mutex> lk(g_stats_mu);
+                g_stats.ext_in_bytes += (int64_t)in_bytes - (int64_t)(((size_t)wire_b + 255) & ~(size_t)255);   // what crossed PCIe, not the device-to-device gather
+                g_stats.kernel_launches += 1;
+                g_stats.host_ms += now_ms() - t0;
+                return CSBWA_OK;
+            }
+        }
+    }
     if (out && n_tasks > 0) {
         rc = launch_extend((const uint8_t *)c->d_aux.p, single_call((int32_t)wire_b, n_tasks), n_tasks, (int16_t *)c->d_out.p,
                            c->d_cells, c->d_scratch.p, (int64_t)c->d_scratch.cap, c->st, c->dev, &c->aux);

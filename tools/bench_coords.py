@@ -52,9 +52,9 @@ def main():
             r0 = int(c) * args.reads_per_call
             reads = np.ascontiguousarray(rb.reads[r0:r0 + args.reads_per_call])
             loc = part.copy(); loc[:, 0] -= r0
-            calls.append((wire, reads, J.seedTasks(loc)))
+            calls.append((wire, reads, J.seedTasks(loc), rb, part))
         done += m
-    n_tasks = sum(len(t) for _, _, t in calls)
+    n_tasks = sum(len(c[2]) for c in calls)
 
     def run_wire(c):
         w = c[0]
@@ -63,11 +63,17 @@ def main():
     def run_coords(c):
         return J.extendCoords(c[1], c[2], opt, device=0)
 
+    def run_wire_packed(c):
+        # what the wire seam costs its caller in full: window fetch, reversal and nibble packing (here by the library's C
+        # packer, csbwa_pack_ext_from_seeds; the reference does it in Scala, MemChainToAlignBatched.scala:76-172, 500-563)
+        w = W.pack_ext_calls(ref, c[3], c[4], args.reads_per_call, opt)[0]
+        return J.SWExtendFPGAJNI(0).swExtendFPGAJNI(10 * len(c[2]), w)
+
     out = {}
     with ThreadPoolExecutor(args.threads) as ex:
         a = list(ex.map(run_wire, calls)); b = list(ex.map(run_coords, calls))      # warm-up + parity
         same = all(np.array_equal(x, y) for x, y in zip(a, b))
-        for name, fn in (("wire", run_wire), ("coords", run_coords)):
+        for name, fn in (("wire", run_wire), ("wire_incl_packing", run_wire_packed), ("coords", run_coords)):
             st0 = pkg.stats()
             t0 = time.perf_counter()
             for _ in range(args.steps):
