@@ -56,12 +56,27 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 
 // One SWExtend call as a row-granular state machine: start() = profile-independent set-up (first row, band
 // clamp), row() = one target row (false once the call is over: rows exhausted, an all-zero row, or the z-drop),
-// result().  sw_extend_p2 below simply runs it to completion.  (A side kernel that stepped the calls of its 32 lanes
-// row by row and refilled finished lanes from the class cursor was built on this and measured -- bit-exact, 8-13 %
-// slower on C1 / C2 / C5: refilled lanes run jobs from different places of the sorted order, and a warp's row costs
-// the width of its widest lane.  DESIGN.md 4.1.)
+// result().  sw_extend_p2 below simply runs it to completion.  (Side kernels that stepped the calls of their 32 lanes
+// row by row and handed a finished lane its next job -- from the class cursor, then from a private chunk of adjacent
+// jobs -- were built on this and measured: bit-exact, 8-13 % resp. 25-60 % slower.  DESIGN.md 4.1.)
 // STRIDE: compile-time element stride between consecutive pairs (threads per block on the device, so
 // the unrolled pair loop addresses shared memory with immediate offsets); 0 = use stride_rt
+// Row-invariant operands of P2Run::row, built once per side and passed by value: the options live in shared memory, the
+// row loop stores to shared memory, so operands derived from them inside row() are reloaded and rebuilt every row
+// (15 instructions per row in the SASS; the same trap as AlnStepK in aln_core.cuh).
+struct P2K {
+    int o_del, e_del, e_ins, oe_del, oe_ins, zdrop, ne_ins;
+    uint32_t ne_del2, noe_del2, noe_ins2;
+    CSW_HD void init(const SwOpt &o)
+    {
+        o_del = o.o_del; e_del = o.e_del; e_ins = o.e_ins; zdrop = o.zdrop;
+        oe_del = o.o_del + o.e_del; oe_ins = o.o_ins + o.e_ins;
+        ne_ins = -e_ins;
+        ne_del2 = pk16(-e_del, -e_del);
+        noe_del2 = pk16(-oe_del, -oe_del); noe_ins2 = pk16(-oe_ins, -oe_ins);
+    }
+};
+
 struct P2Run {
     int qlen, tlen, h0, w;
     int i, beg, end, best, best_i, best_j, best_ie, gscore, max_off, cells, hm1;
@@ -90,22 +105,20 @@ struct P2Run {
     }
 
     template <int STRIDE>
-    CSW_HD bool row(const SwOpt &o, P2Pair *he, const uint16_t *sel, int stride_rt)
+    CSW_HD bool row(const SwOpt &o, const P2K &K, P2Pair *he, const uint16_t *sel, int stride_rt)
     {
         if (i >= tlen) return false;
         const int stride = STRIDE ? STRIDE : stride_rt;
-        const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-        const int e_del = o.e_del, e_ins = o.e_ins, zdrop = o.zdrop;
-        const int ne_ins = -e_ins;
-        const uint32_t ne_del2 = pk16(-e_del, -e_del);
-        const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
+        const int e_del = K.e_del, e_ins = K.e_ins, zdrop = K.zdrop;
+        const int ne_ins = K.ne_ins;
+        const uint32_t ne_del2 = K.ne_del2, noe_del2 = K.noe_del2, noe_ins2 = K.noe_ins2;
         uint16_t *h16 = (uint16_t *)he;
         const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
 #define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
 #define P2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
         int t = ts.next(); if (t > 4) t = 4;
         const uint32_t tlo = o.tlo[t], thi = o.thi[t];
-        const int h1i = imax(h0 - (o.o_del + e_del * (i + 1)), 0);
+        const int h1i = imax(h0 - (K.o_del + e_del * (i + 1)), 0);
         beg = imax(beg, i - w);
         end = min3(end, i + w + 1, qlen);
         uint32_t key2 = 0, zk2 = 0xffffffffu;          // zk2: packed MIN of (h << 7 | pair) ^ 127: smallest h, then last pair
@@ -256,8 +269,10 @@ CSW_HD void sw_extend_p2(const SwOpt &o, P2Pair *he, uint16_t *sel, int stride_r
                          int w, int end_bonus, int h0, SwExtRes &res)
 {
     P2Run r;
+    P2K kk;                                            // by value: registers for the whole call
+    kk.init(o);
     r.start(o, he, STRIDE ? STRIDE : stride_rt, qlen, words, t_nib, tlen, w, end_bonus, h0);
-    while (r.template row<STRIDE>(o, he, sel, stride_rt)) {}
+    while (r.template row<STRIDE>(o, kk, he, sel, stride_rt)) {}
     r.result(res);
 }
 
