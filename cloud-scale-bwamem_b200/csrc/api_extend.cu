@@ -124,8 +124,7 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
         } else if (core == EXT_CORE_P2) {
             // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
             const int npairs = cap / 2;
-            static const int one_warp_cls = env_int("CSBWA_EXT_ONE_WARP_CLS", 2, 0, 6);
-            const bool lng = cls <= one_warp_cls;           // 256 / 192 columns: one warp per block
+            const bool lng = cls <= 2;                      // 256 / 192 columns: one warp per block (more classes: measured slower)
             const int bd = lng ? EXT_BD_LONG : EXT_BD;      // the core is compiled for these strides
             const size_t smem = (size_t)npairs * bd * 10;
             int grid = (n + bd - 1) / bd;

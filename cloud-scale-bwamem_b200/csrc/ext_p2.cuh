@@ -80,7 +80,7 @@ struct P2K {
 struct P2Run {
     int qlen, tlen, h0, w;
     int i, beg, end, best, best_i, best_j, best_ie, gscore, max_off, cells, hm1;
-    NibStream ts;
+    NibStreamAhead ts;
 
     CSW_HD void start(const SwOpt &o, P2Pair *he, int stride, int qlen_, const uint32_t *words, int t_nib, int tlen_,
                       int w_, int end_bonus, int h0_)
@@ -101,7 +101,7 @@ struct P2Run {
         beg = 0; end = qlen; cells = 0;
         hm1 = h0;                                      // H(i-1, -1)
         i = 0;
-        if (tlen > 0) ts.init(words, t_nib);
+        if (tlen > 0) ts.init(words, t_nib, tlen);
     }
 
     template <int STRIDE>

@@ -254,6 +254,37 @@ struct NibStream {
     }
 };
 
+// The same stream with the NEXT word already in flight: the target bases of SWExtend are consumed one per row, so a
+// word lasts 8 rows and the load of its successor has that long to arrive -- the row that needs a new word finds it in
+// a register instead of waiting for a global load it issued a moment ago (long-scoreboard stalls were 0.3-0.8 of a
+// cycle per issued instruction in the class kernels).  Never reads past the last word of the stream.
+struct NibStreamAhead {
+    const uint32_t *p, *pend;   // next word to fetch, one past the last word of the stream
+    uint32_t cur, nxt;
+    int left;
+    CSW_HD void init(const uint32_t *words, int start_nibble, int n_nibbles)
+    {
+        p = words + (start_nibble >> 3);
+        pend = words + ((start_nibble + n_nibbles + 7) >> 3);
+        const int sk = start_nibble & 7;
+        cur = *p++;
+        nxt = p < pend ? *p++ : 0u;
+        cur <<= 4 * sk;
+        left = 8 - sk;
+    }
+    CSW_HD int next()
+    {
+        if (left == 0) {
+            cur = nxt; left = 8;
+            if (p < pend) nxt = *p++;
+        }
+        int v = (int)(cur >> 28);
+        cur <<= 4;
+        --left;
+        return v;
+    }
+};
+
 CSW_HD int nib_at(const uint32_t *words, int k)
 {
     return (int)((words[k >> 3] >> (28 - 4 * (k & 7))) & 0xf);
