@@ -176,9 +176,9 @@ struct CudaAlnCoExec {
         CU_TRY(cudaGetLastError());
         return CSBWA_OK;
     }
-    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen)
+    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen, int others)
     {
-        (void)n_calls; (void)n_units; (void)gen;
+        (void)n_calls; (void)n_units; (void)gen; (void)others;
         Slot &s = slots[slot];
         s.polls = 0; s.n_jobs = n_tasks; s.span = span > table_bytes ? span - table_bytes : 0;
         s.detail.clear();

@@ -92,6 +92,31 @@ extern "C" int csbwa_set_ext_mode(int mode)
     return prev;
 }
 
+// Lane-group side kernels (ext_coop.cuh) serve launch sequences of at most this many tasks -- groups that leave most of
+// the device idle, where the longest side run by ONE lane is the whole phase.  0 = never.  CSBWA_EXT_COOP_MAX sets the
+// start-up value, csbwa_set_ext_coop_max changes it at run time (the seam's graphs follow: CudaCoExec::launch).
+static std::atomic<int> g_ext_coop_max{-1};
+static int ext_coop_max()
+{
+    int v = g_ext_coop_max.load(std::memory_order_relaxed);
+    if (v < 0) {
+        v = env_int("CSBWA_EXT_COOP_MAX", 8192, 0, 1 << 30);
+        g_ext_coop_max.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+extern "C" int csbwa_set_ext_coop_max(int max_tasks)
+{
+    const int prev = ext_coop_max();
+    if (max_tasks >= 0) g_ext_coop_max.store(max_tasks, std::memory_order_relaxed);
+    return prev;
+}
+static int ext_coop_lanes()      // lanes per task: 32 (default), 16 or 8
+{
+    static const int g = [] { const int v = env_int("CSBWA_EXT_COOP_G", 32, 8, 32); return v == 8 || v == 16 ? v : 32; }();
+    return g;
+}
+
 // resident blocks per SM for a block of bd threads using smem bytes of dynamic shared memory
 static int blocks_per_sm(int bd, size_t smem, int regs_per_thread)
 {
@@ -170,6 +195,22 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     int gb = (n + tb - 1) / tb;
     if (gb > dev_sms(dev) * 8) gb = dev_sms(dev) * 8;     // grid-stride kernels
     const int core = ext_core();
+    if (core == EXT_CORE_P2 && n <= ext_coop_max()) {
+        // small launch sequence: one kernel, a lane group per task (ext_kernels.cuh k_ext_small)
+        const int g = ext_coop_lanes();
+        const int per_block = EXT_BD / g;
+        const size_t smem = (size_t)per_block * EXT_COOP_SLOT;
+        int grid = (n + per_block - 1) / per_block;
+        const int cap_grid = dev_sms(dev) * blocks_per_sm(EXT_BD, smem, 128);
+        if (grid > cap_grid) grid = cap_grid;
+        const unsigned long long eh_cap = (unsigned long long)(scratch_bytes - fixed);
+        int16_t *o16 = d_out;
+        if (g == 8) k_ext_small<8><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
+        else if (g == 16) k_ext_small<16><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
+        else k_ext_small<32><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
+        CU_TRY(cudaGetLastError());
+        return CSBWA_OK;
+    }
     k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
     k_ext_scan<<<1, EXT_SCAN_BD, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
@@ -307,7 +348,7 @@ static int check_ext_wire(const uint8_t *hdr, int32_t in_bytes, int32_t *n_out)
 // group costs the host ONE driver call (cudaGraphLaunch) by the coalescer's pump thread; completion
 // is a word the device writes into pinned memory.
 struct CudaCoExec {
-    static constexpr int kGraphVariants = 3;
+    static constexpr int kGraphVariants = 4;
     struct Slot {
         cudaStream_t st = nullptr;
         uint8_t *h_in = nullptr, *h_out = nullptr;       // pinned + mapped: table / staged wire bytes; trailer / staged replies
@@ -316,20 +357,30 @@ struct CudaCoExec {
         void *d_scratch = nullptr;
         unsigned int *d_count = nullptr;                 // block counter of k_co_scatter
         AuxSet aux;
-        // one graph per size class of the group (grids sized for <= 16384 / 65536 / max_tasks tasks): a small
-        // group must not launch the thousands of empty blocks a 262144-task grid needs
+        // one graph per size class of the group (grids sized for <= ext_coop_max() / 16384 / 65536 / max_tasks tasks): a
+        // small group must not launch the thousands of empty blocks a 262144-task grid needs, and the smallest
+        // groups run the lane-group side kernels (launch_extend decides by the same bound)
         cudaGraphExec_t graph[kGraphVariants] = {nullptr};
         int graph_core[kGraphVariants] = {0};
+        int graph_coop[kGraphVariants] = {0};          // ext_coop_max() the graph was captured under
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // non-graph mode only: gather | launch sequence | scatter
         int polls = 0;
         double t_launch = 0;
         size_t span = 0;
         std::string detail;
     };
-    int variant_cap(int v) const { return v == 0 ? (max_tasks < 16384 ? max_tasks : 16384) : v == 1 ? (max_tasks < 65536 ? max_tasks : 65536) : max_tasks; }
-    int graph_variant(int n_tasks) const
+    int variant_cap(int v) const
     {
-        int v = 0;
+        const int c = v == 0 ? (ext_coop_max() < 16384 ? ext_coop_max() : 16384) : v == 1 ? 16384 : v == 2 ? 65536 : max_tasks;
+        return c < max_tasks ? c : max_tasks;
+    }
+    // others: groups already on the device.  The lane-group kernel spends ~5x the instructions of the class kernels to
+    // cut a small group's latency -- a trade for an idle device only (measured, 64 callers: -4 % when small groups took it
+    // regardless of load)
+    int graph_variant(int n_tasks, int others) const
+    {
+        if (ext_coop_max() > 0 && n_tasks <= variant_cap(0) && others <= coop_busy) return 0;
+        int v = 1;
         while (v < kGraphVariants - 1 && variant_cap(v) < n_tasks) ++v;
         return v;
     }
@@ -339,6 +390,7 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
+    int coop_busy = 1;          // CSBWA_EXT_COOP_BUSY: a small group takes the lane-group kernel while at most this many others run
     // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma (default): one cudaMemcpyAsync per call and direction around
     // the graph -- the copy engines move one group's bytes while the SMs run the kernels of the others.  sm: gather /
     // scatter kernels inside the graph -- one driver call per group, but the copy blocks need room on SMs that the side
@@ -359,6 +411,7 @@ struct CudaCoExec {
         use_graph = !(e && e[0] == '0');
         e = getenv("CSBWA_CO_ONE_GRAPH");
         one_graph = e && e[0] == '1';
+        coop_busy = env_int("CSBWA_EXT_COOP_BUSY", 1, 0, 64);
         e = getenv("CSBWA_CO_COPY");
         dma = !(e && e[0] == 's');
         CU_TRY(cudaSetDevice(dev));
@@ -382,6 +435,7 @@ struct CudaCoExec {
             const double t0 = now_ms();
             for (auto &s : slots)
                 for (int v = 0; v < kGraphVariants; ++v) {
+                    if (variant_cap(v) <= 0) continue;     // lane-group path switched off
                     const int rc = build_graph(s, v);
                     if (rc) return rc;
                 }
@@ -422,7 +476,7 @@ struct CudaCoExec {
         CU_TRY(cudaMemsetAsync(s.d_out, 0, kTrailer, s.st));
         if (!dma) {
             k_co_head<<<4, 256, 0, s.st>>>((uint4 *)s.d_in, (const uint4 *)s.dv_in, (int)(table_bytes / 16));
-            k_co_gather<<<variant == 0 ? 16 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off);
+            k_co_gather<<<variant <= 1 ? 16 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off);
         }
         if (timed) CU_TRY(cudaEventRecord(s.ev[1], s.st));
         ExtCalls cs;
@@ -435,7 +489,7 @@ struct CudaCoExec {
         if (dma) k_co_finish<<<1, 32, 0, s.st>>>(s.d_in, hdr_off, &((const ExtHdr *)s.d_scratch)->err, ((const ExtHdr *)s.d_scratch)->bad_call_bits, (CoTrailer *)s.d_out);
         if (timed) CU_TRY(cudaEventRecord(s.ev[2], s.st));
         if (!dma)
-            k_co_scatter<<<variant == 0 ? 8 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
+            k_co_scatter<<<variant <= 1 ? 8 : 32, 256, 0, s.st>>>(s.d_in, hdr_off, ext_off, (const uint32_t *)(s.d_out + kTrailer),
                                                                  (const unsigned long long *)s.d_out, &((const ExtHdr *)s.d_scratch)->err,
                                                                  ((const ExtHdr *)s.d_scratch)->bad_call_bits, (CoTrailer *)s.dv_out, s.d_count, 5);
         if (timed && !dma) CU_TRY(cudaEventRecord(s.ev[3], s.st));
@@ -455,18 +509,19 @@ struct CudaCoExec {
         cudaGraphDestroy(g);
         if (e != cudaSuccess) { s.graph[v] = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
         s.graph_core[v] = ext_core();
+        s.graph_coop[v] = ext_coop_max();
         return CSBWA_OK;
     }
 
     // asynchronous: the group's table is already in the slot's pinned staging (written by the pump)
-    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen)
+    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen, int others)
     {
         (void)n_calls; (void)n_units; (void)gen;
         Slot &s = slots[slot];
         s.polls = 0;
         s.span = span > table_bytes ? span - table_bytes : 0;
         s.detail.clear();
-        int rc = launch_inner(s, n_tasks);
+        int rc = launch_inner(s, n_tasks, others);
         if (rc) {
             s.detail = csbwa_last_error();
             cudaStreamSynchronize(s.st);       // nothing of this group may still be queued when the slot is handed back
@@ -474,11 +529,11 @@ struct CudaCoExec {
         s.t_launch = now_ms();
         return rc;
     }
-    int launch_inner(Slot &s, int n_tasks)
+    int launch_inner(Slot &s, int n_tasks, int others)
     {
         CU_TRY(cudaSetDevice(dev));
-        const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks);
-        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core())) {
+        const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks, others);
+        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core() || s.graph_coop[v] != ext_coop_max())) {
             int rc = build_graph(s, v);
             if (rc) return rc;
         }

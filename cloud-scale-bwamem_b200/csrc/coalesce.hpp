@@ -76,7 +76,8 @@ struct CoRequest {
 // Executor concept:
 //   uint8_t *in_staging(int slot);  int16_t *out_staging(int slot);          host addresses (pinned, capacity = limits)
 //   unsigned long long in_staging_dev(int slot), out_staging_dev(int slot);   the same, as the device sees them
-//   int launch(int slot, int n_calls, size_t span_bytes, int n_tasks, int n_units, unsigned gen);
+//   int launch(int slot, int n_calls, size_t span_bytes, int n_tasks, int n_units, unsigned gen, int others);
+//       (others: groups already on the device when this one starts)
 //       asynchronous: the table {CoCall[max_calls], dyn[4], CoExt[max_calls]} is already in in_staging
 //   int poll(int slot, unsigned gen);      0 = still running, 1 = finished, < 0 = the submission failed
 //   int finish(int slot, int n_calls, int n_tasks, uint8_t *call_bad);
@@ -337,6 +338,8 @@ private:
                 if (g.state != CLOSED) continue;
                 if (g.copying > 0) { busy = true; continue; }
                 g.state = RUNNING;
+                int others = 0;                             // groups on the device when this one starts
+                for (auto &q : groups_) if (&q != &g && q.state == RUNNING) ++others;
                 lk.unlock();
                 const long long t1 = now_ns();
                 uint8_t *h = ex_->in_staging(g.slot);
@@ -345,7 +348,7 @@ private:
                 memcpy(h + header_off(), dyn, sizeof dyn);
                 memcpy(h + ext_off(), g.ext.data(), g.ext.size() * sizeof(CoExt));
                 memset(g.call_bad.data(), 0, g.call_bad.size());
-                const int rc = ex_->launch(g.slot, (int)g.calls.size(), g.bytes, g.tasks, g.units, g.gen);
+                const int rc = ex_->launch(g.slot, (int)g.calls.size(), g.bytes, g.tasks, g.units, g.gen, others);
                 g.t_launched = now_ns();
                 t_close_ += t1 - g.t_closed; t_launch_ += g.t_launched - t1;
                 if (rc < 0) { g.t_launched = 0; complete(&g, rc); }
@@ -362,7 +365,8 @@ private:
             for (auto &g : groups_) if (g.state == OPEN && !g.calls.empty() && inflight_ < max_inflight_) open_work = true;
             if (open_work) continue;
             if (busy) {
-                cv_work_.wait_for(lk, std::chrono::microseconds(nap_us_));
+                // one group in flight = a caller (or two) waiting on exactly that group: poll it closely
+                cv_work_.wait_for(lk, std::chrono::microseconds(inflight_ <= 1 ? (nap_us_ < 5 ? nap_us_ : 5) : nap_us_));
             } else {
                 pump_idle_ = true;
                 cv_work_.wait(lk, [&] {

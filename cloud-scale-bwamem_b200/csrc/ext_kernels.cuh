@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include "ext_core.cuh"
 #include "ext_p2.cuh"
+#include "ext_coop.cuh"
 
 namespace csw {
 
@@ -433,5 +434,115 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     }
     if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
 }
+
+// Small launch sequences (ext_coop.cuh): ONE kernel for the whole call group.  A group of G lanes takes a task, validates
+// its record, runs the LEFT side, then the RIGHT side seeded with the left score, and writes the reply -- no histogram,
+// scan or counting sort (their purpose is lane-uniform work inside a warp of independent sides; a lane group IS one
+// side), no kernel boundary between the sides, so a task's right side starts when ITS left side is done, and the
+// launch sequence is {memset, this kernel} instead of seventeen nodes.  Sides the column-pair core cannot take (scores
+// above 511, query longer than 255: outliers) run the int32 core on the group's first lane.  The host seam launches this
+// for groups small enough to leave the device mostly idle (api_extend.cu launch_extend).
+constexpr int EXT_COOP_PAIRS = 129;                          // p2_pairs(255) + 1
+constexpr int EXT_COOP_SLOT = (EXT_COOP_PAIRS * 10 + 15) & ~15;   // bytes of shared memory per task in flight
+#if defined(__CUDACC__)
+template <int G>
+__global__ void __launch_bounds__(EXT_BD)
+k_ext_small(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr, int *__restrict__ ehbase,
+            unsigned long long eh_cap, int16_t *__restrict__ out, unsigned long long *cells_acc)
+{
+    extern __shared__ uint4 smem4[];
+    ext_resolve(cs, n);
+    __shared__ SwOpt s_opt;
+    if (threadIdx.x == 0) {
+        const uint8_t *in0 = base + ext_call(cs, 0).in_off;
+        ext_parse_header(in0, s_opt);
+        if (blockIdx.x == 0) {                               // coalesced calls must carry the same options (k_ext_hist)
+            for (int c = 1; c < cs.n_calls; ++c) {
+                const uint8_t *inc = base + ext_call(cs, c).in_off;
+                bool same = true;
+                for (int b = 0; b < 32; ++b) if ((b < 8 || b >= 12) && inc[b] != in0[b]) same = false;
+                if (!same) atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
+            }
+        }
+    }
+    __syncthreads();
+    const SwOpt &o = s_opt;
+    constexpr int TPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    CoopLane<G> L;
+    L.init();
+    P2Pair *he = (P2Pair *)((char *)smem4 + (size_t)(threadIdx.x / G) * EXT_COOP_SLOT);
+    uint16_t *sel = (uint16_t *)(he + EXT_COOP_PAIRS);
+    unsigned long long my_cells = 0;
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&hdr->work[0][0], (uint32_t)TPW);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= (uint32_t)n) break;
+        const int k = (int)chunk + lane / G;                 // global task index
+        if (k < n) {
+            const int c = ext_locate(cs, k);
+            const ExtCall &cl = ext_call(cs, c);
+            const uint8_t *in = base + cl.in_off;
+            ExtTask t = read_task(in, k - cl.task_base);
+            int bl = 0, br = 0;
+            if (!ext_task_ok(t, cl.n_tasks, cl.in_bytes)) {
+                if (L.gl == 0) {
+                    atomicExch(&hdr->err, CSBWA_E_BADWIRE_DEV);
+                    if (c < 256) atomicOr(&hdr->bad_call_bits[c >> 5], 1u << (c & 31));
+                }
+                t.lq = t.lr = t.rq = t.rr = 0; t.pos = 8 + 8 * cl.n_tasks;
+            } else {
+                bl = ext_side_bin(o, t.lq, t.h0, EXT_CORE_P2);
+                const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
+                br = ext_side_bin(o, t.rq, h0r, EXT_CORE_P2);
+                if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+            }
+            const uint32_t *words = (const uint32_t *)in + t.pos;
+            SideRes Lr, Rr;
+            Lr.score = 0; Lr.qle = Lr.tle = Lr.gtle = Lr.gscore = 0; Lr.aw = (int16_t)o.w; Lr.cells = 0;
+            Rr = Lr;
+            int *H = nullptr, *E = nullptr;
+            if ((bl == 256 || br == 256) && L.gl == 0) {     // int32 rows of the outlier sides (same budget as k_ext_side)
+                const int qm = t.lq > t.rq ? t.lq : t.rq;
+                const unsigned long long need = ((unsigned long long)(qm + 2) * 8 + 15) & ~15ull;
+                const unsigned long long off = atomicAdd(&hdr->eh_bump, need);
+                if (off + need > eh_cap) atomicExch(&hdr->err, -7);
+                else { H = (int *)((char *)ehbase + off); E = H + (qm + 2); }
+            }
+            if (bl == 256) {
+                if (L.gl == 0 && H)
+                    ext_run_side<false>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
+                                        nullptr, 0, H, E, Lr);
+                __syncwarp(L.gm);
+            } else if (bl) {
+                coop_run_side<G>(L, o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score, he, sel, Lr);
+            }
+            // (a left side on the first lane's int32 core forces the right side there too: Lr is only needed by that lane)
+            const int sc0 = t.lq > 0 ? (int)Lr.score : t.reg_score;
+            if (br == 256) {
+                if (L.gl == 0 && H)
+                    ext_run_side<false>(o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0,
+                                        nullptr, 0, H, E, Rr);
+                __syncwarp(L.gm);
+            } else if (br) {
+                coop_run_side<G>(L, o, words, seg_rq(t), t.rq, seg_rr(t), t.rr, o.pen_clip3, sc0, sc0, he, sel, Rr);
+            }
+            if (L.gl == 0) {
+                if ((bl == 256 || br == 256) && !H) { t.lq = t.rq = 0; }      // scratch exhausted: reported, nothing was run
+                my_cells += (unsigned)Lr.cells + (unsigned)Rr.cells;
+                int16_t rec[10];
+                ext_finalize(o, t, &Lr, &Rr, rec);
+                uint32_t *dst = (uint32_t *)(out + cl.out_off + (size_t)10 * (k - cl.task_base));
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    dst[q] = (uint32_t)(uint16_t)rec[2 * q] | ((uint32_t)(uint16_t)rec[2 * q + 1] << 16);
+            }
+        }
+        __syncwarp();
+    }
+    if (cells_acc && my_cells) atomicAdd(cells_acc, my_cells);
+}
+#endif
 
 } // namespace csw

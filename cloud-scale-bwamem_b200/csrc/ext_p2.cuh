@@ -109,7 +109,7 @@ struct P2Run {
     {
         if (i >= tlen) return false;
         const int stride = STRIDE ? STRIDE : stride_rt;
-        const int e_del = K.e_del, e_ins = K.e_ins, zdrop = K.zdrop;
+        const int e_del = K.e_del;
         const int ne_ins = K.ne_ins;
         const uint32_t ne_del2 = K.ne_del2, noe_del2 = K.noe_del2, noe_ins2 = K.noe_ins2;
         uint16_t *h16 = (uint16_t *)he;
@@ -214,12 +214,36 @@ struct P2Run {
             cells += end - beg;
             if (!hi_out) P2_E(end) = 0;                                // eh(end) = {h1, 0}
         }
+        return row_tail(K, h16, pstr, key2, zk2, hlast, h1i);
+#undef P2_H
+#undef P2_E
+    }
+
+    // Everything of a row after its band pass (gscore :177, row max / z-drop :187-199, band shrink :201-214), from the
+    // pass's packed keys: key2 = per-half maximum of h << 7 | pair, zk2 = per-half minimum of the same key with the
+    // pair bits inverted, hlast = H(i, end-1).
+    CSW_HD bool row_tail(const P2K &K, const uint16_t *h16, size_t pstr, uint32_t key2, uint32_t zk2, int hlast, int h1i)
+    {
+        return row_tail_kk(K, h16, pstr, row_kk(key2), row_clast(zk2), hlast, h1i);
+    }
+    // row max: larger h, then larger column (last j on ties).  Half keys are h << 7 | pair: doubling them (+1 for the odd
+    // half) turns them into h << 8 | column, one max merges them.
+    static CSW_HD int row_kk(uint32_t key2) { return imax((int)((key2 & 0xffffu) << 1), (int)((key2 >> 16) << 1) | 1); }
+    // last column of the band with H == 0 (-1: none): a half holds a zero iff its key is < 128, the pair is 127 - key
+    static CSW_HD int row_clast(uint32_t zk2)
+    {
+        const int zlo = (int)(zk2 & 0xffffu), zhi = (int)(zk2 >> 16);
+        return imax(zlo < 128 ? 2 * (127 - zlo) : -1, zhi < 128 ? 2 * (127 - zhi) + 1 : -1);
+    }
+    // the same from the merged keys (the lane-group pass of ext_coop.cuh reduces kk and clast over its lanes, then every
+    // lane runs this on the same values)
+    CSW_HD bool row_tail_kk(const P2K &K, const uint16_t *h16, size_t pstr, int kk, int clast, int hlast, int h1i)
+    {
+        const int e_del = K.e_del, e_ins = K.e_ins, zdrop = K.zdrop;
+#define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
         hm1 = h1i;
         const int jfin = beg < end ? end : beg;
         if (jfin == qlen && gscore <= hlast) { best_ie = i; gscore = hlast; }
-        // row max: larger h, then larger column (last j on ties).  Lane keys are h << 7 | pair:
-        // doubling them (+1 for the odd lane) turns them into h << 8 | column, one max merges them.
-        const int kk = imax((int)((key2 & 0xffffu) << 1), (int)((key2 >> 16) << 1) | 1);
         const int rm = kk >> 8, rmj = kk & 255;
         if (rm == 0) return false;
         if (rm > best) {
@@ -234,9 +258,6 @@ struct P2Run {
             }
         }
         // band shrink (:201-214) in own-column terms: eh[j].h == (j == beg ? h1i : Hs[j-1])
-        // last column of the band with H == 0: a lane holds a zero iff its key is < 128, the pair is 127 - key
-        const int zlo = (int)(zk2 & 0xffffu), zhi = (int)(zk2 >> 16);
-        const int clast = imax(zlo < 128 ? 2 * (127 - zlo) : -1, zhi < 128 ? 2 * (127 - zhi) + 1 : -1);
         int nbeg, nend;
         if (clast > rmj) {                                         // a zero right of the max: rescan
             int j = rmj;
@@ -253,7 +274,6 @@ struct P2Run {
         ++i;
         return true;
 #undef P2_H
-#undef P2_E
     }
 
     CSW_HD void result(SwExtRes &res) const

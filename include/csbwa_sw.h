@@ -252,6 +252,10 @@ int csbwa_extend_launches_per_call(void);
 /* extension core: 1 = two adjacent query columns per DPX s16x2 instruction (default), 0 = one
  * column per step with u8 scores.  Returns the previous mode; any other argument only queries. */
 int csbwa_set_ext_mode(int mode);
+/* Launch sequences of at most max_tasks tasks run the lane-group side kernels (8 lanes per SWExtend side instead of one
+ * -- same results, a third of the latency, 2.7x the instructions: for groups that leave the device mostly idle).
+ * 0 = never; default 8192 (env CSBWA_EXT_COOP_MAX).  Returns the previous bound; a negative argument only queries. */
+int csbwa_set_ext_coop_max(int max_tasks);
 int csbwa_align2_launches_per_call(void);
 
 /* ---- host-side helper: the caller's packer, for C/C++ hosts --------------

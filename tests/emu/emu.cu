@@ -238,9 +238,9 @@ struct HostCoExec {
     unsigned long long in_staging_dev(int slot) { return (unsigned long long)(uintptr_t)hin[slot].data(); }
     unsigned long long out_staging_dev(int slot) { return (unsigned long long)(uintptr_t)hout[slot].data(); }
     const char *detail(int) { return "host executor failure"; }
-    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen)
+    int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen, int others)
     {
-        (void)span; (void)n_tasks;
+        (void)span; (void)n_tasks; (void)others;
         if (th[slot].joinable()) th[slot].join();
         th[slot] = std::thread([this, slot, n_calls, n_units, gen] {
             if (delay_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));

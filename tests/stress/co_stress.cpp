@@ -28,7 +28,7 @@ struct Exec {
     unsigned long long in_staging_dev(int s) { return (unsigned long long)(uintptr_t)hin[s].data(); }
     unsigned long long out_staging_dev(int s) { return (unsigned long long)(uintptr_t)hout[s].data(); }
     const char *detail(int) { return ""; }
-    int launch(int s, int n_calls, size_t, int, int, unsigned gen)
+    int launch(int s, int n_calls, size_t, int, int, unsigned gen, int)
     {
         if (th[s].joinable()) th[s].join();
         th[s] = std::thread([this, s, n_calls, gen] {

@@ -26,32 +26,42 @@ def _ext_gpu(pkg, wire, device=-1):
     return pkg.jni.SWExtendFPGAJNI(device).swExtendFPGAJNI(10 * n, wire)
 
 
+ALWAYS = 1 << 30      # csbwa_set_ext_coop_max bound that sends every launch to the lane-group kernels
+
+
 def _check_ext(pkg, oracle, wire):
     """Both extension cores (1 = two query columns per DPX instruction, the default; 0 = one column
-    per step) must reproduce the oracle bit for bit, including the exact DP cell count."""
+    per step) and, for the default core, both side-kernel families (one lane per side / a lane group
+    per side) must reproduce the oracle bit for bit, including the exact DP cell count."""
     ref, rcells, _ = oracle.extend_wire(wire, n_threads=8)
     L = pkg.lib()
     prev = L.csbwa_set_ext_mode(-1)
+    prev_coop = L.csbwa_set_ext_coop_max(-1)
     try:
-        for mode in (1, 0):
+        for mode, coop in ((1, 0), (1, ALWAYS), (0, 0)):
             L.csbwa_set_ext_mode(mode)
+            L.csbwa_set_ext_coop_max(coop)
             before = pkg.stats()["ext_cells"]
             got = _ext_gpu(pkg, wire)
             bad = np.flatnonzero((got.reshape(-1, 10) != ref.reshape(-1, 10)).any(axis=1))
-            assert len(bad) == 0, (mode, len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
+            assert len(bad) == 0, (mode, coop, len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
             assert pkg.stats()["ext_cells"] - before == int(rcells.sum())      # exact DP cell count
     finally:
         L.csbwa_set_ext_mode(prev)
+        L.csbwa_set_ext_coop_max(prev_coop)
     return ref
 
 
 def test_ext_golden(pkg, oracle, gpu):
     g = np.load(os.path.join(GOLD, "ext_golden.npz"))
     L = pkg.lib()
-    for mode in (0, 1):
+    prev_coop = L.csbwa_set_ext_coop_max(-1)
+    for mode, coop in ((0, 0), (1, 0), (1, ALWAYS)):
         L.csbwa_set_ext_mode(mode)
+        L.csbwa_set_ext_coop_max(coop)
         got = _ext_gpu(pkg, g["wire"])
-        assert np.array_equal(got, g["reply"]), mode
+        assert np.array_equal(got, g["reply"]), (mode, coop)
+    L.csbwa_set_ext_coop_max(prev_coop)
 
 
 def test_ext_random_and_adversarial(pkg, oracle, gpu):
@@ -396,7 +406,10 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
                                  {"CSBWA_CO_ONE_GRAPH": "1", "CSBWA_CO_INFLIGHT": "4", "CSBWA_CO_COPY": "sm"},
                                  {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_SLOTS": "2"},
                                  {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_COPY": "sm"},
-                                 {"CSBWA_CO_COPY": "dma", "CSBWA_CO_SLOTS": "32"}])
+                                 {"CSBWA_CO_COPY": "dma", "CSBWA_CO_SLOTS": "32"},
+                                 {"CSBWA_EXT_COOP_MAX": "0"},
+                                 {"CSBWA_EXT_COOP_MAX": "100000", "CSBWA_EXT_COOP_G": "16"},
+                                 {"CSBWA_EXT_COOP_MAX": "20000", "CSBWA_EXT_COOP_G": "32", "CSBWA_CO_COPY": "sm"}])
 def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):
     """The host seam's tuning knobs (slots, groups in flight, graph variants, no graph) never change a bit: 12 caller
     threads, calls of three different sizes so that groups of all graph size classes occur; every third call uses
