@@ -374,9 +374,10 @@ struct CudaCoExec {
         const int c = v == 0 ? (ext_coop_max() < 16384 ? ext_coop_max() : 16384) : v == 1 ? 16384 : v == 2 ? 65536 : max_tasks;
         return c < max_tasks ? c : max_tasks;
     }
-    // others: groups already on the device.  The lane-group kernel spends ~5x the instructions of the class kernels to
-    // cut a small group's latency -- a trade for an idle device only (measured, 64 callers: -4 % when small groups took it
-    // regardless of load)
+    // others: groups already on the device.  The lane-group kernel spends 5-8x the instructions of the class kernels to
+    // cut a small group's latency -- a trade for a mostly idle device only.  Measured, 4096-read calls (GCUPS end to end
+    // at 1 / 2 / 3 / 4 / 8 / 16 / 64 callers): never 26 / 49 / 74 / 89 / 154 / 274 / 905; while at most 2 others run
+    // 67 / 102 / 115 / 114 / 169 / 272 / 905; regardless of load, 64 callers lose 4 %.
     int graph_variant(int n_tasks, int others) const
     {
         if (ext_coop_max() > 0 && n_tasks <= variant_cap(0) && others <= coop_busy) return 0;
@@ -390,7 +391,7 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
-    int coop_busy = 1;          // CSBWA_EXT_COOP_BUSY: a small group takes the lane-group kernel while at most this many others run
+    int coop_busy = 2;          // CSBWA_EXT_COOP_BUSY: a small group takes the lane-group kernel while at most this many others run
     // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma (default): one cudaMemcpyAsync per call and direction around
     // the graph -- the copy engines move one group's bytes while the SMs run the kernels of the others.  sm: gather /
     // scatter kernels inside the graph -- one driver call per group, but the copy blocks need room on SMs that the side
@@ -411,7 +412,7 @@ struct CudaCoExec {
         use_graph = !(e && e[0] == '0');
         e = getenv("CSBWA_CO_ONE_GRAPH");
         one_graph = e && e[0] == '1';
-        coop_busy = env_int("CSBWA_EXT_COOP_BUSY", 1, 0, 64);
+        coop_busy = env_int("CSBWA_EXT_COOP_BUSY", 2, 0, 64);
         e = getenv("CSBWA_CO_COPY");
         dma = !(e && e[0] == 's');
         CU_TRY(cudaSetDevice(dev));

@@ -64,7 +64,9 @@ def main():
     dt = time.perf_counter() - t0
     s1 = pkg.stats()
     g = max(1, s1["ext_groups"] - s0["ext_groups"])
-    res = {"threads": args.threads, "slots": os.environ.get("CSBWA_CO_SLOTS", "default"), "inflight": os.environ.get("CSBWA_CO_INFLIGHT", "default"),
+    res = {"threads": args.threads, "small_group_max_tasks": L.csbwa_set_ext_coop_max(-1),
+           "small_group_busy": os.environ.get("CSBWA_EXT_COOP_BUSY", "default"), "ms_per_call": args.threads * dt * 1e3 / (n * args.repeat),
+           "slots": os.environ.get("CSBWA_CO_SLOTS", "default"), "inflight": os.environ.get("CSBWA_CO_INFLIGHT", "default"),
            "pinned": args.pinned, "cpus": len(os.sched_getaffinity(0)), "split": args.split, "zero_copy_calls": s1["ext_zero_copy_calls"] - s0["ext_zero_copy_calls"],
            "calls": n * args.repeat, "calls_per_ms": n * args.repeat / dt / 1e3,
            "gcups": (s1["ext_cells"] - s0["ext_cells"]) / dt / 1e9,
