@@ -38,6 +38,7 @@
 #if defined(__linux__)
 #include <linux/futex.h>
 #include <sys/prctl.h>
+#include <sys/resource.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 #endif
@@ -310,6 +311,14 @@ private:
     {
 #if defined(__linux__)
         prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);             // 1 us: the naps below are 20 us
+        // The pump is the one thread every caller of this GPU waits on, and it sleeps most of the time: when the callers
+        // outnumber the cores (8 GPUs on 32 vCPUs: 64 callers per 4 cores) it should not queue behind them.  Needs
+        // CAP_SYS_NICE; silently stays at the default priority without it.  CSBWA_PUMP_NICE=0 keeps the default.
+        {
+            const char *e = getenv("CSBWA_PUMP_NICE");
+            const int nice_v = e ? atoi(e) : -10;
+            if (nice_v != 0) (void)setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), nice_v);
+        }
 #endif
         std::unique_lock<std::mutex> lk(mu_);
         for (;;) {
