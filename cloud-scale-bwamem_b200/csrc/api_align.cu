@@ -253,7 +253,7 @@ static int get_aln_coalescer(int dev, Coalescer<CudaAlnCoExec> **out)
     std::lock_guard<std::mutex> lk(g_aco_mu);
     if (!g_aco[dev]) {
         AlnCoDev *d = new AlnCoDev();
-        const int n_slots = env_int("CSBWA_ALN_CO_SLOTS", 6, 2, 16);
+        const int n_slots = env_int("CSBWA_ALN_CO_SLOTS", 12, 2, 32);     // 10-pair calls, 64 callers: 6 / 12 / 16 slots = 272 / 300 / 305 GCUPS
         const int inflight = env_int("CSBWA_ALN_CO_INFLIGHT", n_slots - 1, 1, n_slots - 1);
         Coalescer<CudaAlnCoExec>::Limits lim{kAlnCoMaxBytes, kAlnCoMaxJobs, kAlnCoMaxCalls, 14};
         const size_t hdr_off = (size_t)kAlnCoMaxCalls * sizeof(CoCall), ext_off = hdr_off + 16;
