@@ -117,6 +117,10 @@ static int ext_coop_lanes()      // lanes per task: 32 (default), 16 or 8
     return g;
 }
 
+// kernels one launch sequence of n tasks enqueues: the class path (3 preparation kernels + 7 classes x 2 sides) or the
+// one lane-group kernel of a small sequence (launch_extend decides by the same bound)
+static int ext_launches_for(int n) { return ext_core() == EXT_CORE_P2 && n <= ext_coop_max() ? 1 : kExtLaunches; }
+
 // resident blocks per SM for a block of bd threads using smem bytes of dynamic shared memory
 static int blocks_per_sm(int bd, size_t smem, int regs_per_thread)
 {
@@ -240,7 +244,7 @@ extern "C" int csbwa_extend_batch_device(const void *d_in, int32_t in_bytes, int
                            aux_for_stream(dev, (cudaStream_t)stream));
     if (rc == CSBWA_OK && n_tasks > 0) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
-        g_stats.kernel_launches += kExtLaunches;
+        g_stats.kernel_launches += ext_launches_for(n_tasks);
     }
     return rc;
 }
@@ -271,7 +275,7 @@ extern "C" int csbwa_extend_multi_device(const void *d_in_base, const csbwa_ext_
                            aux_for_stream(dev, (cudaStream_t)stream));
     if (rc == CSBWA_OK && n > 0) {
         std::lock_guard<std::mutex> lk(g_stats_mu);
-        g_stats.kernel_launches += kExtLaunches;
+        g_stats.kernel_launches += ext_launches_for((int)n);
     }
     return rc;
 }
@@ -365,6 +369,7 @@ struct CudaCoExec {
         int graph_coop[kGraphVariants] = {0};          // ext_coop_max() the graph was captured under
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // non-graph mode only: gather | launch sequence | scatter
         int polls = 0;
+        int launches = 0;                                // kernels of the group in flight (stats)
         double t_launch = 0;
         size_t span = 0;
         std::string detail;
@@ -534,6 +539,7 @@ struct CudaCoExec {
     {
         CU_TRY(cudaSetDevice(dev));
         const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks, others);
+        s.launches = ext_launches_for(variant_cap(v));
         if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core() || s.graph_coop[v] != ext_coop_max())) {
             int rc = build_graph(s, v);
             if (rc) return rc;
@@ -610,7 +616,7 @@ struct CudaCoExec {
             std::lock_guard<std::mutex> lk(g_stats_mu);
             g_stats.ext_calls += n_calls; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)t->cells;
             g_stats.ext_in_bytes += (int64_t)s.span; g_stats.ext_out_bytes += (int64_t)n_tasks * 20;
-            g_stats.kernel_launches += kExtLaunches + (dma ? 1 : 3);
+            g_stats.kernel_launches += s.launches + (dma ? 1 : 3);
             g_stats.ext_groups += 1;
             g_stats.h2d_ms += t_h2d; g_stats.kernel_ms += t_k; g_stats.d2h_ms += t_d2h;
             g_stats.host_ms += dt;
@@ -829,7 +835,7 @@ static int extend_batch_direct(const uint8_t *in, int32_t in_bytes, int16_t *out
         std::lock_guard<std::mutex> lk(g_stats_mu);
         g_stats.ext_calls++; g_stats.ext_tasks += n; g_stats.ext_cells += (int64_t)*c->h_cells;
         g_stats.ext_in_bytes += in_bytes; g_stats.ext_out_bytes += (int64_t)out_bytes;
-        g_stats.kernel_launches += kExtLaunches;
+        g_stats.kernel_launches += ext_launches_for(n);
         g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += d;
         g_stats.host_ms += now_ms() - t0;
     }
@@ -1080,7 +1086,7 @@ static int coords_run(const uint8_t *reads, int32_t n_reads, int32_t read_len, c
         if (out && n_tasks > 0) {
             g_stats.ext_calls++; g_stats.ext_tasks += n_tasks; g_stats.ext_cells += (int64_t)*c->h_cells;
             g_stats.ext_in_bytes += (int64_t)in_bytes; g_stats.ext_out_bytes += (int64_t)out_bytes;
-            g_stats.kernel_launches += kExtLaunches + 1;
+            g_stats.kernel_launches += ext_launches_for(n_tasks) + 1;
         }
         g_stats.h2d_ms += a; g_stats.kernel_ms += b; g_stats.d2h_ms += dd;
         g_stats.host_ms += now_ms() - t0;

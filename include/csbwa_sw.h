@@ -247,7 +247,8 @@ int csbwa_align2_batch_device(const void *d_jobs, int32_t n_jobs, const void *d_
                               void *d_cells, void *d_scratch, int64_t scratch_bytes,
                               void *stream);
 
-/* number of kernels one *_batch_device call enqueues (for launch accounting) */
+/* number of kernels one *_batch_device call enqueues (for launch accounting); for the extension seam: of a launch
+ * sequence above the small-group bound (csbwa_set_ext_coop_max) -- a smaller one is ONE kernel */
 int csbwa_extend_launches_per_call(void);
 /* extension core: 1 = two adjacent query columns per DPX s16x2 instruction (default), 0 = one
  * column per step with u8 scores.  Returns the previous mode; any other argument only queries. */
