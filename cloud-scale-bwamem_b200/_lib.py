@@ -32,7 +32,7 @@ EXPORTS = [
     "csbwa_extend_scratch_bytes", "csbwa_extend_batch_device", "csbwa_align2_scratch_bytes",
     "csbwa_align2_batch_device", "csbwa_extend_launches_per_call", "csbwa_align2_launches_per_call",
     "csbwa_pack_ext_bytes", "csbwa_pack_ext_tasks", "csbwa_pack_ext_from_seeds", "csbwa_int_peak", "csbwa_extend_profile_device", "csbwa_extend_multi_device", "csbwa_extend_calls", "csbwa_matesw_group", "csbwa_global_batch", "csbwa_global_scratch_bytes",
-    "csbwa_global_batch_device", "csbwa_global_batch_device_ring", "csbwa_global_ring_pairs", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_set_ext_coop_max", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat", "csbwa_h2d_probe",
+    "csbwa_global_batch_device", "csbwa_global_batch_device_ring", "csbwa_global_ring_pairs", "csbwa_global_launches_per_call", "csbwa_set_ext_mode", "csbwa_set_ext_coop_max", "csbwa_set_ext_fused_max", "csbwa_global_z_cells", "csbwa_ref_upload", "csbwa_ref_release", "csbwa_extend_coords_batch", "csbwa_expand_coords", "csbwa_chain2aln_flat", "csbwa_h2d_probe",
     "csbwa_extend_batch_cb", "csbwa_host_alloc", "csbwa_host_free", "csbwa_host_register", "csbwa_host_unregister", "csbwa_host_is_pinned",
     "csbwa_set_matesw_semantics", "csbwa_pestat_prep", "csbwa_pestat_compute", "csbwa_stream_copy", "csbwa_align2_calls",
 ]
@@ -99,6 +99,7 @@ def lib():
     L.csbwa_global_launches_per_call.restype = C.c_int
     L.csbwa_set_ext_mode.argtypes = [C.c_int]; L.csbwa_set_ext_mode.restype = C.c_int
     L.csbwa_set_ext_coop_max.argtypes = [C.c_int]; L.csbwa_set_ext_coop_max.restype = C.c_int
+    L.csbwa_set_ext_fused_max.argtypes = [C.c_int]; L.csbwa_set_ext_fused_max.restype = C.c_int
     L.csbwa_global_z_cells.argtypes = [i32, i32, i32]; L.csbwa_global_z_cells.restype = i64
     L.csbwa_ref_upload.argtypes = [vp, i64, C.c_int]; L.csbwa_ref_upload.restype = C.c_int
     L.csbwa_ref_release.argtypes = [C.c_int]; L.csbwa_ref_release.restype = C.c_int

@@ -44,6 +44,9 @@ static int ensure_dev_attrs(int dev)
     const int big_p2l = 128 * EXT_BD_LONG * 10;      // the 256-column class at one warp per block
     CU_TRY(cudaFuncSetAttribute((k_ext_side<0, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     CU_TRY(cudaFuncSetAttribute((k_ext_side<1, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<2, EXT_CORE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(cudaFuncSetAttribute(k_ext_side<2, EXT_CORE_P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2));
+    CU_TRY(cudaFuncSetAttribute((k_ext_side<2, EXT_CORE_P2, EXT_BD_LONG>), cudaFuncAttributeMaxDynamicSharedMemorySize, big_p2l));
     g_ext_attrs[dev] = true;
     return CSBWA_OK;
 }
@@ -111,6 +114,25 @@ extern "C" int csbwa_set_ext_coop_max(int max_tasks)
     if (max_tasks >= 0) g_ext_coop_max.store(max_tasks, std::memory_order_relaxed);
     return prev;
 }
+// Launch sequences of at most this many tasks run BOTH sides of a task in one thread (k_ext_side<2>, one phase instead of
+// two: ext_kernels.cuh ext_both_bin); larger ones keep the two passes, each sorted by its own side's length.
+// CSBWA_EXT_FUSED_MAX / csbwa_set_ext_fused_max; 0 = never.
+static std::atomic<int> g_ext_fused_max{-1};
+static int ext_fused_max()
+{
+    int v = g_ext_fused_max.load(std::memory_order_relaxed);
+    if (v < 0) {
+        v = env_int("CSBWA_EXT_FUSED_MAX", 65536, 0, 1 << 30);
+        g_ext_fused_max.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+extern "C" int csbwa_set_ext_fused_max(int max_tasks)
+{
+    const int prev = ext_fused_max();
+    if (max_tasks >= 0) g_ext_fused_max.store(max_tasks, std::memory_order_relaxed);
+    return prev;
+}
 static int ext_coop_lanes()      // lanes per task: 32 (default), 16 or 8
 {
     static const int g = [] { const int v = env_int("CSBWA_EXT_COOP_G", 32, 8, 32); return v == 8 || v == 16 ? v : 32; }();
@@ -119,7 +141,11 @@ static int ext_coop_lanes()      // lanes per task: 32 (default), 16 or 8
 
 // kernels one launch sequence of n tasks enqueues: the class path (3 preparation kernels + 7 classes x 2 sides) or the
 // one lane-group kernel of a small sequence (launch_extend decides by the same bound)
-static int ext_launches_for(int n) { return ext_core() == EXT_CORE_P2 && n <= ext_coop_max() ? 1 : kExtLaunches; }
+static int ext_launches_for(int n)
+{
+    if (ext_core() == EXT_CORE_P2 && n <= ext_coop_max()) return 1;
+    return n <= ext_fused_max() ? 3 + EXT_NCLS : kExtLaunches;
+}
 
 // resident blocks per SM for a block of bd threads using smem bytes of dynamic shared memory
 static int blocks_per_sm(int bd, size_t smem, int regs_per_thread)
@@ -137,9 +163,10 @@ template <int SIDE>
 static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch &sc, int16_t *d_out,
                             unsigned long long *d_cells, int n, int sms, cudaStream_t st_main, AuxSet *aux, int core)
 {
+    constexpr int LIST = SIDE == 2 ? 0 : SIDE;          // both-sides mode uses the job list / events of the left pass
     if (aux) {
-        cudaEventRecord(aux->fork[SIDE], st_main);
-        for (int a = 0; a < kAux; ++a) cudaStreamWaitEvent(aux->s[a], aux->fork[SIDE], 0);
+        cudaEventRecord(aux->fork[LIST], st_main);
+        for (int a = 0; a < kAux; ++a) cudaStreamWaitEvent(aux->s[a], aux->fork[LIST], 0);
     }
     for (int cls = 0; cls < EXT_NCLS; ++cls) {
         // classes 0 (generic) and 1 on the main stream, every other class on its own aux stream
@@ -148,7 +175,7 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
         if (cls == 0) {
             int grid = (n + EXT_BD - 1) / EXT_BD;
             if (grid > sms * 8) grid = sms * 8;
-            k_ext_side<SIDE, -1><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+            k_ext_side<SIDE, -1><<<grid, EXT_BD, 0, st>>>(d_in, cs, sc.hdr, sc.order[LIST], sc.left, sc.eh,
                                                            d_out, d_cells, cls, 0);
         } else if (core == EXT_CORE_P2) {
             // 8-byte {H2,E2} record + 2-byte selector per column pair per thread
@@ -160,10 +187,10 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
             const int cap_grid = sms * blocks_per_sm(bd, smem, 96);
             if (grid > cap_grid) grid = cap_grid;
             if (lng)
-                k_ext_side<SIDE, EXT_CORE_P2, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                k_ext_side<SIDE, EXT_CORE_P2, EXT_BD_LONG><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[LIST], sc.left, sc.eh,
                                                                                     d_out, d_cells, cls, npairs);
             else
-                k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+                k_ext_side<SIDE, EXT_CORE_P2><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[LIST], sc.left, sc.eh,
                                                                        d_out, d_cells, cls, npairs);
         } else {
             const int bd = cls <= 2 ? 64 : EXT_BD;
@@ -171,14 +198,14 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
             int grid = (n + bd - 1) / bd;
             const int cap_grid = sms * blocks_per_sm(bd, smem, 80);
             if (grid > cap_grid) grid = cap_grid;
-            k_ext_side<SIDE, EXT_CORE_U8><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[SIDE], sc.left, sc.eh,
+            k_ext_side<SIDE, EXT_CORE_U8><<<grid, bd, smem, st>>>(d_in, cs, sc.hdr, sc.order[LIST], sc.left, sc.eh,
                                                                    d_out, d_cells, cls, 0);
         }
     }
     if (aux) {
         for (int a = 0; a < kAux; ++a) {
-            cudaEventRecord(aux->join[SIDE][a], aux->s[a]);
-            cudaStreamWaitEvent(st_main, aux->join[SIDE][a], 0);
+            cudaEventRecord(aux->join[LIST][a], aux->s[a]);
+            cudaStreamWaitEvent(st_main, aux->join[LIST][a], 0);
         }
     }
 }
@@ -186,7 +213,7 @@ static void launch_ext_side(const uint8_t *d_in, const ExtCalls &cs, ExtScratch 
 // d_in: base of the input region; cs: the calls inside it; n: total tasks
 static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t *d_out,
                          unsigned long long *d_cells, void *d_scratch, int64_t scratch_bytes,
-                         cudaStream_t st, int dev, AuxSet *aux)
+                         cudaStream_t st, int dev, AuxSet *aux, unsigned long long *trace = nullptr)
 {
     if (n <= 0) return CSBWA_OK;
     const int64_t fixed = (int64_t)ext_scratch_fixed(n);
@@ -195,6 +222,7 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
     if (rc) return rc;
     ExtScratch sc = ext_carve(d_scratch, n);
     CU_TRY(cudaMemsetAsync(sc.hdr, 0, sizeof(ExtHdr), st));
+    if (trace) k_co_stamp<<<1, 1, 0, st>>>(trace, 0);
     const int tb = 256;
     int gb = (n + tb - 1) / tb;
     if (gb > dev_sms(dev) * 8) gb = dev_sms(dev) * 8;     // grid-stride kernels
@@ -212,14 +240,24 @@ static int launch_extend(const uint8_t *d_in, const ExtCalls &cs, int n, int16_t
         if (g == 8) k_ext_small<8><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
         else if (g == 16) k_ext_small<16><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
         else k_ext_small<32><<<grid, EXT_BD, smem, st>>>(d_in, cs, n, sc.hdr, sc.eh, eh_cap, o16, d_cells);
+        if (trace) { k_co_stamp<<<1, 1, 0, st>>>(trace, 1); k_co_stamp<<<1, 1, 0, st>>>(trace, 2); k_co_stamp<<<1, 1, 0, st>>>(trace, 3); }
         CU_TRY(cudaGetLastError());
         return CSBWA_OK;
     }
-    k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
+    const int both = n <= ext_fused_max() ? 1 : 0;
+    k_ext_hist<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core, both);
     k_ext_scan<<<1, EXT_SCAN_BD, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(d_in, cs, n, sc.hdr, sc.order[0], sc.order[1]);
-    launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, dev_sms(dev), st, aux, core);
-    launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, dev_sms(dev), st, aux, core);
+    if (trace) k_co_stamp<<<1, 1, 0, st>>>(trace, 1);
+    if (both) {
+        launch_ext_side<2>(d_in, cs, sc, d_out, d_cells, n, dev_sms(dev), st, aux, core);
+        if (trace) k_co_stamp<<<1, 1, 0, st>>>(trace, 2);
+    } else {
+        launch_ext_side<0>(d_in, cs, sc, d_out, d_cells, n, dev_sms(dev), st, aux, core);
+        if (trace) k_co_stamp<<<1, 1, 0, st>>>(trace, 2);
+        launch_ext_side<1>(d_in, cs, sc, d_out, d_cells, n, dev_sms(dev), st, aux, core);
+    }
+    if (trace) k_co_stamp<<<1, 1, 0, st>>>(trace, 3);
     CU_TRY(cudaGetLastError());
     return CSBWA_OK;
 }
@@ -311,7 +349,7 @@ extern "C" int csbwa_extend_profile_device(const void *d_in_base, const csbwa_ex
     const int tb = 256, gb = (n_tasks + tb - 1) / tb;
     CU_TRY(cudaEventRecord(ev[0], st));
     const int core = ext_core();
-    k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core);
+    k_ext_hist<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, (unsigned long long)(scratch_bytes - fixed), core, 0);
     k_ext_scan<<<1, EXT_SCAN_BD, 0, st>>>(sc.hdr);
     k_ext_scatter<<<gb, tb, 0, st>>>(in, cs, n_tasks, sc.hdr, sc.order[0], sc.order[1]);
     CU_TRY(cudaEventRecord(ev[1], st));
@@ -367,6 +405,7 @@ struct CudaCoExec {
         cudaGraphExec_t graph[kGraphVariants] = {nullptr};
         int graph_core[kGraphVariants] = {0};
         int graph_coop[kGraphVariants] = {0};          // ext_coop_max() the graph was captured under
+        int graph_fused[kGraphVariants] = {0};         // ext_fused_max() likewise
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // non-graph mode only: gather | launch sequence | scatter
         int polls = 0;
         int launches = 0;                                // kernels of the group in flight (stats)
@@ -396,6 +435,7 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
+    bool trace = false;         // CSBWA_CO_TRACE=1: device timestamps between the phases (k_co_stamp), printed at shutdown
     int coop_busy = 2;          // CSBWA_EXT_COOP_BUSY: a small group takes the lane-group kernel while at most this many others run
     // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma (default): one cudaMemcpyAsync per call and direction around
     // the graph -- the copy engines move one group's bytes while the SMs run the kernels of the others.  sm: gather /
@@ -418,6 +458,7 @@ struct CudaCoExec {
         e = getenv("CSBWA_CO_ONE_GRAPH");
         one_graph = e && e[0] == '1';
         coop_busy = env_int("CSBWA_EXT_COOP_BUSY", 2, 0, 64);
+        trace = env_int("CSBWA_CO_TRACE", 0, 0, 1) != 0;
         e = getenv("CSBWA_CO_COPY");
         dma = !(e && e[0] == 's');
         CU_TRY(cudaSetDevice(dev));
@@ -453,6 +494,18 @@ struct CudaCoExec {
     void destroy()
     {
         cudaSetDevice(dev);
+        if (trace) {
+            unsigned long long sum[4] = {0, 0, 0, 0};
+            for (auto &s : slots) {
+                unsigned long long t[12];
+                if (s.st) cudaStreamSynchronize(s.st);
+                if (s.d_count && cudaMemcpy(t, s.d_count + 16, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess)
+                    for (int i = 0; i < 4; ++i) sum[i] += t[8 + i];
+            }
+            if (sum[3])
+                fprintf(stderr, "[csbwa coalescer] device phases per group us: prepare %.1f left %.1f right %.1f (%llu groups)\n",
+                        sum[0] / 1e3 / sum[3], sum[1] / 1e3 / sum[3], sum[2] / 1e3 / sum[3], sum[3]);
+        }
         for (auto &s : slots) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
             for (auto &g : s.graph) if (g) cudaGraphExecDestroy(g);
@@ -490,7 +543,7 @@ struct CudaCoExec {
         cs.dyn = (const int32_t *)(s.d_in + hdr_off);
         memset(&cs.single, 0, sizeof(ExtCall));
         int rc = launch_extend(s.d_in, cs, dyn_cap, (int16_t *)(s.d_out + kTrailer), (unsigned long long *)s.d_out, s.d_scratch,
-                               (int64_t)scratch_cap, s.st, dev, &s.aux);
+                               (int64_t)scratch_cap, s.st, dev, &s.aux, trace ? (unsigned long long *)(s.d_count + 16) : nullptr);
         if (rc) return rc;
         if (dma) k_co_finish<<<1, 32, 0, s.st>>>(s.d_in, hdr_off, &((const ExtHdr *)s.d_scratch)->err, ((const ExtHdr *)s.d_scratch)->bad_call_bits, (CoTrailer *)s.d_out);
         if (timed) CU_TRY(cudaEventRecord(s.ev[2], s.st));
@@ -516,6 +569,7 @@ struct CudaCoExec {
         if (e != cudaSuccess) { s.graph[v] = nullptr; return fail(CSBWA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
         s.graph_core[v] = ext_core();
         s.graph_coop[v] = ext_coop_max();
+        s.graph_fused[v] = ext_fused_max();
         return CSBWA_OK;
     }
 
@@ -540,7 +594,7 @@ struct CudaCoExec {
         CU_TRY(cudaSetDevice(dev));
         const int v = one_graph ? kGraphVariants - 1 : graph_variant(n_tasks, others);
         s.launches = ext_launches_for(variant_cap(v));
-        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core() || s.graph_coop[v] != ext_coop_max())) {
+        if (use_graph && (!s.graph[v] || s.graph_core[v] != ext_core() || s.graph_coop[v] != ext_coop_max() || s.graph_fused[v] != ext_fused_max())) {
             int rc = build_graph(s, v);
             if (rc) return rc;
         }

@@ -62,7 +62,7 @@ CSW_HD int ext_locate(const ExtCalls &cs, int g)
 // Jobs are ordered by query length first (longest first, shared-memory class) and by h0 inside a length
 // bucket: the band of row i spans about [(i - h0) / 2, 2i + h0], so lanes with the same (qlen, h0) run
 // rows of the same width -- a warp's row costs the width of its widest lane.
-constexpr int EXT_NBIN = 2 + 112 * 32;
+constexpr int EXT_NBIN = 2 + 64 * 64;   // >= 2 + 112 * 32 of the per-side key; the both-sides key below needs 2 + 4096
 constexpr int EXT_NCLS = 7;            // 0: generic, then fast classes by column capacity: 256, 192, 128, 96, 64, 32
 // extension cores (csbwa_set_ext_mode): which fast core serves the eligible sides
 constexpr int EXT_CORE_U8 = 0;         // one column per step, u8 scores (ext_core.cuh sw_extend_u8)
@@ -76,7 +76,7 @@ struct ExtHdr {
     int32_t n_tasks;
     int32_t err;
     int32_t core;                      // EXT_CORE_*
-    int32_t pad_;
+    int32_t both;                      // 1: one job per task (k_ext_side<2>), job list and cursors of side 0
     uint32_t bad_call_bits[8];         // bit c: call c (< 256) carried a record that points outside its buffer
     uint32_t hist[2][EXT_NBIN];
     uint32_t base[2][EXT_NBIN];        // start of each bin in the descending order
@@ -148,6 +148,27 @@ __host__ __device__ inline int ext_class_cap(int cls)
     return cls == 1 ? 256 : (cls == 2 ? 192 : (cls == 3 ? 128 : (cls == 4 ? 96 : (cls == 5 ? 64 : 32))));
 }
 
+// ---- both-sides mode (k_ext_side<2>): ONE job per task, the thread runs the left side, then the right side, then writes
+// the reply.  A read has only so many bases: a long left side means a short right side, so the longest job of the fused
+// pass is about as long as the longest job of ONE of the two separate passes, and a launch sequence's critical path
+// is one phase instead of two (measured on the device, 4096-read calls, 64 callers: left 315 us + right 326 us per
+// group of the two-pass sequence).  Lanes of a warp must agree on BOTH lengths: the sort key is 2-D,
+//   1 + (max(lq, rq) / 4) * 64 + (the long side is the right one) * 32 + min(lq, rq) / 8
+// descending = longest dominant side first (longest-processing-time order); the seed score h0 follows from the two
+// lengths on reads of one length.  Shared-memory class by max(lq, rq).  0 = nothing to extend, EXT_NBIN - 1 = generic.
+CSW_HD int ext_both_bin(int kind_l, int kind_r, int lq, int rq)
+{
+    if (kind_l == 256 || kind_r == 256) return EXT_NBIN - 1;
+    if (kind_l == 0 && kind_r == 0) return 0;
+    const int mx = lq > rq ? lq : rq, mn = lq > rq ? rq : lq;
+    return 1 + ((mx >> 2) << 6) + (rq > lq ? 32 : 0) + (mn >> 3 > 31 ? 31 : mn >> 3);
+}
+CSW_HD int ext_both_class_top_bin(int cls)
+{
+    const int qmax = cls == 1 ? 255 : (cls == 2 ? 191 : (cls == 3 ? 127 : (cls == 4 ? 95 : (cls == 5 ? 63 : 31))));
+    return 1 + ((qmax >> 2) << 6) + 63;
+}
+
 // parse the 32-byte common header into SwOpt (MemChainToAlignBatched.scala:78-85)
 CSW_HD void ext_parse_header(const uint8_t *in, SwOpt &o)
 {
@@ -178,7 +199,7 @@ CSW_HD int ext_side_bin(const SwOpt &o, int qlen, int h0, int core = EXT_CORE_U8
 }
 
 __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n, ExtHdr *hdr,
-                           unsigned long long eh_cap, int core)
+                           unsigned long long eh_cap, int core, int both)
 {
     __shared__ uint32_t sh[2][EXT_NBIN];
     __shared__ SwOpt sopt;
@@ -188,7 +209,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
         const uint8_t *in0 = base + ext_call(cs, 0).in_off;
         ext_parse_header(in0, sopt);
         if (blockIdx.x == 0) {
-            hdr->opt = sopt; hdr->n_tasks = n; hdr->eh_cap = eh_cap; hdr->core = core;
+            hdr->opt = sopt; hdr->n_tasks = n; hdr->eh_cap = eh_cap; hdr->core = core; hdr->both = both;
             // coalesced calls must carry the same options (header bytes other than taskNum)
             for (int c = 1; c < cs.n_calls; ++c) {
                 const uint8_t *inc = base + ext_call(cs, c).in_off;
@@ -215,6 +236,7 @@ __global__ void k_ext_hist(const uint8_t *__restrict__ base, ExtCalls cs, int n,
             br = ext_side_bin(sopt, t.rq, h0r, core);
             if (t.lq > 0 && bl == 256 && br != 0) br = 256;   // keep score bounds trivially safe
         }
+        if (both) { atomicAdd(&sh[0][ext_both_bin(bl, br, t.lq, t.rq)], 1u); continue; }     // one job per task
         if (bl) atomicAdd(&sh[0][ext_sort_bin(bl, t.lq, t.h0)], 1u);
         atomicAdd(&sh[1][ext_sort_bin(br, t.rq, t.lq > 0 ? t.h0 + t.lq * sopt.max_mat : t.reg_score)], 1u);   // every task has a right/finalise job
     }
@@ -268,7 +290,8 @@ __global__ void __launch_bounds__(EXT_SCAN_BD) k_ext_scan(ExtHdr *hdr)
         for (int w = 0; w < WARPS; ++w) total += s_warp[side][w];
         // class 0 = the generic bin (first in the descending order), class k >= 1 starts at its top bin
         hdr->cls_beg[side][0] = 0;
-        for (int c = 1; c < EXT_NCLS; ++c) hdr->cls_beg[side][c] = hdr->base[side][ext_class_top_bin(c)];
+        for (int c = 1; c < EXT_NCLS; ++c)
+            hdr->cls_beg[side][c] = hdr->base[side][hdr->both ? ext_both_class_top_bin(c) : ext_class_top_bin(c)];
         hdr->cls_beg[side][EXT_NCLS] = total;
         for (int c = 0; c < EXT_NCLS; ++c) hdr->work[side][c] = 0;
     }
@@ -288,6 +311,11 @@ __global__ void k_ext_scatter(const uint8_t *__restrict__ base, ExtCalls cs, int
             const int h0r = t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score;
             br = ext_side_bin(o, t.rq, h0r, hdr->core);
             if (t.lq > 0 && bl == 256 && br != 0) br = 256;
+        }
+        if (hdr->both) {
+            const int sb = ext_both_bin(bl, br, t.lq, t.rq);
+            order_l[hdr->base[0][sb] + atomicAdd(&hdr->cursor[0][sb], 1u)] = (uint32_t)k;
+            continue;
         }
         const int sl = ext_sort_bin(bl, t.lq, t.h0);
         const int sr = ext_sort_bin(br, t.rq, t.lq > 0 ? t.h0 + t.lq * o.max_mat : t.reg_score);
@@ -345,7 +373,8 @@ CSW_HD void ext_run_side_p2(const SwOpt &o, const uint32_t *words, int q_nib, in
     out.cells = cells;
 }
 
-// SIDE 0 = left, 1 = right (+ finalise).  cls selects the job range.
+// SIDE 0 = left, 1 = right (+ finalise), 2 = both sides of the task by the same thread (+ finalise; job list of the
+// both-sides sort, ext_both_bin).  cls selects the job range.
 // CORE: -1 generic (int32 rows in global scratch), EXT_CORE_U8, EXT_CORE_P2 (shared memory).
 // npairs: column pairs per thread of the P2 layout ({H2,E2} records first, then the selectors).
 // BD: threads per block == element stride of the shared-memory rows (compile time for the p2 core).
@@ -364,7 +393,8 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     if (threadIdx.x == 0) s_opt = hdr->opt;
     __syncthreads();
     const SwOpt &o = s_opt;
-    const uint32_t jbeg = hdr->cls_beg[SIDE][cls], jend = hdr->cls_beg[SIDE][cls + 1];
+    constexpr int LIST = SIDE == 2 ? 0 : SIDE;                  // both-sides mode: one job list, kept where the left one is
+    const uint32_t jbeg = hdr->cls_beg[LIST][cls], jend = hdr->cls_beg[LIST][cls + 1];
     const int lane = threadIdx.x & 31;
     const int stride = (int)blockDim.x;
     uint32_t *col = (uint32_t *)smem4 + threadIdx.x;            // U8: column j at col[j * stride]
@@ -373,7 +403,7 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&hdr->work[SIDE][cls], 32u);
+        if (lane == 0) chunk = atomicAdd(&hdr->work[LIST][cls], 32u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0) + jbeg;
         if (chunk >= jend) break;
         const uint32_t job = chunk + lane;
@@ -400,7 +430,7 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
             SideRes L, R;
             L.score = 0; L.qle = L.tle = L.gtle = L.gscore = 0; L.aw = (int16_t)o.w; L.cells = 0;
             R = L;
-            if (SIDE == 0) {
+            if (SIDE == 0 || SIDE == 2) {
                 if (t.lq > 0) {      // (0 only after a validation / scratch failure, already reported)
                     if (CORE == EXT_CORE_P2)
                         ext_run_side_p2<BD>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0, t.reg_score,
@@ -409,10 +439,11 @@ k_ext_side(const uint8_t *__restrict__ base, ExtCalls cs, ExtHdr *hdr, const uin
                         ext_run_side<FAST>(o, words, seg_lq(t), t.lq, seg_lr(t), t.lr, o.pen_clip5, t.h0,
                                            t.reg_score, col, stride, H, E, L);
                 }
-                left[k] = L;
+                if (SIDE == 0) left[k] = L;
                 my_cells += (unsigned)L.cells;
-            } else {
-                if (t.lq > 0) L = left[k];
+            }
+            if (SIDE != 0) {
+                if (SIDE == 1 && t.lq > 0) L = left[k];
                 if (t.rq > 0) {
                     const int sc0 = t.lq > 0 ? (int)L.score : t.reg_score;
                     if (CORE == EXT_CORE_P2)

@@ -257,6 +257,11 @@ int csbwa_set_ext_mode(int mode);
  * -- same results, a third of the latency, 2.7x the instructions: for groups that leave the device mostly idle).
  * 0 = never; default 8192 (env CSBWA_EXT_COOP_MAX).  Returns the previous bound; a negative argument only queries. */
 int csbwa_set_ext_coop_max(int max_tasks);
+/* Launch sequences of at most max_tasks tasks (and above the bound of csbwa_set_ext_coop_max) run both sides of a task in
+ * ONE thread -- one phase whose longest job is about as long as the longest job of either separate pass, because a
+ * long left side means a short right side -- instead of a left pass followed by a right pass.  Same results.
+ * 0 = never; default 65536 (env CSBWA_EXT_FUSED_MAX).  Returns the previous bound; a negative argument only queries. */
+int csbwa_set_ext_fused_max(int max_tasks);
 int csbwa_align2_launches_per_call(void);
 
 /* ---- host-side helper: the caller's packer, for C/C++ hosts --------------

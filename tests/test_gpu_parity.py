@@ -26,7 +26,10 @@ def _ext_gpu(pkg, wire, device=-1):
     return pkg.jni.SWExtendFPGAJNI(device).swExtendFPGAJNI(10 * n, wire)
 
 
-ALWAYS = 1 << 30      # csbwa_set_ext_coop_max bound that sends every launch to the lane-group kernels
+ALWAYS = 1 << 30      # csbwa_set_ext_coop_max / _fused_max bound that sends every launch down that path
+# (extension core, lane-group bound, both-sides-per-thread bound): the two-pass class kernels, the both-sides class
+# kernels, the lane-group kernel -- for the column-pair core -- and the two class paths of the one-column u8 core
+EXT_PATHS = ((1, 0, 0), (1, 0, ALWAYS), (1, ALWAYS, 0), (0, 0, 0), (0, 0, ALWAYS))
 
 
 def _check_ext(pkg, oracle, wire):
@@ -37,31 +40,36 @@ def _check_ext(pkg, oracle, wire):
     L = pkg.lib()
     prev = L.csbwa_set_ext_mode(-1)
     prev_coop = L.csbwa_set_ext_coop_max(-1)
+    prev_fused = L.csbwa_set_ext_fused_max(-1)
     try:
-        for mode, coop in ((1, 0), (1, ALWAYS), (0, 0)):
+        for mode, coop, fused in EXT_PATHS:
             L.csbwa_set_ext_mode(mode)
             L.csbwa_set_ext_coop_max(coop)
+            L.csbwa_set_ext_fused_max(fused)
             before = pkg.stats()["ext_cells"]
             got = _ext_gpu(pkg, wire)
             bad = np.flatnonzero((got.reshape(-1, 10) != ref.reshape(-1, 10)).any(axis=1))
-            assert len(bad) == 0, (mode, coop, len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
+            assert len(bad) == 0, (mode, coop, fused, len(bad), bad[:5], got.reshape(-1, 10)[bad[:3]], ref.reshape(-1, 10)[bad[:3]])
             assert pkg.stats()["ext_cells"] - before == int(rcells.sum())      # exact DP cell count
     finally:
         L.csbwa_set_ext_mode(prev)
         L.csbwa_set_ext_coop_max(prev_coop)
+        L.csbwa_set_ext_fused_max(prev_fused)
     return ref
 
 
 def test_ext_golden(pkg, oracle, gpu):
     g = np.load(os.path.join(GOLD, "ext_golden.npz"))
     L = pkg.lib()
-    prev_coop = L.csbwa_set_ext_coop_max(-1)
-    for mode, coop in ((0, 0), (1, 0), (1, ALWAYS)):
+    prev_coop, prev_fused = L.csbwa_set_ext_coop_max(-1), L.csbwa_set_ext_fused_max(-1)
+    for mode, coop, fused in EXT_PATHS:
         L.csbwa_set_ext_mode(mode)
         L.csbwa_set_ext_coop_max(coop)
+        L.csbwa_set_ext_fused_max(fused)
         got = _ext_gpu(pkg, g["wire"])
-        assert np.array_equal(got, g["reply"]), (mode, coop)
+        assert np.array_equal(got, g["reply"]), (mode, coop, fused)
     L.csbwa_set_ext_coop_max(prev_coop)
+    L.csbwa_set_ext_fused_max(prev_fused)
 
 
 def test_ext_random_and_adversarial(pkg, oracle, gpu):
@@ -408,6 +416,7 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
                                  {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_COPY": "sm"},
                                  {"CSBWA_CO_COPY": "dma", "CSBWA_CO_SLOTS": "32"},
                                  {"CSBWA_EXT_COOP_MAX": "0"},
+                                 {"CSBWA_EXT_COOP_MAX": "0", "CSBWA_EXT_FUSED_MAX": "0"},
                                  {"CSBWA_EXT_COOP_MAX": "100000", "CSBWA_EXT_COOP_G": "16"},
                                  {"CSBWA_EXT_COOP_MAX": "20000", "CSBWA_EXT_COOP_G": "32", "CSBWA_CO_COPY": "sm"}])
 def test_coalescer_knobs_subprocess(pkg, oracle, gpu, env):

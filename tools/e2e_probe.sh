@@ -3,7 +3,7 @@ export CSBWA_CO_TIMING=1
 while read -r t p c extra; do
 [ -z "$t" ] && continue
 echo "== threads $t pinned $p cpus $c $extra"
-env $extra timeout 300 python tools/e2e_probe.py --pairs 250000 --threads $t --pinned $p --cpus $c --repeat ${PROBE_REPEAT:-60} 2>&1 | grep -v Warning | tail -2
+env $extra timeout 300 python tools/e2e_probe.py --pairs 250000 --threads $t --pinned $p --cpus $c --repeat ${PROBE_REPEAT:-60} 2>&1 | grep -v Warning | tail -4
 done <<CFG
 ${PROBE_CFGS:-64 1 0}
 CFG
