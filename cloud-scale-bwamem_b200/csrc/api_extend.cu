@@ -409,6 +409,8 @@ struct CudaCoExec {
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // non-graph mode only: gather | launch sequence | scatter
         int polls = 0;
         int launches = 0;                                // kernels of the group in flight (stats)
+        std::vector<void *> cp_dst, cp_src;              // operands of the group's batched copies
+        std::vector<size_t> cp_len;
         double t_launch = 0;
         size_t span = 0;
         std::string detail;
@@ -435,6 +437,7 @@ struct CudaCoExec {
     int max_tasks = 0;
     bool use_graph = true;
     bool one_graph = false;     // CSBWA_CO_ONE_GRAPH=1: always the full-size graph (experiments)
+    bool batch_copy = true;     // CSBWA_CO_BATCHCOPY=0: one cudaMemcpyAsync per call and direction instead of one batch per direction
     bool trace = false;         // CSBWA_CO_TRACE=1: device timestamps between the phases (k_co_stamp), printed at shutdown
     int coop_busy = 2;          // CSBWA_EXT_COOP_BUSY: a small group takes the lane-group kernel while at most this many others run
     // How a group's bytes travel (CSBWA_CO_COPY=dma|sm).  dma (default): one cudaMemcpyAsync per call and direction around
@@ -459,6 +462,7 @@ struct CudaCoExec {
         one_graph = e && e[0] == '1';
         coop_busy = env_int("CSBWA_EXT_COOP_BUSY", 2, 0, 64);
         trace = env_int("CSBWA_CO_TRACE", 0, 0, 1) != 0;
+        batch_copy = env_int("CSBWA_CO_BATCHCOPY", 1, 0, 1) != 0;
         e = getenv("CSBWA_CO_COPY");
         dma = !(e && e[0] == 's');
         CU_TRY(cudaSetDevice(dev));
@@ -495,16 +499,16 @@ struct CudaCoExec {
     {
         cudaSetDevice(dev);
         if (trace) {
-            unsigned long long sum[4] = {0, 0, 0, 0};
+            unsigned long long sum[5] = {0, 0, 0, 0, 0};
             for (auto &s : slots) {
-                unsigned long long t[12];
+                unsigned long long t[13];
                 if (s.st) cudaStreamSynchronize(s.st);
                 if (s.d_count && cudaMemcpy(t, s.d_count + 16, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess)
-                    for (int i = 0; i < 4; ++i) sum[i] += t[8 + i];
+                    for (int i = 0; i < 5; ++i) sum[i] += t[8 + i];
             }
             if (sum[3])
-                fprintf(stderr, "[csbwa coalescer] device phases per group us: prepare %.1f left %.1f right %.1f (%llu groups)\n",
-                        sum[0] / 1e3 / sum[3], sum[1] / 1e3 / sum[3], sum[2] / 1e3 / sum[3], sum[3]);
+                fprintf(stderr, "[csbwa coalescer] device phases per group us: copies in %.1f prepare %.1f left %.1f right %.1f (%llu groups)\n",
+                        sum[4] / 1e3 / sum[3], sum[0] / 1e3 / sum[3], sum[1] / 1e3 / sum[3], sum[2] / 1e3 / sum[3], sum[3]);
         }
         for (auto &s : slots) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
@@ -604,12 +608,26 @@ struct CudaCoExec {
         const CoCall *tab = (const CoCall *)s.h_in;
         const int n_calls = ((const int32_t *)(s.h_in + hdr_off))[0];
         const CoExt *ext = (const CoExt *)(s.h_in + ext_off);
+        if (trace) k_co_stamp<<<1, 1, 0, s.st>>>((unsigned long long *)(s.d_count + 16), 4);
         if (dma) {
             if (!use_graph) CU_TRY(cudaEventRecord(s.ev[0], s.st));
-            CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, table_bytes, cudaMemcpyHostToDevice, s.st));
-            for (int c = 0; c < n_calls; ++c)
-                CU_TRY(cudaMemcpyAsync(s.d_in + tab[c].in_off, (const void *)(uintptr_t)ext[c].src, (size_t)tab[c].in_bytes,
-                                       cudaMemcpyDefault, s.st));
+            bool batched = false;
+            if (batch_copy && n_calls > 1) {               // ONE driver call for the tables and every call's bytes
+                s.cp_dst.clear(); s.cp_src.clear(); s.cp_len.clear();
+                s.cp_dst.push_back(s.d_in); s.cp_src.push_back(s.h_in); s.cp_len.push_back(table_bytes);
+                for (int c = 0; c < n_calls; ++c) {
+                    s.cp_dst.push_back(s.d_in + tab[c].in_off);
+                    s.cp_src.push_back((void *)(uintptr_t)ext[c].src);
+                    s.cp_len.push_back((size_t)tab[c].in_bytes);
+                }
+                batched = copy_batch(s) == CSBWA_OK;
+            }
+            if (!batched) {
+                CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, table_bytes, cudaMemcpyHostToDevice, s.st));
+                for (int c = 0; c < n_calls; ++c)
+                    CU_TRY(cudaMemcpyAsync(s.d_in + tab[c].in_off, (const void *)(uintptr_t)ext[c].src, (size_t)tab[c].in_bytes,
+                                           cudaMemcpyDefault, s.st));
+            }
         }
         if (use_graph) CU_TRY(cudaGraphLaunch(s.graph[v], s.st));
         else {
@@ -617,13 +635,40 @@ struct CudaCoExec {
             if (rc) return rc;
         }
         if (dma) {
-            for (int c = 0; c < n_calls; ++c)
-                CU_TRY(cudaMemcpyAsync((void *)(uintptr_t)ext[c].dst, s.d_out + kTrailer + (size_t)tab[c].out_off * 2,
-                                       (size_t)tab[c].n_tasks * 20, cudaMemcpyDefault, s.st));
-            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, kTrailer, cudaMemcpyDeviceToHost, s.st));
+            bool batched = false;
+            if (batch_copy && n_calls > 1) {
+                s.cp_dst.clear(); s.cp_src.clear(); s.cp_len.clear();
+                for (int c = 0; c < n_calls; ++c) {
+                    if (tab[c].n_tasks <= 0) continue;
+                    s.cp_dst.push_back((void *)(uintptr_t)ext[c].dst);
+                    s.cp_src.push_back(s.d_out + kTrailer + (size_t)tab[c].out_off * 2);
+                    s.cp_len.push_back((size_t)tab[c].n_tasks * 20);
+                }
+                batched = s.cp_dst.empty() || copy_batch(s) == CSBWA_OK;
+            }
+            if (!batched)
+                for (int c = 0; c < n_calls; ++c)
+                    CU_TRY(cudaMemcpyAsync((void *)(uintptr_t)ext[c].dst, s.d_out + kTrailer + (size_t)tab[c].out_off * 2,
+                                           (size_t)tab[c].n_tasks * 20, cudaMemcpyDefault, s.st));
+            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, kTrailer, cudaMemcpyDeviceToHost, s.st));   // after the replies: stream order
             if (!use_graph) CU_TRY(cudaEventRecord(s.ev[3], s.st));
         }
         return CSBWA_OK;
+    }
+    // the copies listed in s.cp_* as one cudaMemcpyBatchAsync (CUDA 12.8+); on any error the caller falls back to one
+    // cudaMemcpyAsync per copy and the batch path is switched off for good
+    int copy_batch(Slot &s)
+    {
+        cudaMemcpyAttributes at;
+        memset(&at, 0, sizeof at);
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t idx0 = 0, fail = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(s.cp_dst.data(), s.cp_src.data(), s.cp_len.data(), s.cp_dst.size(), &at, &idx0, 1,
+                                                   &fail, s.st);
+        if (e == cudaSuccess) return CSBWA_OK;
+        (void)cudaGetLastError();
+        batch_copy = false;
+        return CSBWA_E_CUDA;
     }
     // 0 = running, 1 = finished, < 0 = failed.  The fast path is one load from pinned memory; the stream is
     // queried now and then so that a faulted kernel cannot leave the callers waiting for ever.

@@ -128,13 +128,14 @@ static __global__ void k_co_finish(const uint8_t *__restrict__ d_in, size_t hdr_
 }
 
 // CSBWA_CO_TRACE=1 (diagnosis): device timestamps between the phases of a group's launch sequence, accumulated per
-// staging slot -- tr[0..3] stamps, tr[8..11] sums {prepare, left, right} in ns and the group count
+// staging slot -- tr[0..3] stamps (tr[4]: before the group's host-to-device copies), tr[8..12] sums {prepare, left, right}
+// in ns, the group count, and the time from tr[4] to the first kernel (copies in + graph launch)
 static __global__ void k_co_stamp(unsigned long long *tr, int idx)
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     tr[idx] = t;
-    if (idx == 3) { tr[8] += tr[1] - tr[0]; tr[9] += tr[2] - tr[1]; tr[10] += tr[3] - tr[2]; tr[11] += 1; }
+    if (idx == 3) { tr[8] += tr[1] - tr[0]; tr[9] += tr[2] - tr[1]; tr[10] += tr[3] - tr[2]; tr[11] += 1; tr[12] += tr[0] - tr[4]; }
 }
 
 } // namespace csw

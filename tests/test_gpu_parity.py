@@ -416,6 +416,7 @@ def test_direct_path_subprocess(pkg, oracle, gpu):
                                  {"CSBWA_CO_GRAPH": "0", "CSBWA_CO_COPY": "sm"},
                                  {"CSBWA_CO_COPY": "dma", "CSBWA_CO_SLOTS": "32"},
                                  {"CSBWA_EXT_COOP_MAX": "0"},
+                                 {"CSBWA_CO_BATCHCOPY": "0"},
                                  {"CSBWA_EXT_COOP_MAX": "0", "CSBWA_EXT_FUSED_MAX": "0"},
                                  {"CSBWA_EXT_COOP_MAX": "100000", "CSBWA_EXT_COOP_G": "16"},
                                  {"CSBWA_EXT_COOP_MAX": "20000", "CSBWA_EXT_COOP_G": "32", "CSBWA_CO_COPY": "sm"}])
