@@ -153,20 +153,24 @@ __host__ __device__ inline int ext_class_cap(int cls)
 // pass is about as long as the longest job of ONE of the two separate passes, and a launch sequence's critical path
 // is one phase instead of two (measured on the device, 4096-read calls, 64 callers: left 315 us + right 326 us per
 // group of the two-pass sequence).  Lanes of a warp must agree on BOTH lengths: the sort key is 2-D,
-//   1 + (max(lq, rq) / 4) * 64 + (the long side is the right one) * 32 + min(lq, rq) / 8
+//   1 + (max(lq, rq) / 8) * 128 + (the long side is the right one) * 64 + min(lq, rq) / 4
 // descending = longest dominant side first (longest-processing-time order); the seed score h0 follows from the two
-// lengths on reads of one length.  Shared-memory class by max(lq, rq).  0 = nothing to extend, EXT_NBIN - 1 = generic.
+// lengths on reads of one length.  Resolution chosen on the job lists of 5-call groups with a lockstep cost model
+// (lane utilisation max/4 + min/8 0.73, this key 0.78) and confirmed on the device (end to end, 64 callers:
+// 1045 -> 1085 GCUPS).  A 13-bit key that also buckets the target rows (model 0.81; a side runs to the end of its
+// target segment, and segments of equal query length differ by up to 130 rows) shortened the side kernels by 2 % and
+// lengthened histogram + scan by 30 us per group (8194 bins): 1058 GCUPS end to end, not kept.  Shared-memory class by max(lq, rq).  0 = nothing to extend, EXT_NBIN - 1 = generic.
 CSW_HD int ext_both_bin(int kind_l, int kind_r, int lq, int rq)
 {
     if (kind_l == 256 || kind_r == 256) return EXT_NBIN - 1;
     if (kind_l == 0 && kind_r == 0) return 0;
     const int mx = lq > rq ? lq : rq, mn = lq > rq ? rq : lq;
-    return 1 + ((mx >> 2) << 6) + (rq > lq ? 32 : 0) + (mn >> 3 > 31 ? 31 : mn >> 3);
+    return 1 + ((mx >> 3) << 7) + (rq > lq ? 64 : 0) + (mn >> 2 > 63 ? 63 : mn >> 2);
 }
 CSW_HD int ext_both_class_top_bin(int cls)
 {
     const int qmax = cls == 1 ? 255 : (cls == 2 ? 191 : (cls == 3 ? 127 : (cls == 4 ? 95 : (cls == 5 ? 63 : 31))));
-    return 1 + ((qmax >> 2) << 6) + 63;
+    return 1 + ((qmax >> 3) << 7) + 127;
 }
 
 // parse the 32-byte common header into SwOpt (MemChainToAlignBatched.scala:78-85)
