@@ -159,7 +159,9 @@ __host__ __device__ inline int ext_class_cap(int cls)
 // (lane utilisation max/4 + min/8 0.73, this key 0.78) and confirmed on the device (end to end, 64 callers:
 // 1045 -> 1085 GCUPS).  A 13-bit key that also buckets the target rows (model 0.81; a side runs to the end of its
 // target segment, and segments of equal query length differ by up to 130 rows) shortened the side kernels by 2 % and
-// lengthened histogram + scan by 30 us per group (8194 bins): 1058 GCUPS end to end, not kept.  Shared-memory class by max(lq, rq).  0 = nothing to extend, EXT_NBIN - 1 = generic.
+// lengthened histogram + scan by 25-30 us per group (8194 bins, also with a one-list histogram and a partial memset):
+// 1058-1070 GCUPS end to end; on 1M-pair resident launch sequences the both-sides pass with it reaches 1298 GCUPS
+// against 1330 of the two passes.  Not kept.  Shared-memory class by max(lq, rq).  0 = nothing to extend, EXT_NBIN - 1 = generic.
 CSW_HD int ext_both_bin(int kind_l, int kind_r, int lq, int rq)
 {
     if (kind_l == 256 || kind_r == 256) return EXT_NBIN - 1;
