@@ -354,3 +354,23 @@ extern "C" int emu_global_batch(const GlbJob *jobs, int n, const uint8_t *seqs, 
     if (n_p2) *n_p2 = np2 | (nring << 16);
     return 0;
 }
+
+// both-sides sort key (csrc/ext_kernels.cuh ext_both_bin) and the class a bin falls into by the class boundaries
+// k_ext_scan derives from ext_both_class_top_bin: tests check that no job is sorted into a class whose shared-memory
+// rows are too short for it
+extern "C" void emu_both_bins(const int32_t *lq, const int32_t *rq, int n, int32_t *bin, int32_t *cls)
+{
+    for (int k = 0; k < n; ++k) {
+        const int kl = lq[k] > 0 ? lq[k] : 0, kr = rq[k] > 0 ? rq[k] : 0;       // fast sides: kind = length
+        const int b = ext_both_bin(kl, kr, lq[k], rq[k]);
+        bin[k] = b;
+        int c = 0;                                       // descending order: class c holds bins (top(c+1), top(c)]
+        if (b != EXT_NBIN - 1) {
+            c = EXT_NCLS - 1;
+            for (int q = 1; q < EXT_NCLS; ++q)
+                if (b <= ext_both_class_top_bin(q) && (q == EXT_NCLS - 1 || b > ext_both_class_top_bin(q + 1))) { c = q; break; }
+        }
+        cls[k] = c;
+    }
+}
+extern "C" int emu_class_cap(int cls) { return ext_class_cap(cls); }
