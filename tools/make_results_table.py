@@ -39,7 +39,8 @@ def main():
     full = load("r2_bench_full.json")
     refarm = load("r2_bench_reference_arm.json")
     rows.append(ext_row("**C2** extension (1M x 2, 151 bp, 4096 reads/call)", full, refarm))
-    rows.append(ext_row("C2 extension, 8 GPUs (1M x 2 per GPU, weak)", load("r2_bench_8gpu.json")))
+    for n in (2, 4, 8):
+        rows.append(ext_row("C2 extension, %d GPUs (1M x 2 per GPU, weak)" % n, load("r2_bench_%dgpu.json" % n)))
     rows.append(ext_row("C1 extension (101 bp)", load("r2_bench_C1.json")))
     rows.append(ext_row("C5 extension (250 bp, 5 % error)", load("r2_bench_C5.json")))
     out = ["| config | GPUs | kernel GCUPS (resident) | fraction of int roofline (ALU pipe / dual issue) | pairs/s resident | end to end, host buffers (GCUPS) | CPU arm | parity |",
