@@ -48,10 +48,11 @@ def main():
     out += [r for r in rows if r]
     ms = load("r2_matesw_bench.jsonl") or []
     big = load("r2_matesw_C3_1M.json")
-    for m in ms + ([big] if big else []):
+    two = load("r2_matesw_C3_2gpu.json")
+    for m in ms + ([big] if big else []) + ([two] if two else []):
         rc = m.get("reference_cpu") or {}
         out.append("| %s | %d | **%s** | %.2f / – | %.2f M | %s (4096-pair calls, 4 callers), %s (10-pair calls, 64 callers) | %s | bit-exact (7 fields) |" % (
-            m["workload"].split(":")[0].replace(" mate-SW", "") + " mate-SW, " + ("%d pairs" % (m["jobs"] // 2)), m.get("n_gpus", 1), f0(m["kernel_gcups"]),
+            m["workload"].split(":")[0].replace(" mate-SW", "") + " mate-SW, " + ("%d pairs%s" % (m["jobs"] // 2, " per GPU" if m.get("n_gpus", 1) > 1 else "")), m.get("n_gpus", 1), f0(m["kernel_gcups"]),
             m["roofline_frac_alu"], m.get("read_pairs_per_s", 0) / 1e6,
             f0((m.get("host_abi_large") or {}).get("gcups")), f0((m.get("host_abi_sbatch10") or {}).get("gcups")),
             ("%.1f GCUPS (SSE2 ksw_align2, %d cores)" % (rc["gcups"], rc["cores"])) if "gcups" in rc else "–"))
