@@ -161,7 +161,7 @@ __device__ __forceinline__ bool coop_row(P2Run &r, const CoopLane<G> &L, const S
     if (r.i >= r.tlen) return false;
     constexpr int S = CoopChunk<G>::S;
     uint16_t *h16 = (uint16_t *)he;
-    int t = r.ts.next(); if (t > 4) t = 4;
+    int t = r.ts.next(r.i); if (t > 4) t = 4;
     CoopRowK k;
     k.tlo = o.tlo[t]; k.thi = o.thi[t];
     k.e2x = 2 * K.e_ins; k.ne_ins = K.ne_ins;

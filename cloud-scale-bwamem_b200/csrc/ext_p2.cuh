@@ -116,7 +116,7 @@ struct P2Run {
         const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
 #define P2_H(c) h16[(size_t)((c) >> 1) * pstr + ((c) & 1)]
 #define P2_E(c) h16[(size_t)((c) >> 1) * pstr + 2 + ((c) & 1)]
-        int t = ts.next(); if (t > 4) t = 4;
+        int t = ts.next(i); if (t > 4) t = 4;
         const uint32_t tlo = o.tlo[t], thi = o.thi[t];
         const int h1i = imax(h0 - (K.o_del + e_del * (i + 1)), 0);
         beg = imax(beg, i - w);

@@ -254,33 +254,46 @@ struct NibStream {
     }
 };
 
-// The same stream with the NEXT word already in flight: the target bases of SWExtend are consumed one per row, so a
-// word lasts 8 rows and the load of its successor has that long to arrive -- the row that needs a new word finds it in
-// a register instead of waiting for a global load it issued a moment ago (long-scoreboard stalls were 0.3-0.8 of a
-// cycle per issued instruction in the class kernels).  Never reads past the last word of the stream.
+// The target bases of SWExtend, one per row.  A lane's stream starts at an arbitrary nibble of its task's block, but
+// all lanes of a warp count rows together, so the stream is kept ROW-aligned: `rw` holds the eight bases of rows
+// 8k .. 8k+7 (built by a funnel shift over two consecutive words), a row costs a shift, and the refill happens at rows
+// 8, 16, ... for every lane at once -- a uniform branch.  (The byte-aligned form refilled when ITS word ran out: some
+// lane did so in nearly every row, and the divergent refill block cost the whole warp ~10 instructions per row.)
+// Two words are kept ahead of `rw`, so the load issued at a refill has eight rows to arrive.  Never reads past the last
+// word of the stream.
 struct NibStreamAhead {
     const uint32_t *p, *pend;   // next word to fetch, one past the last word of the stream
-    uint32_t cur, nxt;
-    int left;
+    uint32_t rw, w1, w2;        // rows 8k..8k+7; the word after the one rw starts in; the word after that
+    int sh;                     // 4 * (start nibble & 7)
+    CSW_HD uint32_t fetch() { return p < pend ? *p++ : 0u; }
+    CSW_HD static uint32_t join(uint32_t hi, uint32_t lo, int sh)     // hi << sh | lo >> (32 - sh), sh in 0..28
+    {
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_l(lo, hi, sh);
+#else
+        return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+    }
     CSW_HD void init(const uint32_t *words, int start_nibble, int n_nibbles)
     {
         p = words + (start_nibble >> 3);
         pend = words + ((start_nibble + n_nibbles + 7) >> 3);
-        const int sk = start_nibble & 7;
-        cur = *p++;
-        nxt = p < pend ? *p++ : 0u;
-        cur <<= 4 * sk;
-        left = 8 - sk;
+        sh = 4 * (start_nibble & 7);
+        const uint32_t w0 = fetch();
+        w1 = fetch();
+        w2 = fetch();
+        rw = join(w0, w1, sh);
     }
-    CSW_HD int next()
+    // base of row i; rows must be asked for in order, every row once
+    CSW_HD int next(int i)
     {
-        if (left == 0) {
-            cur = nxt; left = 8;
-            if (p < pend) nxt = *p++;
+        if ((i & 7) == 0 && i > 0) {
+            rw = join(w1, w2, sh);
+            w1 = w2;
+            w2 = fetch();
         }
-        int v = (int)(cur >> 28);
-        cur <<= 4;
-        --left;
+        const int v = (int)(rw >> 28);
+        rw <<= 4;
         return v;
     }
 };
