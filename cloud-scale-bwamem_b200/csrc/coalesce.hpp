@@ -311,6 +311,7 @@ private:
     {
 #if defined(__linux__)
         prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);             // 1 us: the naps below are 20 us
+        { const char *e = getenv("CSBWA_CO_NAP_US"); if (e && atoi(e) > 0 && atoi(e) <= 1000) nap_us_ = atoi(e); }
         // The pump is the one thread every caller of this GPU waits on, and it sleeps most of the time: when the callers
         // outnumber the cores (8 GPUs on 32 vCPUs: 64 callers per 4 cores) it should not queue behind them.  Needs
         // CAP_SYS_NICE; silently stays at the default priority without it.  CSBWA_PUMP_NICE=0 keeps the default.
