@@ -226,11 +226,14 @@ struct HostCoExec {
     std::vector<int> rcs;
     size_t hdr_off = 0, ext_off = 0;
     int delay_us = 0;
+    std::vector<unsigned> started;              // generation launched per slot (pump thread only)
+    std::atomic<int> others_low{0}, max_others{0};
     HostCoExec(int n_slots, size_t max_bytes, int max_tasks, int max_calls, int delay)
         : hin(n_slots, std::vector<uint8_t>(max_bytes)), hout(n_slots, std::vector<int16_t>((size_t)max_tasks * 10 + 32)), th(n_slots),
           done(n_slots), bad(n_slots, std::vector<uint8_t>((size_t)max_calls, 0)), rcs(n_slots, 0), delay_us(delay)
     {
         for (auto &d : done) d.store(0);
+        started.assign((size_t)n_slots, 0u);
     }
     ~HostCoExec() { for (auto &t : th) if (t.joinable()) t.join(); }
     uint8_t *in_staging(int slot) { return hin[slot].data(); }
@@ -240,7 +243,15 @@ struct HostCoExec {
     const char *detail(int) { return "host executor failure"; }
     int launch(int slot, int n_calls, size_t span, int n_tasks, int n_units, unsigned gen, int others)
     {
-        (void)span; (void)n_tasks; (void)others;
+        (void)span; (void)n_tasks;
+        // `others` = groups the coalescer believes are on the device: must match what this executor has in flight
+        int running = 0;
+        for (size_t q = 0; q < started.size(); ++q)
+            if ((int)q != slot && started[q] != 0 && done[q].load(std::memory_order_acquire) != started[q]) ++running;
+        // (a group whose completion the pump has not yet collected still counts as running for the coalescer)
+        if (others < running) others_low.fetch_add(1);
+        if (others > max_others.load()) max_others.store(others);
+        started[slot] = gen;
         if (th[slot].joinable()) th[slot].join();
         th[slot] = std::thread([this, slot, n_calls, n_units, gen] {
             if (delay_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));
@@ -304,6 +315,12 @@ extern "C" void emu_co_stats(void *h, long long *groups, long long *calls)
 {
     *groups = ((EmuCo *)h)->co->groups_run();
     *calls = ((EmuCo *)h)->co->calls_run();
+}
+// launches whose `others` argument was below the number of groups really in flight (must be 0), and the largest value seen
+extern "C" void emu_co_others(void *h, int *low, int *max_seen)
+{
+    *low = ((EmuCo *)h)->ex.others_low.load();
+    *max_seen = ((EmuCo *)h)->ex.max_others.load();
 }
 extern "C" void emu_co_destroy(void *h)
 {

@@ -108,6 +108,13 @@ class EmuCoalescer:
         self.L.emu_co_stats(self.h, C.byref(g), C.byref(c))
         return g.value, c.value
 
+    def others(self):
+        """(launches told fewer groups were in flight than really were, largest `others` value passed to a launch)"""
+        lo, mx = C.c_int(0), C.c_int(0)
+        self.L.emu_co_others.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.L.emu_co_others(self.h, C.byref(lo), C.byref(mx))
+        return lo.value, mx.value
+
     def close(self):
         if self.h:
             self.L.emu_co_destroy(self.h)

@@ -36,6 +36,10 @@ def test_coalescer_many_threads(pkg, oracle, emu):
         groups, calls = co.stats()
         assert calls == 6 * len(wires)
         assert groups < calls            # calls really travelled together
+        # what the executor is told about the load (it picks the small-group kernel by it): never fewer groups than it
+        # really has in flight, and with two permits at most one other
+        low, seen = co.others()
+        assert low == 0 and seen <= 1
     finally:
         co.close()
 
@@ -50,6 +54,7 @@ def test_coalescer_single_caller_no_added_latency(pkg, oracle, emu):
             rc, out = co.submit(wire)
             assert rc == 0 and np.array_equal(out, oracle.extend_wire(wire)[0])
         assert co.stats() == (5, 5)
+        assert co.others() == (0, 0)     # an isolated caller always finds the device idle
     finally:
         co.close()
 
