@@ -202,6 +202,130 @@ def config_block(args, n_pairs):
 
 
 # ---------------------------------------------------------------------------------------------
+# the other BASELINE read lengths, as sub-objects of the default line
+# ---------------------------------------------------------------------------------------------
+def resident_leg(pkg, L, torch, dev, cfg_name, n_pairs, steps, nstreams_max, gsz, alu_peak):
+    """Resident-input throughput of another BASELINE config (C1: 101 bp, C5: 250 bp at 5 % error) on the launch
+    path of the headline leg -- all seam calls of a shard resident, `gsz` calls per launch sequence, launch sequences
+    round-robin over streams, one CUDA graph per step -- at a reduced shard, so that the default run shows the
+    kernel's fraction of the roofline at every read length.  The first call's replies and exact cell counts are
+    checked against the oracle."""
+    global CFG
+    saved = CFG
+    CFG = CFGS[cfg_name]
+    try:
+        w = gen_workload(pkg, n_pairs, 0)
+        cfg_txt = config_block(None, n_pairs)["workload"]
+    finally:
+        CFG = saved
+    bufs = w["bufs"]
+    ntasks = [task_count(b) for b in bufs]
+    CALL = pkg._lib.CALL_DTYPE
+    offs, pos = [], 0
+    for b in bufs:
+        offs.append(pos)
+        pos += (b.size + 255) & ~255
+    d_in = torch.empty(pos, dtype=torch.uint8, device=dev)
+    for b, o in zip(bufs, offs):
+        d_in[o:o + b.size].copy_(torch.from_numpy(b))
+    ooffs = np.concatenate([[0], np.cumsum([10 * n for n in ntasks])]).astype(np.int64)
+    d_out = torch.zeros(int(ooffs[-1]), dtype=torch.int16, device=dev)
+    d_cells = torch.zeros(1, dtype=torch.int64, device=dev)
+    groups = []
+    for g0 in range(0, len(bufs), gsz):
+        idx = range(g0, min(len(bufs), g0 + gsz))
+        tab = np.zeros(len(idx), dtype=CALL)
+        tb = 0
+        for j, i in enumerate(idx):
+            tab[j] = (offs[i] - offs[g0], bufs[i].size, ntasks[i], int(ooffs[i] - ooffs[g0]), tb, 0)
+            tb += ntasks[i]
+        groups.append((g0, tab, torch.from_numpy(tab.view(np.uint8).copy()).to(dev), tb))
+    nstreams = max(1, min(nstreams_max, len(groups)))
+    scr_bytes = max(L.csbwa_extend_scratch_bytes(g[3], 0) for g in groups) + (64 << 20)
+    scratch = [torch.empty(scr_bytes, dtype=torch.uint8, device=dev) for _ in range(nstreams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+
+    def enqueue_step(main_stream):
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        for s in streams:
+            s.wait_event(fork)
+        for gi, (g0, tab, d_tab, _nt) in enumerate(groups):
+            rc = L.csbwa_extend_multi_device(d_in.data_ptr() + offs[g0], tab.ctypes.data, d_tab.data_ptr(), len(tab),
+                                             d_out.data_ptr() + 2 * int(ooffs[g0]), d_cells.data_ptr(),
+                                             scratch[gi % nstreams].data_ptr(), scr_bytes,
+                                             C.c_void_p(streams[gi % nstreams].cuda_stream))
+            if rc != 0:
+                raise RuntimeError("csbwa_extend_multi_device: %d %s" % (rc, L.csbwa_last_error().decode()))
+        for s in streams:
+            j = torch.cuda.Event()
+            j.record(s)
+            main_stream.wait_event(j)
+
+    main_stream = torch.cuda.current_stream()
+    enqueue_step(main_stream)
+    torch.cuda.synchronize()
+    cells_per_step = int(d_cells.item())
+    graph = None
+    try:
+        g = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.graph(g, stream=cap_stream):
+            enqueue_step(torch.cuda.current_stream())
+        graph = g
+    except Exception as e:
+        sys.stderr.write("bench: CUDA graph capture failed in the %s leg (%s); using direct launches\n" % (cfg_name, e))
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            enqueue_step(main_stream)
+
+    for _ in range(3):
+        run_step()
+    d_out.zero_()
+    d_cells.zero_()
+    torch.cuda.synchronize()
+    # the 101 bp shard is smaller than L2: every step is timed by its own event pair, L2 flushed in between
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    cells = int(d_cells.item())
+    if cells != cells_per_step * steps:
+        raise RuntimeError("cell counter differs between steps: %d vs %d x %d" % (cells, cells_per_step, steps))
+    from oracle import oracle as O
+    O.build()
+    oref, ocells, _ = O.extend_wire(bufs[0], n_threads=os.cpu_count() or 1)
+    got = d_out[:10 * ntasks[0]].cpu().numpy()
+    d_cells.zero_()
+    ms3 = (C.c_float * 3)()
+    g0, tab, d_tab, _nt = groups[0]
+    rc = L.csbwa_extend_profile_device(d_in.data_ptr(), tab.ctypes.data, d_tab.data_ptr(), 1, d_out.data_ptr(),
+                                       d_cells.data_ptr(), scratch[0].data_ptr(), scr_bytes, C.c_void_p(0), ms3)
+    torch.cuda.synchronize()
+    cells_ok = rc == 0 and int(d_cells.item()) == int(ocells.sum())
+    gcups = cells / (ms * 1e-3) / 1e9
+    return {"workload": cfg_txt, "pairs": n_pairs, "steps": steps, "ms_per_step": ms / steps,
+            "tasks_per_step": int(sum(ntasks)), "cells_per_step": cells_per_step, "value": gcups, "unit": "GCUPS",
+            "read_pairs_per_s": (w["n_reads"] / 2) * steps / (ms * 1e-3),
+            "roofline_frac_alu": (gcups * OPS_PER_CELL / alu_peak) if alu_peak else None,
+            "cuda_graph": graph is not None, "streams": nstreams, "calls_per_launch_sequence": gsz,
+            "inputs": "resident in HBM (%d MB of wire buffers per step)" % (pos >> 20),
+            "l2_policy": "L2 flushed between the timed steps (256 MB write); each step timed by its own CUDA-event pair",
+            "parity_first_call_ok": bool(np.array_equal(got, oref)), "cells_match_oracle": bool(cells_ok)}
+
+
+# ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -222,6 +346,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(CFGS), help="BASELINE config (the headline is C2)")
     ap.add_argument("--no-matesw", action="store_true", help="skip the short mate-SW (C3 shape) leg reported under 'matesw'")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs under ncu only)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short C1 / C5 resident legs reported under 'other_configs'")
+    ap.add_argument("--other-pairs", type=int, default=524288, help="read pairs of the C1 / C5 legs under 'other_configs'")
     ap.add_argument("--ext-mode", type=int, default=-1, help="extension core: 1 column pairs (s16x2), 0 one column per step (u8); -1 library default")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -558,6 +684,16 @@ def main():
                                                       "cpu_oracle_gcups", "parity_sample_ok")}
             except Exception as e:
                 line["swglobal"] = {"error": repr(e)}
+        if world == 1 and args.workload == "C2" and not args.no_other_configs and not args.no_matesw:
+            # the other read lengths BASELINE names (C1: 101 bp, C5: 250 bp at 5 % error): resident-input legs on the
+            # headline's launch path at a reduced shard -- the kernel's fraction of the roofline is length-dependent
+            line["other_configs"] = {}
+            for name in ("C1", "C5"):
+                try:
+                    line["other_configs"][name] = resident_leg(pkg, L, torch, dev, name, args.other_pairs, 3, args.streams,
+                                                               gsz, alu_peak)
+                except Exception as e:   # never lose the headline line over the extra legs
+                    line["other_configs"][name] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()

@@ -301,7 +301,7 @@ extern "C" int csbwa_align2_batch(const csbwa_job *jobs, int32_t n_jobs, const u
     for (int32_t k = 0; k < n_jobs; ++k) {
         const csbwa_job &j = jobs[k];
         if (j.q_len < 0 || j.t_len < 0 || j.q_off < 0 || j.t_off < 0 ||
-            j.q_off + j.q_len > seq_bytes || j.t_off + j.t_len > seq_bytes)
+            j.q_off > seq_bytes - j.q_len || j.t_off > seq_bytes - j.t_len)      // no sum that could overflow
             return fail(CSBWA_E_BADARG, "job sequence range outside seqs[]");
         tq += j.q_len; tt += j.t_len;
     }
@@ -470,7 +470,7 @@ extern "C" int csbwa_pestat_prep(int64_t l_pac, int32_t n_pairs, const csbwa_aln
 
 extern "C" int csbwa_pestat_compute(int32_t n, const int32_t *dir, const int32_t *dist, int32_t max_ins, csbwa_pestat pes[4])
 {
-    if (n < 0 || max_ins < 1 || !pes || (n > 0 && (!dir || !dist))) return fail(CSBWA_E_BADARG, "bad argument");
+    if (n < 0 || max_ins < 1 || max_ins > (1 << 26) || !pes || (n > 0 && (!dir || !dist))) return fail(CSBWA_E_BADARG, "bad argument");
     const int kMinDirCnt = 10;
     const double kMinDirRatio = 0.05, kOutlier = 2.0, kMapping = 3.0, kMaxStd = 4.0;
     // counting sort (:955-981): one histogram over [1, max_ins] per orientation IS the sorted array

@@ -23,8 +23,8 @@ csbwa_stats g_stats;
 std::atomic<long long> g_zero_copy_calls{0};
 
 std::mutex g_mu;
-bool g_inited = false;
-int g_ndev = 0;
+std::atomic<bool> g_inited{false};
+std::atomic<int> g_ndev{0};
 std::atomic<unsigned> g_rr{0};
 
 static int g_sms[64] = {0};
@@ -55,9 +55,11 @@ int pick_device(int device, int *dev_out)
         int rc = csbwa_init(0);
         if (rc < 0) return rc;
     }
+    const int ndev = g_ndev.load();                     // read once: csbwa_shutdown on another thread zeroes it
+    if (ndev <= 0) return fail(CSBWA_E_NODEVICE, "library shut down while a call was starting");
     int dev = device;
-    if (dev < 0) dev = (int)(g_rr.fetch_add(1) % (unsigned)g_ndev);
-    if (dev >= g_ndev) return fail(CSBWA_E_BADARG, "device index out of range");
+    if (dev < 0) dev = (int)(g_rr.fetch_add(1) % (unsigned)ndev);
+    if (dev >= ndev) return fail(CSBWA_E_BADARG, "device index out of range");
     *dev_out = dev;
     return CSBWA_OK;
 }
@@ -225,7 +227,7 @@ extern "C" const char *csbwa_strerror(int code)
 extern "C" int csbwa_init(int n_gpus)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_inited) return g_ndev;
+    if (g_inited) return g_ndev.load();
     // submission streams + their aux streams exceed the default 8 hardware queues; ask for 32 so
     // independent groups do not serialise behind one another (no effect once a context exists)
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
@@ -244,10 +246,10 @@ extern "C" int csbwa_init(int n_gpus)
         memset(&g_stats, 0, sizeof g_stats);
     }
     g_inited = true;
-    return g_ndev;
+    return n;
 }
 
-extern "C" int csbwa_device_count(void) { return g_inited ? g_ndev : 0; }
+extern "C" int csbwa_device_count(void) { return g_inited.load() ? g_ndev.load() : 0; }
 
 extern "C" int csbwa_shutdown(void)
 {

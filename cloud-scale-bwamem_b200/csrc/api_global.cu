@@ -126,7 +126,7 @@ extern "C" int csbwa_global_batch(const csbwa_gjob *jobs, int32_t n_jobs, const 
     for (int32_t k = 0; k < n_jobs; ++k) {
         const csbwa_gjob &j = jobs[k];
         if (j.q_len < 0 || j.t_len < 0 || j.w < 0 || j.q_off < 0 || j.t_off < 0 || j.cigar_cap < 0 || j.cigar_off < 0 ||
-            j.q_off + j.q_len > seq_bytes || j.t_off + j.t_len > seq_bytes || j.cigar_off + j.cigar_cap > cigar_words)
+            j.q_off > seq_bytes - j.q_len || j.t_off > seq_bytes - j.t_len || j.cigar_off > cigar_words - j.cigar_cap)   // no sum that could overflow
             return fail(CSBWA_E_BADARG, "job range outside seqs[] / cigars[]");
         if (j.q_len > max_q) max_q = j.q_len;
         const long long zc = glb_z_cells(j.q_len, j.t_len, j.w);

@@ -40,8 +40,8 @@ extern std::atomic<long long> g_zero_copy_calls;   // merged into csbwa_stats::e
 
 // ---- devices ----------------------------------------------------------------------------------
 extern std::mutex g_mu;
-extern bool g_inited;
-extern int g_ndev;
+extern std::atomic<bool> g_inited;      // written under g_mu, read by every entry point without it
+extern std::atomic<int> g_ndev;
 extern std::atomic<unsigned> g_rr;
 int dev_sms(int dev);                       // multiprocessor count (cached)
 // resolves `device` (-1 = round robin) after making sure the library is initialised
@@ -88,7 +88,15 @@ int acquire_ctx(int device, Ctx **out);
 void release_ctx(Ctx *c);
 struct CtxGuard {
     Ctx *c;
-    ~CtxGuard() { if (c) release_ctx(c); }
+    // Every successful path has synchronised the stream; an early error return may leave copies or kernels queued
+    // that still use the context's buffers: drain them before the context goes back to the pool.
+    ~CtxGuard()
+    {
+        if (!c) return;
+        if (c->st && cudaStreamQuery(c->st) == cudaErrorNotReady) cudaStreamSynchronize(c->st);
+        (void)cudaGetLastError();
+        release_ctx(c);
+    }
 };
 
 // Host -> pinned staging -> device for the direct paths: the staging memcpy of chunk k + 1 runs while
