@@ -45,6 +45,15 @@ void orc_default_opt(orc_opt_t *o)
 /* ------------------------------------------------------------------------- */
 /* SWExtend  (S/util/SWUtil.scala:61-230)                                     */
 /* ------------------------------------------------------------------------- */
+/* Number of SWExtend rows so far in which the Scala z-drop rule and the C's decided differently (the run then follows
+ * the Scala).  Lets the tests compare whole drivers with a RUN of the reference's C at the default zdrop wherever the
+ * count did not move: there the two are the same computation.  reset != 0 zeroes it after reading. */
+static long orc_zd_div = 0;
+long orc_zdrop_divergences(int reset)
+{
+    return reset ? __atomic_exchange_n(&orc_zd_div, 0, __ATOMIC_RELAXED) : __atomic_load_n(&orc_zd_div, __ATOMIC_RELAXED);
+}
+
 void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                    int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
                    int w, int end_bonus, int zdrop, int h0, orc_ext_t *out)
@@ -116,10 +125,17 @@ void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
              * e_ins test is only reached when di > dj, and there is no test at
              * all when di <= dj.  (C ksw_extend2 differs, N/ksw.c:455-461.) */
             int di = i - best_i, dj = rmj - best_j;
+            int brk = 0;
             if (di > dj) {
-                if (best - rm - (di - dj) * e_del > zdrop) break;
-                else if (best - rm - (dj - di) * e_ins > zdrop) break;
+                if (best - rm - (di - dj) * e_del > zdrop) brk = 1;
+                else if (best - rm - (dj - di) * e_ins > zdrop) brk = 1;
             }
+            /* test aid: rows where the reference's C (N/ksw.c:455-461) would decide otherwise from the same state */
+            {
+                const int c_brk = di > dj ? (best - rm - (di - dj) * e_del > zdrop) : (best - rm - (dj - di) * e_ins > zdrop);
+                if (c_brk != brk) __atomic_fetch_add(&orc_zd_div, 1, __ATOMIC_RELAXED);
+            }
+            if (brk) break;
         }
         /* band shrink for the next row (:202-214) */
         j = rmj;

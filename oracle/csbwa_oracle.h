@@ -11,11 +11,16 @@
  * The restatement is therefore pinned against the reference's own bundled C
  * (src/main/native/ksw.c, compiled out-of-tree into oracle/_ref/ by
  * oracle/Makefile) in the regimes where Scala and C provably agree
- * (zdrop<=0 for extension; qlen*a<250 and qlen%16==0 for align2; SWGlobal == ksw_global2;
- * the worker1 round loop == mem_chain2aln of N/bwamem.c with zdrop = 0, via oracle/_ref/
- * libbwamem_ref.so) -- see tests/test_oracle.py, tests/test_global.py, tests/test_chain2aln.py.
- * Where Scala and C differ (the z-drop dangling else, ...), the Scala text wins and an independent
- * literal Python transliteration of the Scala (tests/util.py) is the second witness.
+ * (zdrop<=0 for extension, and with the default zdrop = 100 every row up to the first z-drop decision
+ * the two rules make differently -- which on the BASELINE C1 / C2 / C5 workloads leaves every reply equal
+ * to the C's; qlen*a<250 and qlen%16==0 for align2 through ksw_u8, qlen%16==8 through ksw_i16, and
+ * score / te / qe / tb / qb at any length; SWGlobal == ksw_global2; the worker1 round loop ==
+ * mem_chain2aln of N/bwamem.c with zdrop = 0 and, read by read, with its default options wherever no
+ * differing z-drop decision occurred; the mate-rescue driver and the insert-size statistics ==
+ * mem_group_matesw / mem_pestat via oracle/ref_shim.c) -- see tests/test_oracle.py, tests/test_global.py,
+ * tests/test_chain2aln.py, tests/test_matesw_ref.py.
+ * Where Scala and C differ (the outcome of the z-drop dangling else, ...), the Scala text wins and an
+ * independent literal Python transliteration of the Scala (tests/util.py) is the second witness.
  * NOT pinned against a run of the reference's Scala itself (impossible in this image).
  *
  * Reference citations use S/ = src/main/scala/cs/ucla/edu/bwaspark/.
@@ -53,6 +58,7 @@ typedef struct {
     int64_t cells;              /* number of inner-loop bodies executed (SWUtil.scala:151-171) */
 } orc_ext_t;
 
+long orc_zdrop_divergences(int reset);   /* test aid: rows where the Scala and the C z-drop rules decided differently */
 void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                    int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
                    int w, int end_bonus, int zdrop, int h0, orc_ext_t *out);

@@ -438,6 +438,14 @@ SEED_DTYPE = np.dtype([("r_beg", "<i8"), ("q_beg", "<i4"), ("len", "<i4")])
 CHAIN_DTYPE = np.dtype([("seed_off", "<i4"), ("n_seeds", "<i4")])
 
 
+def zdrop_divergences(reset=False):
+    """Rows of SWExtend so far in which the Scala z-drop rule and the reference C's decided differently (test aid)."""
+    L = lib()
+    L.orc_zdrop_divergences.restype = C.c_long
+    L.orc_zdrop_divergences.argtypes = [C.c_int]
+    return int(L.orc_zdrop_divergences(1 if reset else 0))
+
+
 def chain2aln(reads, read_chain_off, chains, seeds, pac, l_pac, opt=None, cap=None):
     """memChainToAlnBatched, read by read, extensions on demand (the reference's own order of work).
     Returns (regs ALNREG_DTYPE[], out_off int32[n+1], cells, n_ext)."""

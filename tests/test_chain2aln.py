@@ -82,6 +82,37 @@ def test_oracle_pinned_vs_reference_c(pkg, oracle):
         assert same or (np.array_equal(goff, woff) and (got != want).mean() < 0.02)
 
 
+def test_oracle_pinned_vs_reference_c_default_zdrop(pkg, oracle):
+    """The same pin at the DEFAULT zdrop = 100, read by read: the oracle counts the SWExtend rows in which the Scala
+    z-drop rule and the C's decide differently from the same state (orc_zdrop_divergences); for every read whose
+    extensions met no such row the two round loops are the same computation, and the region list must be
+    byte-identical to a run of the reference's mem_chain2aln with its default options.  Indel-rich and high-error
+    reads so that the z-drop tests run (and fire) in many rows."""
+    if not oracle.ref_mem_available():
+        pytest.skip("oracle/_ref/libbwamem_ref.so not built")
+    n_same = n_div = 0
+    for eps, seed in ((0.03, 21), (0.08, 22)):
+        opt, ref, reads, rco, chains, seeds = _workload_chains(pkg, seed=seed, n_pairs=150, eps=eps)
+        pac = pkg.jni.packPac(ref)
+        sets = [(reads, rco, chains, seeds), _crafted_chains(pkg, np.random.default_rng(seed), ref, n_reads=150)]
+        for rd, rc_, ch, sd in sets:
+            for r in range(len(rd)):
+                c0, c1 = int(rc_[r]), int(rc_[r + 1])
+                if c0 == c1:
+                    continue
+                one_rco = np.array([0, c1 - c0], dtype=np.int32)
+                oracle.zdrop_divergences(reset=True)
+                got, goff, _, _ = oracle.chain2aln(rd[r:r + 1], one_rco, ch[c0:c1], sd, pac, len(ref))
+                if oracle.zdrop_divergences() != 0:
+                    n_div += 1
+                    continue
+                want, woff = oracle.ref_mem_chain2aln(rd[r:r + 1], one_rco, ch[c0:c1], sd, pac, len(ref))
+                assert np.array_equal(goff, woff), r
+                assert got.tobytes() == want.tobytes(), r
+                n_same += 1
+    assert n_same > 500 and n_div < n_same
+
+
 @pytest.mark.gpu
 def test_chain2aln_flat_parity(pkg, oracle):
     L_ = pkg.lib()

@@ -36,6 +36,125 @@ def test_extend_vs_reference_c_zdrop0(oracle):
         assert {k: a[k] for k in b} == b, it
 
 
+def test_extend_vs_reference_c_zdrop_active(oracle):
+    """zdrop = 100 (the default, the value every product call runs with): the Scala and the C make the same z-drop
+    decision in every row until the FIRST row where the dangling else (SWUtil.scala:194-199 vs N/ksw.c:455-461) decides
+    differently, and a break in row r leaves the same outputs as running out of target after row r.  So with the
+    target cut after that row -- or whole, when the decisions never differ -- the oracle must equal a RUN of the
+    reference's C on all six outputs, z-drop tests executed, fired or not.  The row is found by the literal Python
+    transliteration, which evaluates both predicates on the same state."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(111)
+    n_cut = n_fired_both = n_tested = 0
+    for it in range(3000):
+        kind = it % 3
+        if kind == 0:                                      # the z-drop stress recipe (SURVEY appendix B): the quirk fires often
+            n = int(rng.integers(60, 132)); p = int(rng.integers(5, 60))
+            q = rng.integers(0, 4, n).astype(np.uint8)
+            t = rng.integers(0, 4, n + int(rng.integers(20, 100))).astype(np.uint8); t[:p] = q[:p]
+            h0 = int(rng.integers(40, 231))
+        elif kind == 1:                                    # a good prefix, a few inserted rows, then a heavily mutated rest:
+            n = int(rng.integers(60, 132)); p = int(rng.integers(5, 60))      # with a narrow band both sides z-drop
+            q = rng.integers(0, 4, n).astype(np.uint8)
+            t = np.concatenate([q[:p], rng.integers(0, 4, int(rng.integers(1, 8))).astype(np.uint8),
+                                util.mutate(rng, q[p:], float(rng.choice([0.4, 0.6, 0.75])))])
+            h0 = int(rng.integers(80, 231))
+        else:                                              # read-like extensions with errors and indels
+            ql = int(rng.integers(20, 140))
+            q = rng.integers(0, 4, ql).astype(np.uint8)
+            t = util.mutate(rng, np.concatenate([q, rng.integers(0, 4, int(rng.integers(0, 100))).astype(np.uint8)]),
+                            float(rng.choice([0.02, 0.05, 0.1, 0.3])), indel=0.3)
+            h0 = int(rng.integers(19, 120))
+        if len(t) == 0:
+            continue
+        w = int(rng.choice([3, 5, 10, 20])) if kind == 1 else int(rng.choice([3, 5, 10, 20, 30, 100, 200]))
+        log = []
+        util.py_sw_extend(q, t, h0, w, 5, 100, zd_log=log)
+        cut = next((i for i, s_brk, c_brk in log if s_brk != c_brk), None)
+        tt = t if cut is None else t[:cut + 1]
+        n_cut += cut is not None
+        n_tested += len([1 for i, _, _ in log if cut is None or i <= cut])
+        n_fired_both += any(s_brk and c_brk for i, s_brk, c_brk in log if cut is None or i < cut)
+        a = oracle.sw_extend(q, tt, h0, w=w, zdrop=100)
+        b = oracle.ref_ksw_extend2(q, tt, h0, w=w, zdrop=100)
+        assert {k: a[k] for k in b} == b, (it, cut)
+    # the cases must exercise what the docstring claims: rows that ran the test, breaks both sides agree on, and cuts
+    assert n_tested > 10000 and n_fired_both >= 10 and n_cut > 100, (n_tested, n_fired_both, n_cut)
+
+
+def test_baseline_workloads_equal_reference_c_default_zdrop(oracle, pkg):
+    """BASELINE C1 / C2 / C5 seam calls at the default zdrop = 100: the oracle's replies (Scala semantics) against the
+    reference's compiled ksw_extend2 under the same extension() control flow (oracle.extend_wire_ref).  A task can
+    differ only if one of its SWExtend rows decided the z-drop differently under the two rules, so the number of
+    differing tasks is bounded by the oracle's count of such rows; on these workloads the rows exist (thousands at
+    151 / 250 bp: the Scala's second test ends a side a little earlier than the C) but never change a reply --
+    every struct of every task equals a RUN of the reference's own C."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    W = pkg.workload
+    for name, L, ref_bp, eps, mu, sigma, seed in (("C1", 101, 5_000_000, 0.01, 300, 30, 20260102),
+                                                 ("C2", 151, 20_000_000, 0.01, 400, 50, 20260103),
+                                                 ("C5", 250, 20_000_000, 0.05, 600, 60, 20260106)):
+        w = W.ext_workload(4096, L, ref_bp, eps, mu, sigma, seed, reads_per_call=4096, numpy_packer=True)
+        n_tasks = n_diff = n_rows = 0
+        for b in w["bufs"]:
+            oracle.zdrop_divergences(reset=True)
+            a, _, _ = oracle.extend_wire(b, n_threads=oracle.max_threads())
+            n_rows += oracle.zdrop_divergences()
+            r = oracle.extend_wire_ref(b, n_threads=oracle.max_threads())
+            n = len(a) // 10
+            n_diff += int((a.reshape(n, 10) != r.reshape(n, 10)).any(axis=1).sum())
+            n_tasks += n
+        assert n_tasks > 5000, name
+        assert n_diff <= n_rows, (name, n_diff, n_rows)          # the principled bound
+        assert n_diff == 0, (name, n_diff, n_rows)               # what these workloads show
+
+
+def test_baseline_matesw_workloads_equal_reference_c(oracle, pkg):
+    """BASELINE C1 (101 bp, windows ~ 400 rows) and C3 (151 bp, windows ~ 4 kb) mate-rescue jobs: the oracle's
+    SWAlign2 rows against a RUN of the reference's SSE2 ksw_align2 (what -bPSWJNI 1 executes).  The padded profile
+    columns of the C's 8-bit kernel can only reach the row maxima behind score2 / te2 (never the maximum itself, its
+    first row, or the start recovery), so score / te / qe / tb / qb must agree on every job at ANY read length; on
+    these workloads the second-best fields agree as well."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    W = pkg.workload
+    ref = W.make_reference(5_000_000, 99)
+    for name, L, mu, sigma in (("C1", 101, 300, 30), ("C3", 151, 1500, 500)):
+        w = W.matesw_workload(384, L, len(ref), 0.01, mu, sigma, 1.0, seed=20260100 + len(name), pairs_per_call=384, ref=ref)
+        jobs, seqs = w["calls"][0]
+        a, _ = oracle.align2_batch(jobs, seqs, n_threads=oracle.max_threads())
+        r = oracle.ref_align2_batch(jobs, seqs, oracle.max_threads())
+        a = np.asarray(a).reshape(len(jobs), 7)
+        r = np.asarray(r).reshape(len(jobs), 7)
+        assert len(jobs) >= 700 and (a[:, 0] >= 19).mean() > 0.9, name          # the mates really are found
+        assert np.array_equal(a[:, [0, 1, 2, 5, 6]], r[:, [0, 1, 2, 5, 6]]), name   # score, te, qe, tb, qb
+        assert np.array_equal(a[:, 3:5], r[:, 3:5]), name                        # score2, te2: equal on these workloads too
+
+
+def test_align_vs_reference_c_16bit_path(oracle):
+    """qlen % 16 == 8: the C's 8-bit kernel pads its striped profile to 16 columns (score-0 columns leak into the row
+    maxima), its 16-bit kernel (ksw_i16, taken when KSW_XBYTE is clear: N/ksw.c:349-351) pads to 8 -- no padding at
+    these lengths.  Below the 8-bit saturation point (score < 250) the Scala SWAlign2 must equal it on all seven
+    outputs: pins the oracle at read lengths the 8-bit comparison cannot (104, 120, 136, 152 ...)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(112)
+    xtra = util.XSUBO | util.XSTART | 19                   # no XBYTE: ksw_align2 takes ksw_i16; the Scala ignores the flag
+    n = 0
+    for it in range(500):
+        L = 16 * int(rng.integers(1, 15)) + 8
+        q, t = util.rand_aln_job(rng, L)
+        a = oracle.sw_align(q, t, xtra)
+        if a["score"] >= 250:
+            continue
+        b = oracle.ref_ksw_align2(q, t, xtra)
+        assert {k: a[k] for k in b} == b, (it, L)
+        n += 1
+    assert n > 300
+
+
 def test_align_vs_reference_c(oracle):
     """Scala SWAlign2 == C ksw_align2 (SSE2 ksw_u8) when qlen*a < 250 and qlen % 16 == 0 (the C
     pads the striped profile with score-0 columns otherwise, which leaks into its row maxima)."""

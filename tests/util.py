@@ -30,7 +30,9 @@ def mutate(rng, s, eps, indel=0.1):
 # ---------------------------------------------------------------------------------------
 # literal transliteration of SWUtil.SWExtend (S/util/SWUtil.scala:61-230)
 # ---------------------------------------------------------------------------------------
-def py_sw_extend(query, target, h0, w=100, end_bonus=5, zdrop=100, o_del=6, e_del=1, o_ins=6, e_ins=1):
+def py_sw_extend(query, target, h0, w=100, end_bonus=5, zdrop=100, o_del=6, e_del=1, o_ins=6, e_ins=1, zd_log=None):
+    """zd_log (a list): receives (row, scala_breaks, c_breaks) for every row that reaches the z-drop test --
+    c_breaks is what the reference's C (N/ksw.c:455-461) decides from the same state."""
     qlen, tlen = len(query), len(target)
     ehh = [0] * (qlen + 1)
     ehe = [0] * (qlen + 1)
@@ -100,6 +102,12 @@ def py_sw_extend(query, target, h0, w=100, end_bonus=5, zdrop=100, o_del=6, e_de
                     else:
                         if mmax - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop:
                             brk = True
+                if zd_log is not None:
+                    if (i - max_i) > (mj - max_j):
+                        c_brk = mmax - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop
+                    else:
+                        c_brk = mmax - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop
+                    zd_log.append((i, brk, c_brk))
             if not brk:
                 j = mj
                 while j >= beg and ehh[j] > 0: j -= 1
