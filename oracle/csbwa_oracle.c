@@ -53,6 +53,14 @@ long orc_zdrop_divergences(int reset)
 {
     return reset ? __atomic_exchange_n(&orc_zd_div, 0, __ATOMIC_RELAXED) : __atomic_load_n(&orc_zd_div, __ATOMIC_RELAXED);
 }
+/* Test aid: c_rule != 0 makes SWExtend take the z-drop decision of the reference's C (N/ksw.c:455-461) instead of the
+ * Scala's (SWUtil.scala:194-199).  With it the whole restatement must equal runs of the C at ANY zdrop -- which shows
+ * that those lines are the only place where the two differ.  Never set outside tests; returns the previous value. */
+static int orc_zd_c_rule = 0;
+int orc_set_zdrop_rule(int c_rule)
+{
+    return __atomic_exchange_n(&orc_zd_c_rule, c_rule ? 1 : 0, __ATOMIC_RELAXED);
+}
 
 void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                    int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
@@ -134,6 +142,7 @@ void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *targ
             {
                 const int c_brk = di > dj ? (best - rm - (di - dj) * e_del > zdrop) : (best - rm - (dj - di) * e_ins > zdrop);
                 if (c_brk != brk) __atomic_fetch_add(&orc_zd_div, 1, __ATOMIC_RELAXED);
+                if (__atomic_load_n(&orc_zd_c_rule, __ATOMIC_RELAXED)) brk = c_brk;
             }
             if (brk) break;
         }

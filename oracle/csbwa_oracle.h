@@ -58,6 +58,7 @@ typedef struct {
     int64_t cells;              /* number of inner-loop bodies executed (SWUtil.scala:151-171) */
 } orc_ext_t;
 
+int orc_set_zdrop_rule(int c_rule);      /* test aid: 1 = decide the z-drop like the reference's C; returns the previous value */
 long orc_zdrop_divergences(int reset);   /* test aid: rows where the Scala and the C z-drop rules decided differently */
 void orc_sw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                    int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,

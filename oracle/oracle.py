@@ -446,6 +446,18 @@ def zdrop_divergences(reset=False):
     return int(L.orc_zdrop_divergences(1 if reset else 0))
 
 
+class c_zdrop_rule:
+    """Context manager (tests only): inside it SWExtend decides the z-drop like the reference's C."""
+
+    def __enter__(self):
+        self.prev = int(lib().orc_set_zdrop_rule(1))
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_zdrop_rule(self.prev)
+        return False
+
+
 def chain2aln(reads, read_chain_off, chains, seeds, pac, l_pac, opt=None, cap=None):
     """memChainToAlnBatched, read by read, extensions on demand (the reference's own order of work).
     Returns (regs ALNREG_DTYPE[], out_off int32[n+1], cells, n_ext)."""

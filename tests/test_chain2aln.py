@@ -113,6 +113,22 @@ def test_oracle_pinned_vs_reference_c_default_zdrop(pkg, oracle):
     assert n_same > 500 and n_div < n_same
 
 
+def test_oracle_round_loop_equals_reference_c_with_its_zdrop_rule(pkg, oracle):
+    """The restated round loop with ONLY the z-drop decision swapped for the C's (oracle.c_zdrop_rule): byte-identical
+    to the reference's mem_chain2aln with its default options on every read -- so that decision is all that separates
+    orc_chain2aln from a run of the reference's C."""
+    if not oracle.ref_mem_available():
+        pytest.skip("oracle/_ref/libbwamem_ref.so not built")
+    opt, ref, reads, rco, chains, seeds = _workload_chains(pkg, seed=23, n_pairs=200, eps=0.08)
+    pac = pkg.jni.packPac(ref)
+    for rd, rc_, ch, sd in ((reads, rco, chains, seeds), _crafted_chains(pkg, np.random.default_rng(23), ref, n_reads=300)):
+        want, woff = oracle.ref_mem_chain2aln(rd, rc_, ch, sd, pac, len(ref))
+        with oracle.c_zdrop_rule():
+            got, goff, _, _ = oracle.chain2aln(rd, rc_, ch, sd, pac, len(ref))
+        assert np.array_equal(goff, woff)
+        assert got.tobytes() == want.tobytes()
+
+
 @pytest.mark.gpu
 def test_chain2aln_flat_parity(pkg, oracle):
     L_ = pkg.lib()

@@ -83,6 +83,35 @@ def test_extend_vs_reference_c_zdrop_active(oracle):
     assert n_tested > 10000 and n_fired_both >= 10 and n_cut > 100, (n_tested, n_fired_both, n_cut)
 
 
+def test_zdrop_rule_is_the_only_difference(oracle):
+    """With the z-drop DECISION of a row swapped for the C's (a test switch of the oracle, oracle.c_zdrop_rule), the
+    whole SWExtend restatement must equal runs of the reference's C at the default zdrop on every case, cut or not --
+    the stress recipe where the two rules disagree in most cases included.  What separates the oracle from the C is
+    then exactly the four lines of SWUtil.scala:194-199, which the oracle and the Python transliteration restate
+    independently (test_zdrop_quirk_is_reachable_and_kept)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(115)
+    n_quirk = 0
+    for it in range(1200):
+        n = int(rng.integers(60, 132)); p = int(rng.integers(5, 60))
+        q = rng.integers(0, 4, n).astype(np.uint8)
+        if it % 2:
+            t = rng.integers(0, 4, n + int(rng.integers(20, 100))).astype(np.uint8); t[:p] = q[:p]
+        else:
+            t = np.concatenate([q[:p], rng.integers(0, 4, int(rng.integers(1, 8))).astype(np.uint8),
+                                util.mutate(rng, q[p:], float(rng.choice([0.1, 0.4, 0.75])))])
+        h0 = int(rng.integers(40, 231))
+        w = int(rng.choice([3, 5, 10, 20, 100]))
+        b = oracle.ref_ksw_extend2(q, t, h0, w=w, zdrop=100)
+        with oracle.c_zdrop_rule():
+            a = oracle.sw_extend(q, t, h0, w=w, zdrop=100)
+        assert {k: a[k] for k in b} == b, it
+        s = oracle.sw_extend(q, t, h0, w=w, zdrop=100)
+        n_quirk += any(s[k] != b[k] for k in b)
+    assert n_quirk > 50                                    # and with the Scala rule the same cases do differ
+
+
 def test_baseline_workloads_equal_reference_c_default_zdrop(oracle, pkg):
     """BASELINE C1 / C2 / C5 seam calls at the default zdrop = 100: the oracle's replies (Scala semantics) against the
     reference's compiled ksw_extend2 under the same extension() control flow (oracle.extend_wire_ref).  A task can
@@ -131,6 +160,65 @@ def test_baseline_matesw_workloads_equal_reference_c(oracle, pkg):
         assert len(jobs) >= 700 and (a[:, 0] >= 19).mean() > 0.9, name          # the mates really are found
         assert np.array_equal(a[:, [0, 1, 2, 5, 6]], r[:, [0, 1, 2, 5, 6]]), name   # score, te, qe, tb, qb
         assert np.array_equal(a[:, 3:5], r[:, 3:5]), name                        # score2, te2: equal on these workloads too
+
+
+def test_align_saturation_regime_vs_reference_c_8bit_kernel(oracle):
+    """L >= 250: the Scala SWAlign has no 16-bit path -- it is the 8-bit kernel's arithmetic, saturation at 255 included
+    (SWUtil.scala:537-549) -- while the reference's C picks ksw_i16 there BY THE CALLER'S FLAG (N/bwamem_pair.c:200 clears
+    KSW_XBYTE when l_ms * a >= 250).  Passing KSW_XBYTE to ksw_align2 ourselves runs the C's 8-bit kernel at these
+    lengths: the regime the Scala restates.  All seven outputs must agree at qlen % 16 == 0, saturated jobs included
+    (score 255, qe = -1, a reverse pass over an empty query); at 250 bp (padding acts) the five primary fields."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(113)
+    xtra = util.XSUBO | util.XSTART | util.XBYTE | 19
+    n_sat = 0
+    for it in range(400):
+        L = int(rng.choice([250, 256, 272, 288, 320]))
+        q, t = util.rand_aln_job(rng, L)
+        if it % 3 == 0:                                    # a near-perfect long hit: the forward pass saturates
+            t = np.concatenate([rng.integers(0, 4, int(rng.integers(0, 80))).astype(np.uint8),
+                                util.mutate(rng, q, float(rng.choice([0, 0.005, 0.01]))), rng.integers(0, 4, 50).astype(np.uint8)])
+        a = oracle.sw_align(q, t, xtra)
+        b = oracle.ref_ksw_align2(q, t, xtra)
+        keys = list(b) if L % 16 == 0 else ["score", "te", "qe", "tb", "qb"]
+        assert {k: a[k] for k in keys} == {k: b[k] for k in keys}, (it, L)
+        n_sat += a["score"] == 255
+        if a["score"] == 255:
+            assert (a["qe"], a["tb"], a["qb"]) == (-1, -1, -1)
+    assert n_sat > 80
+
+
+def test_align_padding_explains_every_difference(oracle):
+    """Read lengths with qlen % 16 != 0 (101, 151, 250 ...): the ONLY thing the reference's 8-bit C kernel does that
+    the Scala text does not is to pad its striped profile with score-0 columns up to a multiple of 16
+    (N/ksw.c:100-104).  Feed the oracle those very columns -- the query extended with a symbol that scores 0 against
+    everything -- and it must reproduce a run of the C on the unpadded query bit for bit, all seven outputs; without
+    them the two differ in a few per cent of cases, in score2 / te2 only.  (Matrix with the N row / column set to 0 on
+    both sides so that N can serve as that symbol; sequences without N.)"""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(114)
+    xtra = util.XSUBO | util.XSTART | util.XBYTE | 19
+    o = oracle.default_opt()
+    for k in range(5):
+        o.mat[4 * 5 + k] = 0
+        o.mat[k * 5 + 4] = 0
+    n_leak = 0
+    for it in range(700):
+        L = int(rng.choice([101, 151, 36, 75, 77, 201, 250]))
+        q, t = util.rand_aln_job(rng, L)
+        q = np.where(q > 3, 0, q).astype(np.uint8)
+        t = np.where(t > 3, 1, t).astype(np.uint8)
+        padded = np.concatenate([q, np.full((-L) % 16, 4, np.uint8)])
+        a = oracle.sw_align(padded, t, xtra, opt=o)
+        b = oracle.ref_ksw_align2(q, t, xtra, opt=o)
+        assert {k: a[k] for k in b} == b, (it, L)
+        plain = oracle.sw_align(q, t, xtra, opt=o)
+        diff = [k for k in b if plain[k] != b[k]]
+        assert set(diff) <= {"score2", "te2"}, (it, L, diff)
+        n_leak += bool(diff)
+    assert n_leak > 0                                      # the padding really acts at these lengths
 
 
 def test_align_vs_reference_c_16bit_path(oracle):
