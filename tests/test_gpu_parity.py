@@ -72,6 +72,32 @@ def test_ext_golden(pkg, oracle, gpu):
     L.csbwa_set_ext_fused_max(prev_fused)
 
 
+def test_reference_run_golden(pkg, gpu):
+    """tests/golden/*_refc.npz: expected outputs PRODUCED BY THE REFERENCE'S OWN C run (tools/make_golden_ref.py;
+    BASELINE C1 / C2 / C5 seam calls through ksw_extend2 under extension(), C1 / C3 mate-rescue jobs through the SSE2
+    ksw_align2).  Every kernel path of the extension seam and the mate-SW seam must reproduce them bit for bit -- no
+    oracle involved."""
+    g = np.load(os.path.join(GOLD, "ext_golden_refc.npz"))
+    L = pkg.lib()
+    prev, prev_coop, prev_fused = L.csbwa_set_ext_mode(-1), L.csbwa_set_ext_coop_max(-1), L.csbwa_set_ext_fused_max(-1)
+    try:
+        for mode, coop, fused in EXT_PATHS:
+            L.csbwa_set_ext_mode(mode)
+            L.csbwa_set_ext_coop_max(coop)
+            L.csbwa_set_ext_fused_max(fused)
+            for name in ("C1", "C2", "C5"):
+                assert np.array_equal(_ext_gpu(pkg, g["wire_" + name]), g["reply_" + name]), (name, mode, coop, fused)
+    finally:
+        L.csbwa_set_ext_mode(prev)
+        L.csbwa_set_ext_coop_max(prev_coop)
+        L.csbwa_set_ext_fused_max(prev_fused)
+    g = np.load(os.path.join(GOLD, "aln_golden_refc.npz"))
+    for name in ("C1", "C3"):
+        jobs, seqs = g["jobs_" + name], g["seqs_" + name]
+        got = np.asarray(pkg.jni.swAlign2Batch(jobs, seqs)).reshape(len(jobs), 7)
+        assert np.array_equal(got, g["out_" + name]), name
+
+
 def test_ext_random_and_adversarial(pkg, oracle, gpu):
     rng = np.random.default_rng(51)
     for L in (101, 151, 250):

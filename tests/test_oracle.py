@@ -327,3 +327,24 @@ def test_golden_vectors(oracle):
     out, cells = oracle.align2_batch(g["jobs"], g["seqs"])
     assert np.array_equal(out, g["out"])
     assert np.array_equal(cells, g["cells"])
+
+
+def test_reference_run_golden_vectors(oracle):
+    """tests/golden/*_refc.npz (tools/make_golden_ref.py): BASELINE-shaped inputs whose expected outputs were PRODUCED
+    BY THE REFERENCE'S OWN C run in this container (ksw_extend2 under extension() at default zdrop; SSE2 ksw_align2).
+    The oracle must reproduce them; where oracle/_ref is present the reference is run again and must reproduce its
+    own fixture."""
+    g = np.load(os.path.join(GOLD, "ext_golden_refc.npz"))
+    for name in ("C1", "C2", "C5"):
+        out, _, _ = oracle.extend_wire(g["wire_" + name], n_threads=oracle.max_threads())
+        assert np.array_equal(out, g["reply_" + name]), name
+        if oracle.ref_available():
+            assert np.array_equal(oracle.extend_wire_ref(g["wire_" + name], n_threads=oracle.max_threads()), g["reply_" + name]), name
+    g = np.load(os.path.join(GOLD, "aln_golden_refc.npz"))
+    for name in ("C1", "C3"):
+        jobs, seqs = g["jobs_" + name], g["seqs_" + name]
+        out, _ = oracle.align2_batch(jobs, seqs, n_threads=oracle.max_threads())
+        assert np.array_equal(np.asarray(out).reshape(len(jobs), 7), g["out_" + name]), name
+        if oracle.ref_available():
+            again = np.asarray(oracle.ref_align2_batch(jobs, seqs, oracle.max_threads())).reshape(len(jobs), 7)
+            assert np.array_equal(again, g["out_" + name]), name
