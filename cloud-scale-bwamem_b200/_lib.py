@@ -59,7 +59,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # CSBWA_LIB_PATH: load this build of the library instead (A/B runs of kernel variants, tools/sessions)
+    path = os.environ.get("CSBWA_LIB_PATH") or _build.build()
     if not os.path.exists(path):
         raise RuntimeError("libcsbwa_sw.so missing: the CUDA extension is required, there is no fallback")
     L = C.CDLL(path)

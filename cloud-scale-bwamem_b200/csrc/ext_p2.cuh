@@ -66,7 +66,7 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 // (15 instructions per row in the SASS; the same trap as AlnStepK in aln_core.cuh).
 struct P2K {
     int o_del, e_del, e_ins, oe_del, oe_ins, zdrop, ne_ins;
-    uint32_t ne_del2, noe_del2, noe_ins2;
+    uint32_t ne_del2, noe_del2, noe_ins2, ne_ins2;
     CSW_HD void init(const SwOpt &o)
     {
         o_del = o.o_del; e_del = o.e_del; e_ins = o.e_ins; zdrop = o.zdrop;
@@ -74,8 +74,49 @@ struct P2K {
         ne_ins = -e_ins;
         ne_del2 = pk16(-e_del, -e_del);
         noe_del2 = pk16(-oe_del, -oe_del); noe_ins2 = pk16(-oe_ins, -oe_ins);
+        ne_ins2 = pk16(-e_ins, -e_ins);
     }
 };
+
+// The insertion chain of one column pair.  In: f = F entering column 2p (a clean 32-bit value, <= 511), g2 = the packed
+// relu(H' - oeIns) of the two columns.  Out: f2 = {F entering 2p | F entering 2p+1 << 16}; returns F leaving the pair.
+// CSBWA_P2_VARIANT 0: two scalar VIADDMNMX on the extracted halves of g2 (LOP3 + SHF + 2 DPX on the ALU pipe, 1 IMAD).
+// 1: the chain stays packed -- A.lo = max(f - e, g.lo) is F(2p+1); f2 = A << 16 | f by one IMAD; B = max(f2 - e, g2) has
+//    F leaving the pair in its high half: 2 DPX + 1 SHF on the ALU pipe, 1 IMAD.  The ALU pipe (one warp instruction per
+//    two cycles per scheduler) is what the pair loop saturates, so an instruction moved off it is time saved.
+// 3: as 1, the final shift through the dot-product unit (hi16_dp) -- no ALU instruction besides the two DPX.
+// Measured on B200, resident inputs, 262144 pairs (tools/sessions/r2_run40.sh): C2 1271 / 1304 / 1341 GCUPS and C1 808 / -- / 907
+// with variants 0 / 1 / 3; all bit-exact.  3 is the default.
+#ifndef CSBWA_P2_VARIANT
+#define CSBWA_P2_VARIANT 3
+#endif
+CSW_HD int p2_chain(int f, uint32_t g2, const P2K &K, uint32_t &f2)
+{
+#if CSBWA_P2_VARIANT == 0
+    const int t1 = addmax(f, K.ne_ins, (int)(g2 & 0xffffu));        // F(i, 2p+1)
+    const int fn = addmax(t1, K.ne_ins, (int)(g2 >> 16));           // F(i, 2p+2)
+    f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);
+    return fn;
+#else
+    const uint32_t a2 = addmax2((uint32_t)f, K.ne_ins2, g2);        // low half: F(i, 2p+1)
+    f2 = umad(a2, 65536u, (uint32_t)f);
+    const uint32_t b2 = addmax2(f2, K.ne_ins2, g2);                 // high half: F(i, 2p+2)
+#if CSBWA_P2_VARIANT >= 3
+    return (int)hi16_dp(b2);
+#else
+    return (int)(b2 >> 16);
+#endif
+#endif
+}
+// the diagonal of a pair: H(i-1, 2p-1) | H(i-1, 2p) << 16 from the previous and the current H2 word
+CSW_HD uint32_t p2_diag(uint32_t hprev2, uint32_t h2cur)
+{
+#if CSBWA_P2_VARIANT >= 3
+    return umad(h2cur, 65536u, hi16_dp(hprev2));                    // two FMA-side instructions instead of one SHF
+#else
+    return funnel16(hprev2, h2cur);
+#endif
+}
 
 struct P2Run {
     int qlen, tlen, h0, w;
@@ -110,7 +151,6 @@ struct P2Run {
         if (i >= tlen) return false;
         const int stride = STRIDE ? STRIDE : stride_rt;
         const int e_del = K.e_del;
-        const int ne_ins = K.ne_ins;
         const uint32_t ne_del2 = K.ne_del2, noe_del2 = K.noe_del2, noe_ins2 = K.noe_ins2;
         uint16_t *h16 = (uint16_t *)he;
         const size_t pstr = (size_t)stride * 4;           // uint16 elements between consecutive pairs
@@ -155,13 +195,12 @@ struct P2Run {
                 sl = ld_u16(ps + stride);                                                                  \
                 const uint32_t keep = ~(out);                                                              \
                 const uint32_t s2 = prmt(tlo, thi, sx);                                                    \
-                const uint32_t hd2 = funnel16(hprev2, x.h2);                                               \
+                const uint32_t hd2 = p2_diag(hprev2, x.h2);                                                \
                 hprev2 = x.h2;                                                                             \
                 const uint32_t hp2 = addmax2(hd2, s2, x.e2);                                               \
                 const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2) & keep;                          \
-                const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));                                     \
-                const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));                                        \
-                const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);                               \
+                uint32_t f2;                                                                               \
+                const int fn = p2_chain(f, g2, K, f2);                                                     \
                 h2 = max2(hp2, f2);                                                                        \
                 const uint32_t e2n = addmax2(x.e2, ne_del2, addmax2_relu(h2, noe_del2, noe_del2));         \
                 /* out-of-band halves: H := {h1i | unchanged}, E := {unchanged | 0} */                   \
@@ -187,14 +226,13 @@ struct P2Run {
                     cur = ph[stride];
                     sl = ld_u16(ps + stride);
                     const uint32_t s2 = prmt(tlo, thi, sx);
-                    const uint32_t hd2 = funnel16(hprev2, x.h2);
+                    const uint32_t hd2 = p2_diag(hprev2, x.h2);
                     hprev2 = x.h2;
                     const uint32_t hp2 = addmax2(hd2, s2, x.e2);
                     const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2);     // relu(hp - oe): a negative 3rd operand
                                                                                 // avoids materialising a packed 0
-                    const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));        // F(i, 2p+1)
-                    const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));           // F(i, 2p+2)
-                    const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);
+                    uint32_t f2;
+                    const int fn = p2_chain(f, g2, K, f2);                        // F(i, 2p+1) inside f2, F(i, 2p+2) returned
                     h2 = max2(hp2, f2);
                     P2Pair y;
                     y.h2 = h2;

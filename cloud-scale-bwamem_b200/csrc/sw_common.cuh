@@ -140,6 +140,17 @@ CSW_HD uint32_t umad(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// high 16-bit half of a word through the integer dot-product unit (IDP.2A: a.h0 * 0 + a.h1 * 1 + 0), i.e. a >> 16
+// issued on the FMA-side pipe instead of a SHF on the ALU pipe, which the DPX instructions saturate
+CSW_HD uint32_t hi16_dp(uint32_t a)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(a, 0x00000100u, 0u);
+#else
+    return a >> 16;
+#endif
+}
+
 // 16-bit load zero-extended into a 32-bit register (LDS.U16 without a masking LOP3)
 CSW_HD uint32_t ld_u16(const uint16_t *p)
 {

@@ -9,7 +9,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "emu.cu")
-LIB = os.path.join(HERE, "emu", "libcsbwa_emu.so")
+# CSBWA_EMU_FLAGS: extra compiler flags (e.g. -DCSBWA_P2_VARIANT=3 to run a kernel-core variant through the CPU parity
+# tests before it ever meets a GPU); such builds get their own file name
+EXTRA = os.environ.get("CSBWA_EMU_FLAGS", "").split()
+LIB = os.path.join(HERE, "emu", "libcsbwa_emu%s.so" % ("_" + "".join(c if c.isalnum() else "_" for c in "".join(EXTRA)) if EXTRA else ""))
 CSRC = os.path.join(os.path.dirname(HERE), "cloud-scale-bwamem_b200", "csrc")
 
 JOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"),
@@ -74,7 +77,7 @@ def load():
                 return Emu(C.CDLL(LIB))
             raise RuntimeError("nvcc missing and emu library not built")
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                               "-Xcompiler", "-fPIC", "-shared", "-o", LIB, SRC])
+                               "-Xcompiler", "-fPIC", "-shared"] + EXTRA + ["-o", LIB, SRC])
     return Emu(C.CDLL(LIB))
 
 
