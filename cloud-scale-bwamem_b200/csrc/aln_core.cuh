@@ -156,12 +156,22 @@ constexpr int ALN_G = 16;      // lanes per job
 // Row-invariant operands of AlnLaneP::step, built once per pass.  Passing the options by reference made
 // every step reload them: the kernel keeps them in global memory and stores the b-array to global memory
 // in the same loop, so the loads cannot be hoisted.
+// CSBWA_ALN_VARIANT: 0 = insertion chain as two scalar VIADDMNMX on the extracted halves of g2, diagonal by a funnel
+// shift; 3 = the pair step of the extension's p2 core (ext_p2.cuh p2_chain / p2_diag, variant 3): the chain stays packed
+// and the 16-bit shifts run on the dot-product unit, three ALU-pipe instructions per column pair fewer on the pipe the
+// systolic step saturates (ALU pipe 83 % busy in the round-1 capture).
+// Measured on B200 (tools/sessions/r2_run41.sh, 8192 pairs resident): C3 windows 1624 -> 1858 GCUPS, C1 windows 1018 -> 1114,
+// bit-exact.  3 is the default.
+#ifndef CSBWA_ALN_VARIANT
+#define CSBWA_ALN_VARIANT 3
+#endif
 struct AlnStepK {
     int ne_ins;
-    uint32_t ne_del2, noe_del2, noe_ins2, sn2;
+    uint32_t ne_del2, noe_del2, noe_ins2, sn2, ne_ins2;
     CSW_HD void init(const SwOpt &o)
     {
         ne_ins = -o.e_ins;
+        ne_ins2 = pk16(-o.e_ins, -o.e_ins);
         ne_del2 = pk16(-o.e_del, -o.e_del);
         noe_del2 = pk16(-(o.o_del + o.e_del), -(o.o_del + o.e_del));
         noe_ins2 = pk16(-(o.o_ins + o.e_ins), -(o.o_ins + o.e_ins));
@@ -198,7 +208,7 @@ struct AlnLaneP {
     template <bool TN>
     CSW_HD void step(const AlnStepK &kk, const AlnMsgP &in, AlnMsgP &out)
     {
-        const int ne_ins = kk.ne_ins;
+        const int ne_ins = kk.ne_ins; (void)ne_ins;
         const uint32_t ne_del2 = kk.ne_del2, noe_del2 = kk.noe_del2, noe_ins2 = kk.noe_ins2, sn2 = kk.sn2;
         const uint32_t t = in.ft >> 16;
         const uint32_t sel = t * 0x1111u + 0xc480u;        // {a[t], sign, b[t], sign}
@@ -210,21 +220,36 @@ struct AlnLaneP {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const uint32_t s2 = TN ? sn2 : prmt(pa[p], pb[p], sel);
+#if CSBWA_ALN_VARIANT >= 3
+            const uint32_t hd2 = umad(H2[p], 65536u, hi16_dp(hprev2));
+#else
             const uint32_t hd2 = funnel16(hprev2, H2[p]);
+#endif
             hprev2 = H2[p];
             const uint32_t hp2 = addmax2(hd2, s2, E2[p]);
             const uint32_t g2 = addmax2_relu(hp2, noe_ins2, noe_ins2);
+#if CSBWA_ALN_VARIANT >= 3
+            const uint32_t a2 = addmax2((uint32_t)f, kk.ne_ins2, g2);         // low half: F(i, 2p+1)
+            const uint32_t f2 = umad(a2, 65536u, (uint32_t)f);                // {F entering 2p, F entering 2p+1}
+            const int fn = (int)hi16_dp(addmax2(f2, kk.ne_ins2, g2));         // high half: F(i, 2p+2)
+#else
             const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));
             const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));
             const uint32_t f2 = umad((uint32_t)t1, 65536u, (uint32_t)f);
+#endif
             h2 = max2(hp2, f2);
             E2[p] = addmax2(E2[p], ne_del2, addmax2_relu(h2, noe_del2, noe_del2));
             key2 = umax2(key2, umad(h2 & mk2[p], 256u, kc2[p]));
             H2[p] = h2;
             f = fn;
         }
+#if CSBWA_ALN_VARIANT >= 3
+        out.h = hi16_dp(h2);
+        out.ft = umad(t, 65536u, (uint32_t)f);
+#else
         out.h = h2 >> 16;
         out.ft = (uint32_t)f | (t << 16);
+#endif
         out.key2 = key2;
     }
 };

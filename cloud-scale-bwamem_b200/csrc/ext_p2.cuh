@@ -67,8 +67,10 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 struct P2K {
     int o_del, e_del, e_ins, oe_del, oe_ins, zdrop, ne_ins;
     uint32_t ne_del2, noe_del2, noe_ins2, ne_ins2;
+    uint32_t one;               // the value 1, unknown to the compiler (variant 4: x + c written as one * c + x stays an IMAD)
     CSW_HD void init(const SwOpt &o)
     {
+        one = opaque_one();
         o_del = o.o_del; e_del = o.e_del; e_ins = o.e_ins; zdrop = o.zdrop;
         oe_del = o.o_del + o.e_del; oe_ins = o.o_ins + o.e_ins;
         ne_ins = -e_ins;
@@ -87,8 +89,20 @@ struct P2K {
 // 3: as 1, the final shift through the dot-product unit (hi16_dp) -- no ALU instruction besides the two DPX.
 // Measured on B200, resident inputs, 262144 pairs (tools/sessions/r2_run40.sh): C2 1271 / 1304 / 1341 GCUPS and C1 808 / -- / 907
 // with variants 0 / 1 / 3; all bit-exact.  3 is the default.
+// 4: as 3, and the two pair counters behind the row-maximum / last-zero keys advance by IMAD (one * c + x, `one` a
+//    value the compiler cannot see through), the last-zero key is its own IMAD (h * 128 + 127 - pair) instead of an XOR
+//    of the maximum key: two more ALU-pipe instructions per pair become FMA-pipe instructions (hot loop of four pairs:
+//    ALU 52 -> 44, FMA 24 -> 37 instructions).  Measured slower (tools/sessions/r2_run41.sh: C2 1334 -> 1298, C1 910 -> 901
+//    GCUPS): the counters become a dependent IMAD chain and the FMA-side pipe now carries the IDP pair as well.  Not the default.
 #ifndef CSBWA_P2_VARIANT
 #define CSBWA_P2_VARIANT 3
+#endif
+#if CSBWA_P2_VARIANT >= 4
+#define P2_NEXT_PAIR(pp2, ipp2) { pp2 = umad(K.one, 0x00010001u, pp2); ipp2 = umad(K.one, 0xfffeffffu, ipp2); }
+#define P2_ZKEY(h2, kp2, ipp2) umad(h2, 128u, ipp2)
+#else
+#define P2_NEXT_PAIR(pp2, ipp2) { pp2 += 0x00010001u; }
+#define P2_ZKEY(h2, kp2, ipp2) ((kp2) ^ 0x007f007fu)
 #endif
 CSW_HD int p2_chain(int f, uint32_t g2, const P2K &K, uint32_t &f2)
 {
@@ -183,6 +197,8 @@ struct P2Run {
             int f = 0;
             const uint16_t *ps = sel + (size_t)pb * stride;
             uint32_t pp2 = (uint32_t)pb * 0x00010001u;
+            uint32_t ipp2 = 0x007f007fu - pp2;                         // 127 - pair in both halves (variant 4)
+            (void)ipp2;
             uint32_t h2 = 0;
             P2Pair cur = *ph;
             uint32_t sl = ld_u16(ps);
@@ -211,9 +227,9 @@ struct P2Run {
                 *ph = y;                                                                                   \
                 const uint32_t kp2 = umad(h2, 128u, pp2);                                                  \
                 key2 = umax2(key2, kp2 & keep);                                                            \
-                zk2 = umin2(zk2, (kp2 ^ 0x007f007fu) | (out));                                             \
+                zk2 = umin2(zk2, P2_ZKEY(h2, kp2, ipp2) | (out));                                          \
                 f = fn;                                                                                    \
-                pp2 += 0x00010001u;                                                                        \
+                P2_NEXT_PAIR(pp2, ipp2)                                                                    \
                 ph += stride; ps += stride;                                                                \
             }
             if (pb == pl) {
@@ -240,9 +256,9 @@ struct P2Run {
                     *ph = y;
                     const uint32_t kp2 = umad(h2, 128u, pp2);                  // h << 7 | pair, both lanes
                     key2 = umax2(key2, kp2);
-                    zk2 = umin2(zk2, kp2 ^ 0x007f007fu);
+                    zk2 = umin2(zk2, P2_ZKEY(h2, kp2, ipp2));
                     f = fn;
-                    pp2 += 0x00010001u;
+                    P2_NEXT_PAIR(pp2, ipp2)
                     ph += stride; ps += stride;
                 }
                 P2_EDGE_STEP(hi_out)

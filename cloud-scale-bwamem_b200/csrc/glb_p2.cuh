@@ -27,6 +27,15 @@
 
 namespace csw {
 
+// CSBWA_GLB_VARIANT: 0 = insertion chain as two scalar VIADDMNMX on the extracted halves of g2 plus two IMAD that pack
+// F entering / leaving each column; 3 = the chain stays packed (B = max(fin2 - e, g2) IS the pair of F values leaving
+// the two columns) and the 16-bit shifts run on the dot-product unit (ext_p2.cuh, variant 3): the ALU pipe is the one
+// the pair loop saturates.
+// Measured on B200 (tools/sessions/r2_run41.sh): 951.5 vs 960.4 GCUPS, bit-exact -- inside the run-to-run noise (the pair
+// loop's direction bits, not the chain, hold most of its ALU-pipe instructions); 0 stays the default.
+#ifndef CSBWA_GLB_VARIANT
+#define CSBWA_GLB_VARIANT 0
+#endif
 constexpr int GP2_BIAS = 16384;
 constexpr int GP2_MINF = 8192;            // biased representation of "minus infinity" (-8192)
 
@@ -95,6 +104,8 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
     const int ne_ins = -e_ins;
     const uint32_t ne_del2 = pk16(-e_del, -e_del);
     const uint32_t noe_del2 = pk16(-oe_del, -oe_del), noe_ins2 = pk16(-oe_ins, -oe_ins);
+    const uint32_t ne_ins2 = pk16(-e_ins, -e_ins);
+    (void)ne_ins2; (void)ne_ins;
     const uint32_t low2 = pk16(-100, -100);            // below every biased value: a no-op third operand
     const uint32_t one2 = 0x00010001u;
     uint16_t *h16 = (uint16_t *)he;
@@ -185,17 +196,28 @@ CSW_HD int sw_global_p2(const SwOpt &o, const uint8_t *q, int qlen, const uint8_
                         cur = ph[stride];
                         sl = ld_u16(ps + stride);
                         const uint32_t s2 = prmt(tlo, thi, sx);
+#if CSBWA_GLB_VARIANT >= 3
+                        const uint32_t hd2 = umad(x.h2, 65536u, hi16_dp(hprev2));
+#else
                         const uint32_t hd2 = funnel16(hprev2, x.h2);
+#endif
                         hprev2 = x.h2;
                         const uint32_t m2 = addmax2(hd2, s2, low2);                    // M = Hd + S
                         const uint32_t hm2 = max2(m2, x.e2);
                         const uint32_t tt2 = addmax2(m2, noe_del2, low2);              // M - oeDel
                         const uint32_t en2 = addmax2(x.e2, ne_del2, tt2);              // E' = max(E - eDel, M - oeDel)
                         const uint32_t g2 = addmax2(m2, noe_ins2, low2);               // M - oeIns
+#if CSBWA_GLB_VARIANT >= 3
+                        const uint32_t a2 = addmax2((uint32_t)f, ne_ins2, g2);         // low half: F(i, 2p+1)
+                        const uint32_t fin2 = umad(a2, 65536u, (uint32_t)f);           // F entering each column
+                        const uint32_t fout2 = addmax2(fin2, ne_ins2, g2);             // F leaving each column: {F(i, 2p+1), F(i, 2p+2)}
+                        const int fn = (int)hi16_dp(fout2);
+#else
                         const int t1 = addmax(f, ne_ins, (int)(g2 & 0xffffu));         // F(i, 2p+1)
                         const int fn = addmax(t1, ne_ins, (int)(g2 >> 16));            // F(i, 2p+2)
                         const uint32_t fin2 = umad((uint32_t)t1, 65536u, (uint32_t)f); // F entering each column
                         const uint32_t fout2 = umad((uint32_t)fn, 65536u, (uint32_t)t1);   // F leaving each column
+#endif
                         const uint32_t h2 = max2(hm2, fin2);
                         // direction bits: (a > b) == min(max(a, b) - b, 1), lane-wise on positive values
                         const uint32_t c1 = umin2(hm2 - m2, one2);                     // E > M

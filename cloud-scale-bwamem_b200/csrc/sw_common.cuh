@@ -140,6 +140,20 @@ CSW_HD uint32_t umad(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// The value 1 as something the compiler cannot see through (read from a device variable): x + c written as
+// one * c + x stays a multiply-add on the FMA-side pipe instead of becoming an add on the ALU pipe.
+#if defined(__CUDACC__)
+static __device__ unsigned int g_csw_one = 1u;
+#endif
+CSW_HD uint32_t opaque_one()
+{
+#if defined(__CUDA_ARCH__)
+    return *(volatile unsigned int *)&g_csw_one;
+#else
+    return 1u;
+#endif
+}
+
 // high 16-bit half of a word through the integer dot-product unit (IDP.2A: a.h0 * 0 + a.h1 * 1 + 0), i.e. a >> 16
 // issued on the FMA-side pipe instead of a SHF on the ALU pipe, which the DPX instructions saturate
 CSW_HD uint32_t hi16_dp(uint32_t a)
