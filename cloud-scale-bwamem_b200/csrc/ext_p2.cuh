@@ -64,13 +64,21 @@ CSW_HD void p2_stage_query(uint16_t *sel, int stride, const uint32_t *words, int
 // Row-invariant operands of P2Run::row, built once per side and passed by value: the options live in shared memory, the
 // row loop stores to shared memory, so operands derived from them inside row() are reloaded and rebuilt every row
 // (15 instructions per row in the SASS; the same trap as AlnStepK in aln_core.cuh).
+// pair-step variant (described at p2_chain below); 3 is the default
+#ifndef CSBWA_P2_VARIANT
+#define CSBWA_P2_VARIANT 3
+#endif
 struct P2K {
     int o_del, e_del, e_ins, oe_del, oe_ins, zdrop, ne_ins;
     uint32_t ne_del2, noe_del2, noe_ins2, ne_ins2;
     uint32_t one;               // the value 1, unknown to the compiler (variant 4: x + c written as one * c + x stays an IMAD)
     CSW_HD void init(const SwOpt &o)
     {
+#if CSBWA_P2_VARIANT >= 4
         one = opaque_one();
+#else
+        one = 1u;                  // unused below variant 4: no volatile load per side
+#endif
         o_del = o.o_del; e_del = o.e_del; e_ins = o.e_ins; zdrop = o.zdrop;
         oe_del = o.o_del + o.e_del; oe_ins = o.o_ins + o.e_ins;
         ne_ins = -e_ins;
@@ -94,9 +102,6 @@ struct P2K {
 //    of the maximum key: two more ALU-pipe instructions per pair become FMA-pipe instructions (hot loop of four pairs:
 //    ALU 52 -> 44, FMA 24 -> 37 instructions).  Measured slower (tools/sessions/r2_run41.sh: C2 1334 -> 1298, C1 910 -> 901
 //    GCUPS): the counters become a dependent IMAD chain and the FMA-side pipe now carries the IDP pair as well.  Not the default.
-#ifndef CSBWA_P2_VARIANT
-#define CSBWA_P2_VARIANT 3
-#endif
 #if CSBWA_P2_VARIANT >= 4
 #define P2_NEXT_PAIR(pp2, ipp2) { pp2 = umad(K.one, 0x00010001u, pp2); ipp2 = umad(K.one, 0xfffeffffu, ipp2); }
 #define P2_ZKEY(h2, kp2, ipp2) umad(h2, 128u, ipp2)
