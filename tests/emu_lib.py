@@ -12,17 +12,22 @@ SRC = os.path.join(HERE, "emu", "emu.cu")
 # CSBWA_EMU_FLAGS: extra compiler flags (e.g. -DCSBWA_P2_VARIANT=3 to run a kernel-core variant through the CPU parity
 # tests before it ever meets a GPU); such builds get their own file name
 EXTRA = os.environ.get("CSBWA_EMU_FLAGS", "").split()
-LIB = os.path.join(HERE, "emu", "libcsbwa_emu%s.so" % ("_" + "".join(c if c.isalnum() else "_" for c in "".join(EXTRA)) if EXTRA else ""))
+LIB = os.path.join(HERE, "emu", "libcsbwa_emu%s.so" % ("_" + "".join(c if c.isalnum() else "_" for c in "".join(EXTRA)) if EXTRA else ""))   # == _lib_path(EXTRA)
 CSRC = os.path.join(os.path.dirname(HERE), "cloud-scale-bwamem_b200", "csrc")
 
 JOB_DTYPE = np.dtype([("q_off", "<i8"), ("t_off", "<i8"), ("q_len", "<i4"), ("t_len", "<i4"),
                       ("xtra", "<i4"), ("pad", "<i4")])
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _lib_path(extra):
+    return os.path.join(HERE, "emu", "libcsbwa_emu%s.so" % ("_" + "".join(c if c.isalnum() else "_" for c in "".join(extra)) if extra else ""))
+
+
+def _stale(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -69,16 +74,19 @@ class Emu:
         return out, cells, nfast.value
 
 
-def load():
-    if _stale():
+def load(extra=None):
+    """extra: compiler flags of a kernel-core variant (e.g. ["-DCSBWA_P2_VARIANT=1"]); default: CSBWA_EMU_FLAGS / none."""
+    extra = EXTRA if extra is None else list(extra)
+    lib = _lib_path(extra)
+    if _stale(lib):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         if not os.path.exists(nvcc):
-            if os.path.exists(LIB):
-                return Emu(C.CDLL(LIB))
+            if os.path.exists(lib):
+                return Emu(C.CDLL(lib))
             raise RuntimeError("nvcc missing and emu library not built")
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                               "-Xcompiler", "-fPIC", "-shared"] + EXTRA + ["-o", LIB, SRC])
-    return Emu(C.CDLL(LIB))
+                               "-Xcompiler", "-fPIC", "-shared"] + extra + ["-o", lib, SRC])
+    return Emu(C.CDLL(lib))
 
 
 class EmuCoalescer:

@@ -134,3 +134,38 @@ def test_aln_workload_sample(pkg, oracle, emu):
         assert nfast == len(jobs)
         assert (ref[:, 0] > 100).mean() > 0.9     # the mate is really found in its window
         assert (ref[:, 6] >= 0).mean() > 0.9
+
+
+def test_kernel_core_variants_stay_bit_exact(pkg, oracle):
+    """The pair-step variants that are NOT the default (kept for A/B runs: CSBWA_P2_VARIANT 0 / 1 / 4, CSBWA_ALN_VARIANT 0,
+    CSBWA_GLB_VARIANT 3) compiled into the emulation library and run against the oracle: a variant that rots is found
+    here, not on a GPU."""
+    import pytest
+    from tests import emu_lib
+    rng = np.random.default_rng(26)
+    tuples = util.adversarial_ext_tasks(rng)
+    for L in (101, 151, 250):
+        tuples += [util.rand_ext_task(rng, L=L) for _ in range(120)]
+    wire = pkg.jni.packTasks(util.make_ext_params(pkg, tuples))
+    ref, rcells, _ = oracle.extend_wire(wire)
+    pairs = [util.rand_aln_job(rng) for _ in range(60)]
+    xt = [pkg.jni.mateXtra(len(q)) for q, _ in pairs]
+    jobs, seqs = util.build_jobs(pairs, xt, emu_dtype())
+    aref, acells = oracle.align2_batch(jobs, seqs)
+    try:
+        variants = [emu_lib.load(f) for f in (["-DCSBWA_P2_VARIANT=0", "-DCSBWA_ALN_VARIANT=0"], ["-DCSBWA_P2_VARIANT=1"],
+                                              ["-DCSBWA_P2_VARIANT=4", "-DCSBWA_GLB_VARIANT=3"])]
+    except RuntimeError as e:
+        pytest.skip(str(e))
+    for emu in variants:
+        got, cells, _ = emu.extend_wire_p2(wire)
+        assert np.array_equal(got, ref) and np.array_equal(cells, rcells)
+        agot, ac, _ = emu.align2_batch(jobs, seqs)
+        assert np.array_equal(agot, aref) and np.array_equal(ac, acells)
+    # SWGlobal variant 3 against the oracle
+    from tests.test_global import build_gjobs, rand_global_job
+    grng = np.random.default_rng(27)
+    gj, gs = build_gjobs([rand_global_job(grng, pkg) for _ in range(200)], oracle.GJOB_DTYPE)
+    want, wcig, wcells = oracle.global_batch(gj, gs)
+    res, cig, cells, n_p2, _ = emu_lib.emu_global_batch(variants[2], gj, gs, want_count=True)
+    assert np.array_equal(res, want) and np.array_equal(cig, wcig) and np.array_equal(cells, wcells) and n_p2 >= 150
