@@ -69,6 +69,19 @@ def main():
     if c2:
         out.append("| next row: round-flattened chain -> alignment driver | 1 | – | – | %.1f M reads/s | – | %.0f k reads/s (oracle, 1 core) | regions identical |" % (
             c2["reads_per_s"] / 1e6, c2["oracle_single_core_reads_per_s"] / 1e3))
+    # A/B runs of the last session (pair steps with fewer ALU-pipe instructions), one box each, reduced shards
+    ab = (load("r2_p2_variants_ab.jsonl") or [])
+    by = {(r["run"].split("_v")[0], r["variant"]): r["gcups"] for r in ab}
+    for wl in ("C2", "C1"):
+        if (wl, 0) in by and (wl, 3) in by:
+            out.append("| A/B, extension %s, 262144 pairs resident: pair step before / after the ALU-pipe relief (the rows above predate it) | 1 | %s -> **%s** | – | – | – | – | bit-exact (all kernel paths) |" % (
+                wl, f0(by[(wl, 0)]), f0(by[(wl, 3)])))
+    ab2 = (load("r2_alu_relief_ab.jsonl") or [])
+    ms2 = {(r["workload"][:2], "exp" in r["build"]): r["gcups"] for r in ab2 if r["kernel"] == "mate-SW"}
+    for wl in ("C3", "C1"):
+        if (wl, False) in ms2 and (wl, True) in ms2:
+            out.append("| A/B, mate-SW %s windows, 8192 pairs resident: systolic step before / after the ALU-pipe relief (the rows above predate it) | 1 | %s -> **%s** | – / %.2f | – | – | – | bit-exact (7 fields) |" % (
+                wl, f0(ms2[(wl, False)]), f0(ms2[(wl, True)]), [r["roofline_frac_alu"] for r in ab2 if r["kernel"] == "mate-SW" and r["workload"][:2] == wl and "exp" in r["build"]][0]))
     table = "\n".join(out)
     p = os.path.join(ROOT, "BASELINE.md")
     s = open(p).read()
